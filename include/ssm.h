@@ -1,0 +1,165 @@
+/*
+ * ssm.h -- C ABI of libssm.so: the B200-native (sm_100a) dense stereo-to-semantic-map path.
+ *
+ * Drop-in boundary for the reference's two entry points on this path:
+ *   calDisparity_SGBM(img_L, img_R, disp)      /root/reference include/stereo.h:15, src/stereo.cpp:11-38
+ *   rgbd_tutor::Mapper (generatePointCloud,    /root/reference include/mapper.h:15-70,
+ *     semantic_motion_fuse, viewer's VoxelGrid   src/mapper.cpp:12-94,96-178,189-216
+ *     fusion)
+ * plus the glue between them (FrameReader::next disparity->depth, src/rgbdframe.cpp:85-116, and
+ * RGBDFrame::project2dTo3d, include/rgbdframe.h:63-75).
+ *
+ * Conventions: extern "C"; plain pointers and sizes; every call returns an ssm_status (0 = ok,
+ * <0 = error, message via ssm_last_error); no exceptions cross the boundary; no OpenCV / PCL /
+ * Eigen / torch types.  "host" entry points take host pointers and block; "device" entry points
+ * take device pointers on the ctx's GPU and are asynchronous on the given cudaStream_t (passed
+ * as void*; NULL = the ctx's own stream).  One ssm_ctx per GPU; calls on a ctx are serialised
+ * by the caller (the reference runs SGBM on its main thread and mapping on the viewer thread:
+ * use two contexts or a lock).  There is no CPU fallback: ssm_create fails when no sm_100
+ * device is present.
+ *
+ * Image layouts match cv::Mat: row-major, `stride` in BYTES between rows; 8UC3 is interleaved BGR.
+ */
+#ifndef SSM_H
+#define SSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSM_MAX_LABELS 32
+#define SSM_LABEL_UNKNOWN 255
+
+typedef enum {
+    SSM_OK = 0,
+    SSM_ERR_INVALID_ARGUMENT = -1, /* bad shape / parameter (the reference would throw cv::Exception) */
+    SSM_ERR_CUDA = -2,             /* CUDA runtime error; text in ssm_last_error */
+    SSM_ERR_NO_DEVICE = -3,        /* no sm_100 GPU: there is no CPU fallback */
+    SSM_ERR_CAPACITY = -4,         /* frame larger than ctx limits, or voxel hash table full */
+    SSM_ERR_COMM = -5,             /* NCCL error / communicator not initialised */
+    SSM_ERR_UNSUPPORTED = -6       /* parameter combination outside the 16-bit cost range */
+} ssm_status;
+
+/* All tunables of the path in one POD (SURVEY.md section 5 "Config / flags"). */
+typedef struct ssm_params {
+    /* cv::StereoSGBM fields as set by src/stereo.cpp:16-28 */
+    int min_disparity;       /* 0 (only 0 is supported) */
+    int num_disparities;     /* 80 in the reference; 128 / 256 in BASELINE.json configs; multiple of 16 */
+    int block_size;          /* SADWindowSize = 11 */
+    int p1, p2;              /* 4*11*11, 32*11*11 */
+    int disp12_max_diff;     /* 1 */
+    int pre_filter_cap;      /* 63 */
+    int uniqueness_ratio;    /* 10 */
+    int speckle_window_size; /* 100 */
+    int speckle_range;       /* 32 */
+    /* camera: parameters.txt:37-41,50-54,63 (read at src/rgbdframe.cpp:87-94) */
+    double cx, cy, fx, fy, baseline, scale;
+    double roix, roiy, roiz;
+    /* mapper: parameters.txt:97-98 (include/mapper.h:24-25) */
+    double resolution;   /* voxel leaf, metres */
+    double max_distance; /* metres */
+    /* labels: class id -> semantic BGR colour (src/mapper.cpp:42-54) */
+    int num_labels;
+    uint8_t palette_bgr[SSM_MAX_LABELS][3];
+    uint32_t drop_mask;      /* bit l set: class l is removed from the cloud (mapper.cpp:41-55) */
+    uint32_t dynamic_mask;   /* bit l set: class l seeds the dilated moving mask (mapper.cpp:206-208) */
+    int dilate_iterations;   /* mapper.cpp:214 */
+    int colour_source;       /* 0: left rgb image (mapper.cpp:72-84); 1: semantic colour (mapper.cpp~:60) */
+    /* capacities (allocation limits of the context) */
+    int max_width, max_height, max_batch;
+    uint64_t map_capacity;   /* voxel hash slots (rounded up to a power of two) */
+} ssm_params;
+
+typedef struct ssm_ctx ssm_ctx;
+
+/* One fused voxel, as exported.  xyz = centroid, rgba = 0x00RRGGBB of the truncated mean colour
+ * (pcl::VoxelGrid semantics), label = majority vote (ties -> lowest id). */
+typedef struct ssm_voxel_export {
+    int32_t* ijk;     /* [n][3] voxel coordinates floor(coord / leaf) */
+    float* xyz;       /* [n][3] */
+    uint32_t* rgba;   /* [n]    */
+    uint8_t* label;   /* [n]    */
+    uint32_t* count;  /* [n]    */
+    uint32_t* votes;  /* [n][num_labels] */
+} ssm_voxel_export;   /* any member may be NULL */
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+void ssm_default_params(ssm_params* p); /* reference defaults (stereo.cpp:16-28, parameters.txt) */
+int ssm_create(const ssm_params* p, int device, ssm_ctx** out);
+void ssm_destroy(ssm_ctx* ctx);
+const char* ssm_last_error(void);
+const char* ssm_version(void);
+/* number of kernels this library launched on the ctx since creation (for bench.py gpu_launches) */
+uint64_t ssm_kernel_launches(const ssm_ctx* ctx);
+/* per-stage device time of the most recent *_host / pipeline call, ms (stage ids below) */
+enum { SSM_STAGE_COST = 0, SSM_STAGE_AGGREGATE = 1, SSM_STAGE_SELECT = 2, SSM_STAGE_POST = 3,
+       SSM_STAGE_POINTS = 4, SSM_STAGE_FUSE = 5, SSM_STAGE_COUNT = 6 };
+int ssm_set_stage_timing(ssm_ctx* ctx, int enabled);
+int ssm_stage_time_ms(ssm_ctx* ctx, int stage, float* ms);
+
+/* ---- stereo.h: calDisparity_SGBM -------------------------------------------------------------- */
+/* Host, blocking.  left/right 8UC1 w x h; disp 16SC1 w x h (disparity x16, invalid = -16). */
+int ssm_sgbm(ssm_ctx* ctx, const uint8_t* left, const uint8_t* right, int w, int h, size_t stride,
+             int16_t* disp, size_t disp_stride);
+/* Device, async.  Densely packed [batch][h][w] buffers. */
+int ssm_sgbm_batch_device(ssm_ctx* ctx, int batch, const uint8_t* d_left, const uint8_t* d_right, int w, int h,
+                          int16_t* d_disp, void* stream);
+/* Debug/parity taps (device buffers, valid after ssm_sgbm*, batch item 0..): matching cost C and
+ * aggregated cost S, both [batch][h][w-D][D] int16; raw WTA disparity before median/speckle. */
+int ssm_debug_copy_volume(ssm_ctx* ctx, int which /*0=C,1=S,2=disp_raw,3=disp_median*/, int batch_index,
+                          void* host_dst, size_t bytes);
+
+/* ---- FrameReader::next glue: disparity -> depth (rgbdframe.cpp:85-116) ----------------------- */
+int ssm_disparity_to_depth(ssm_ctx* ctx, const int16_t* disp, int w, int h, size_t disp_stride,
+                           uint16_t* depth, size_t depth_stride);
+
+/* ---- mapper.h ----------------------------------------------------------------------------------- */
+/* Mapper::semantic_motion_fuse: semantic 8UC3 BGR -> moving mask 8UC1 (255 = moving). */
+int ssm_semantic_motion_fuse(ssm_ctx* ctx, const uint8_t* semantic_bgr, int w, int h, size_t stride,
+                             uint8_t* mask, size_t mask_stride);
+/* Mapper::generatePointCloud: depth 16UC1 + semantic/rgb 8UC3 + pose (row-major 4x4 double,
+ * camera->world = frame->T_f_w) -> row-major-ordered cloud.  Outputs hold up to max_points; the
+ * number produced is returned in *n_points.  xyz [n][3] fp32 world frame; rgba 0x00RRGGBB; label id. */
+int ssm_generate_point_cloud(ssm_ctx* ctx, const uint16_t* depth, const uint8_t* semantic_bgr,
+                             const uint8_t* rgb_bgr, int w, int h, const double* T_f_w,
+                             float* xyz, uint32_t* rgba, uint8_t* label, int max_points, int* n_points);
+/* Mapper::viewer accumulate + VoxelGrid: fuse one frame (host buffers) into the global map. */
+int ssm_map_integrate_frame(ssm_ctx* ctx, const uint16_t* depth, const uint8_t* semantic_bgr,
+                            const uint8_t* rgb_bgr, int w, int h, const double* T_f_w);
+/* fuse an explicit cloud (e.g. one returned by ssm_generate_point_cloud) */
+int ssm_map_integrate_points(ssm_ctx* ctx, const float* xyz, const uint32_t* rgba, const uint8_t* label, int n);
+int ssm_map_clear(ssm_ctx* ctx);                      /* globalMap->clear(), mapper.cpp:125 */
+int ssm_map_size(ssm_ctx* ctx, uint64_t* n_voxels);   /* "points in global map", mapper.cpp:161 */
+/* Export up to max_voxels voxels of THIS rank's table; sorted != 0 orders them by (k,j,i)
+ * (pcl::VoxelGrid output order).  *n_out receives the number written. */
+int ssm_map_export(ssm_ctx* ctx, const ssm_voxel_export* out, uint64_t max_voxels, int sorted, uint64_t* n_out);
+/* Write the fused map as a binary PCD with fields x y z rgba (pcl::PCDWriter, mapper.cpp:165-170). */
+int ssm_map_save_pcd(ssm_ctx* ctx, const char* path);
+
+/* ---- the whole path, batched (north_star: stereo pair + labels + pose -> map) ----------------- */
+/* Device-resident inputs: [batch][h][w] u8 left/right, [batch][h][w][3] u8 semantic/rgb BGR,
+ * [batch][16] double poses.  d_disp_out (optional, may be NULL) receives [batch][h][w] int16. */
+int ssm_pipeline_batch_device(ssm_ctx* ctx, int batch, const uint8_t* d_left, const uint8_t* d_right,
+                              const uint8_t* d_semantic, const uint8_t* d_rgb, const double* d_poses,
+                              int w, int h, int16_t* d_disp_out, void* stream);
+/* Same through host buffers (pinned or pageable): H2D copies, the path, and a D2H of the map size. */
+int ssm_pipeline_batch_host(ssm_ctx* ctx, int batch, const uint8_t* left, const uint8_t* right,
+                            const uint8_t* semantic, const uint8_t* rgb, const double* poses,
+                            int w, int h, int16_t* disp_out /* may be NULL */, uint64_t* n_voxels_out);
+int ssm_synchronize(ssm_ctx* ctx);
+
+/* ---- multi-GPU: spatially owned voxel hash, NCCL all-to-all point routing ---------------------- */
+#define SSM_UNIQUE_ID_BYTES 128
+int ssm_comm_get_unique_id(uint8_t id[SSM_UNIQUE_ID_BYTES]);               /* rank 0, then broadcast by the host */
+int ssm_comm_init(ssm_ctx* ctx, const uint8_t id[SSM_UNIQUE_ID_BYTES], int rank, int nranks);
+int ssm_comm_destroy(ssm_ctx* ctx);
+/* owner rank of a voxel (pure function of ijk, brick shift and nranks; exposed for host-side tests) */
+int ssm_voxel_owner(int32_t i, int32_t j, int32_t k, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSM_H */

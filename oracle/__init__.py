@@ -1,0 +1,284 @@
+"""ctypes loader for the CPU oracle (oracle/ssm_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of bench.py -- never from the product package
+``semantic_slam_mapping_b200`` (tests/test_boundary.py greps for that).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libssm_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/ssm_oracle.c with gcc (a few seconds)."""
+    src = os.path.join(_HERE, "ssm_oracle.c")
+    hdr = os.path.join(_HERE, "ssm_oracle.h")
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in (src, hdr)
+    )
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libssm_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+class _SgbmParams(C.Structure):
+    _fields_ = [
+        ("num_disparities", C.c_int),
+        ("block_size", C.c_int),
+        ("p1", C.c_int),
+        ("p2", C.c_int),
+        ("disp12_max_diff", C.c_int),
+        ("pre_filter_cap", C.c_int),
+        ("uniqueness_ratio", C.c_int),
+        ("speckle_window_size", C.c_int),
+        ("speckle_range", C.c_int),
+        ("legacy_p2_form", C.c_int),
+    ]
+
+
+class _MapParams(C.Structure):
+    _fields_ = [
+        ("cx", C.c_double),
+        ("cy", C.c_double),
+        ("fx", C.c_double),
+        ("fy", C.c_double),
+        ("baseline", C.c_double),
+        ("scale", C.c_double),
+        ("roix", C.c_double),
+        ("roiy", C.c_double),
+        ("roiz", C.c_double),
+        ("max_distance", C.c_double),
+        ("num_labels", C.c_int),
+        ("palette_bgr", (C.c_uint8 * 3) * 32),
+        ("drop_mask", C.c_uint32),
+        ("dynamic_mask", C.c_uint32),
+        ("dilate_iterations", C.c_int),
+        ("colour_source", C.c_int),
+    ]
+
+
+@dataclass
+class SgbmParams:
+    """Defaults = src/stereo.cpp:16-28 of the reference."""
+
+    num_disparities: int = 80
+    block_size: int = 11
+    p1: int = 4 * 11 * 11
+    p2: int = 32 * 11 * 11
+    disp12_max_diff: int = 1
+    pre_filter_cap: int = 63
+    uniqueness_ratio: int = 10
+    speckle_window_size: int = 100
+    speckle_range: int = 32
+    legacy_p2_form: int = 0
+
+    def c(self) -> _SgbmParams:
+        return _SgbmParams(
+            self.num_disparities, self.block_size, self.p1, self.p2, self.disp12_max_diff, self.pre_filter_cap,
+            self.uniqueness_ratio, self.speckle_window_size, self.speckle_range, self.legacy_p2_form,
+        )
+
+
+# 12-class SegNet palette, BGR (src/mapper.cpp:42-54,206-208)
+SEGNET12_BGR = [
+    (128, 128, 128),  # 0 sky
+    (0, 0, 128),      # 1 building
+    (128, 192, 192),  # 2 pole
+    (0, 69, 255),     # 3 road marking
+    (128, 64, 128),   # 4 road
+    (222, 40, 60),    # 5 pavement
+    (0, 128, 128),    # 6 tree
+    (128, 128, 192),  # 7 sign symbol
+    (128, 64, 64),    # 8 fence
+    (128, 0, 64),     # 9 car
+    (0, 64, 64),      # 10 pedestrian
+    (192, 128, 0),    # 11 cyclist
+]
+
+
+@dataclass
+class MapParams:
+    """Defaults = parameters.txt:37-41,50-54,63,97-98 and the shipped mapper.cpp class sets."""
+
+    cx: float = 607.1928
+    cy: float = 185.2157
+    fx: float = 718.8560
+    fy: float = 718.8560
+    baseline: float = 0.532331858
+    scale: float = 1000.0
+    roix: float = 20.0
+    roiy: float = 5.0
+    roiz: float = 40.0
+    max_distance: float = 40.0
+    palette_bgr: list = field(default_factory=lambda: list(SEGNET12_BGR))
+    drop_mask: int = (1 << 0) | (1 << 2) | (1 << 11)   # sky, pole, cyclist  (mapper.cpp:41-55)
+    dynamic_mask: int = (1 << 10) | (1 << 11)          # pedestrian, cyclist (mapper.cpp:206-208)
+    dilate_iterations: int = 2
+    colour_source: int = 0
+
+    def c(self) -> _MapParams:
+        m = _MapParams()
+        for k in ("cx", "cy", "fx", "fy", "baseline", "scale", "roix", "roiy", "roiz", "max_distance"):
+            setattr(m, k, float(getattr(self, k)))
+        m.num_labels = len(self.palette_bgr)
+        for i, (b, g, r) in enumerate(self.palette_bgr):
+            m.palette_bgr[i][0], m.palette_bgr[i][1], m.palette_bgr[i][2] = b, g, r
+        m.drop_mask = self.drop_mask
+        m.dynamic_mask = self.dynamic_mask
+        m.dilate_iterations = self.dilate_iterations
+        m.colour_source = self.colour_source
+        return m
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        vp = C.c_void_p
+        L.oracle_sgbm.restype = C.c_int
+        L.oracle_sgbm.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, C.POINTER(_SgbmParams), vp, C.c_size_t, vp, vp, vp, vp]
+        L.oracle_median3x3_s16.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.oracle_filter_speckles.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oracle_disparity_to_depth.argtypes = [vp, C.c_int, C.c_int, C.POINTER(_MapParams), vp]
+        L.oracle_moving_mask.argtypes = [vp, C.c_int, C.c_int, C.POINTER(_MapParams), vp]
+        L.oracle_generate_point_cloud.restype = C.c_int
+        L.oracle_generate_point_cloud.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.POINTER(_MapParams), vp, vp, vp, vp, vp, vp]
+        L.oracle_map_create.restype = vp
+        L.oracle_map_create.argtypes = [C.c_double, C.c_int]
+        L.oracle_map_destroy.argtypes = [vp]
+        L.oracle_map_clear.argtypes = [vp]
+        L.oracle_map_insert.argtypes = [vp, vp, vp, vp, C.c_int]
+        L.oracle_map_size.restype = C.c_int64
+        L.oracle_map_size.argtypes = [vp]
+        L.oracle_map_export.restype = C.c_int64
+        L.oracle_map_export.argtypes = [vp] * 8
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def sgbm(left: np.ndarray, right: np.ndarray, params: SgbmParams, want_volumes: bool = False):
+    """calDisparity_SGBM (src/stereo.cpp:11-38).  Returns disp int16 [H][W] (x16, invalid -16);
+    with want_volumes also a dict of C, S, disp_raw (pre-median), disp_median (pre-speckle)."""
+    left = np.ascontiguousarray(left, dtype=np.uint8)
+    right = np.ascontiguousarray(right, dtype=np.uint8)
+    H, W = left.shape
+    D = params.num_disparities
+    disp = np.empty((H, W), np.int16)
+    vols = {}
+    Cv = Sv = raw = med = None
+    if want_volumes:
+        Cv = np.empty((H, W - D, D), np.int16)
+        Sv = np.empty((H, W - D, D), np.int16)
+        raw = np.empty((H, W), np.int16)
+        med = np.empty((H, W), np.int16)
+        vols = {"C": Cv, "S": Sv, "disp_raw": raw, "disp_median": med}
+    cp = params.c()
+    rc = lib().oracle_sgbm(_p(left), _p(right), W, H, W, C.byref(cp), _p(disp), W, _p(Cv), _p(Sv), _p(raw), _p(med))
+    if rc != 0:
+        raise ValueError(f"oracle_sgbm rejected the arguments (rc={rc})")
+    return (disp, vols) if want_volumes else disp
+
+
+def median3x3(img: np.ndarray) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.int16)
+    out = np.empty_like(img)
+    lib().oracle_median3x3_s16(_p(img), _p(out), img.shape[1], img.shape[0])
+    return out
+
+
+def filter_speckles(img: np.ndarray, new_val: int, max_size: int, max_diff: int) -> np.ndarray:
+    out = np.ascontiguousarray(img, np.int16).copy()
+    lib().oracle_filter_speckles(_p(out), out.shape[1], out.shape[0], new_val, max_size, max_diff)
+    return out
+
+
+def disparity_to_depth(disp: np.ndarray, mp: MapParams) -> np.ndarray:
+    disp = np.ascontiguousarray(disp, np.int16)
+    depth = np.empty(disp.shape, np.uint16)
+    cp = mp.c()
+    lib().oracle_disparity_to_depth(_p(disp), disp.shape[1], disp.shape[0], C.byref(cp), _p(depth))
+    return depth
+
+
+def moving_mask(semantic_bgr: np.ndarray, mp: MapParams) -> np.ndarray:
+    sem = np.ascontiguousarray(semantic_bgr, np.uint8)
+    H, W = sem.shape[:2]
+    out = np.empty((H, W), np.uint8)
+    cp = mp.c()
+    lib().oracle_moving_mask(_p(sem), W, H, C.byref(cp), _p(out))
+    return out
+
+
+def generate_point_cloud(depth, semantic_bgr, rgb_bgr, mp: MapParams, T):
+    """Mapper::generatePointCloud (src/mapper.cpp:12-94).  Returns dict of row-major-ordered arrays."""
+    depth = np.ascontiguousarray(depth, np.uint16)
+    sem = np.ascontiguousarray(semantic_bgr, np.uint8)
+    rgb = np.ascontiguousarray(rgb_bgr, np.uint8)
+    T = np.ascontiguousarray(T, np.float64).reshape(16)
+    H, W = depth.shape
+    n = H * W
+    xyz = np.empty((n, 3), np.float32)
+    cam = np.empty((n, 3), np.float32)
+    rgba = np.empty(n, np.uint32)
+    lab = np.empty(n, np.uint8)
+    pix = np.empty(n, np.int32)
+    cp = mp.c()
+    k = lib().oracle_generate_point_cloud(_p(depth), _p(sem), _p(rgb), W, H, C.byref(cp), _p(T), _p(xyz), _p(cam), _p(rgba), _p(lab), _p(pix))
+    return {"xyz": xyz[:k].copy(), "xyz_cam": cam[:k].copy(), "rgba": rgba[:k].copy(), "label": lab[:k].copy(), "pix": pix[:k].copy()}
+
+
+class VoxelMap:
+    """pcl::VoxelGrid<PointXYZRGBA> over the union of inserted clouds + per-voxel label votes."""
+
+    def __init__(self, leaf: float, num_labels: int):
+        self.num_labels = num_labels
+        self._h = lib().oracle_map_create(float(leaf), num_labels)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_map_destroy(self._h)
+            self._h = None
+
+    def clear(self):
+        lib().oracle_map_clear(self._h)
+
+    def insert(self, xyz, rgba, label):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        rgba = np.ascontiguousarray(rgba, np.uint32)
+        label = np.ascontiguousarray(label, np.uint8)
+        lib().oracle_map_insert(self._h, _p(xyz), _p(rgba), _p(label), xyz.shape[0])
+
+    def __len__(self):
+        return int(lib().oracle_map_size(self._h))
+
+    def export(self):
+        n = len(self)
+        L = self.num_labels
+        out = {
+            "ijk": np.empty((n, 3), np.int32),
+            "centroid": np.empty((n, 3), np.float32),
+            "centroid_d": np.empty((n, 3), np.float64),
+            "rgba": np.empty(n, np.uint32),
+            "count": np.empty(n, np.uint32),
+            "votes": np.empty((n, L), np.uint32),
+            "label": np.empty(n, np.uint8),
+        }
+        lib().oracle_map_export(self._h, _p(out["ijk"]), _p(out["centroid"]), _p(out["centroid_d"]), _p(out["rgba"]),
+                                _p(out["count"]), _p(out["votes"]), _p(out["label"]))
+        return out
