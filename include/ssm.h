@@ -9,8 +9,8 @@
  * plus the glue between them (FrameReader::next disparity->depth, src/rgbdframe.cpp:85-116, and
  * RGBDFrame::project2dTo3d, include/rgbdframe.h:63-75).
  *
- * Conventions: extern "C"; plain pointers and sizes; every call returns an ssm_status (0 = ok,
- * <0 = error, message via ssm_last_error); no exceptions cross the boundary; no OpenCV / PCL /
+ * Conventions: extern "C"; plain pointers and sizes; every call returns an ssm_status code: 0 = ok,
+ * <0 = error with the message in ssm_last_error; no exceptions cross the boundary; no OpenCV / PCL /
  * Eigen / torch types.  "host" entry points take host pointers and block; "device" entry points
  * take device pointers on the ctx's GPU and are asynchronous on the given cudaStream_t (passed
  * as void*; NULL = the ctx's own stream).  One ssm_ctx per GPU; calls on a ctx are serialised
@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SSM_MAX_LABELS 32
+#define SSM_MAX_LABELS 20 /* 12 (SegNet) and 19 (Cityscapes) fit one 128-byte voxel record */
 #define SSM_LABEL_UNKNOWN 255
 
 typedef enum {

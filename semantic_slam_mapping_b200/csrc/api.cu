@@ -1,0 +1,583 @@
+// api.cu -- the C ABI of include/ssm.h: context, buffers, host/device entry points, the batched path.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "ssm_internal.cuh"
+
+namespace ssm {
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+int cuda_fail(cudaError_t e, const char* what)
+{
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what;
+    return SSM_ERR_CUDA;
+}
+
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+static int validate(const ssm_params& p)
+{
+    if (p.min_disparity != 0) return fail(SSM_ERR_UNSUPPORTED, "min_disparity must be 0 (src/stereo.cpp:19)");
+    if (p.num_disparities < 16 || p.num_disparities % 16 != 0 || p.num_disparities > 512)
+        return fail(SSM_ERR_INVALID_ARGUMENT, "num_disparities must be a multiple of 16 in [16, 512]");
+    if (p.block_size < 1 || p.block_size % 2 == 0) return fail(SSM_ERR_INVALID_ARGUMENT, "block_size must be odd and >= 1");
+    if (p.block_size > 11) return fail(SSM_ERR_UNSUPPORTED, "block_size > 11 is outside the 16-bit cost range");
+    const int P1 = p.p1 > 0 ? p.p1 : 2, P2 = std::max(p.p2 > 0 ? p.p2 : 5, P1 + 1);
+    if (189 * p.block_size * p.block_size + P2 > 32767 || P1 > 8000)
+        return fail(SSM_ERR_UNSUPPORTED, "189*block_size^2 + P2 must stay <= 32767 (16-bit path costs)");
+    if (p.max_width <= p.num_disparities || p.max_width > 65535 || p.max_height < 1 || p.max_batch < 1)
+        return fail(SSM_ERR_INVALID_ARGUMENT, "max_width must exceed num_disparities (and be <= 65535); max_height, max_batch >= 1");
+    if (p.num_labels < 1 || p.num_labels > SSM_MAX_LABELS) return fail(SSM_ERR_INVALID_ARGUMENT, "num_labels must be in [1, 20]");
+    if (!(p.resolution > 0) || !(p.scale > 0) || !(p.fx != 0) || !(p.fy != 0))
+        return fail(SSM_ERR_INVALID_ARGUMENT, "resolution, scale, fx, fy must be non-zero/positive");
+    if (p.dilate_iterations < 0 || p.dilate_iterations > 8) return fail(SSM_ERR_INVALID_ARGUMENT, "dilate_iterations in [0, 8]");
+    if (p.map_capacity < 1024) return fail(SSM_ERR_INVALID_ARGUMENT, "map_capacity must be >= 1024 slots");
+    return SSM_OK;
+}
+
+static void fill_dev_params(ssm_ctx* c, int w, int h)
+{
+    const ssm_params& p = c->p;
+    DevParams& d = c->dp;
+    d.W = w; d.H = h; d.D = p.num_disparities; d.W1 = w - p.num_disparities;
+    d.bs = p.block_size;
+    d.P1 = p.p1 > 0 ? p.p1 : 2;
+    d.P2 = std::max(p.p2 > 0 ? p.p2 : 5, d.P1 + 1);
+    d.uniq = p.uniqueness_ratio >= 0 ? p.uniqueness_ratio : 10;
+    d.d12 = p.disp12_max_diff > 0 ? p.disp12_max_diff : 1;
+    d.ftzero = std::max(p.pre_filter_cap, 15) | 1;
+    d.speckle_win = p.speckle_window_size;
+    d.speckle_diff = kDispScale * p.speckle_range;
+    d.cx = p.cx; d.cy = p.cy; d.fx = p.fx; d.fy = p.fy; d.baseline = p.baseline; d.scale = p.scale;
+    d.roix = p.roix; d.roiy = p.roiy; d.roiz = p.roiz;
+    d.max_depth_units = p.max_distance * p.scale;          // mapper.cpp:30
+    d.inv_leaf = 1.0f / (float)p.resolution;               // VoxelGrid::setLeafSize -> inverse_leaf_size_ (fp32)
+    d.num_labels = p.num_labels;
+    for (int i = 0; i < SSM_MAX_LABELS; ++i)
+        d.palette[i] = i < p.num_labels ? ((uint32_t)p.palette_bgr[i][0] | ((uint32_t)p.palette_bgr[i][1] << 8) |
+                                           ((uint32_t)p.palette_bgr[i][2] << 16))
+                                        : 0xffffffffu;
+    d.drop_mask = p.drop_mask; d.dynamic_mask = p.dynamic_mask;
+    d.dilate_radius = p.dilate_iterations; d.colour_source = p.colour_source;
+}
+
+static int set_shape(ssm_ctx* c, int w, int h, int batch)
+{
+    if (w <= c->p.num_disparities) return fail(SSM_ERR_INVALID_ARGUMENT, "image width must exceed num_disparities");
+    if (w > c->cap_w || h > c->cap_h || h < 1 || (size_t)w * h > (size_t)c->cap_w * c->cap_h)
+        return fail(SSM_ERR_CAPACITY, "frame larger than the context's max_width x max_height");
+    if (batch < 1 || batch > c->cap_b) return fail(SSM_ERR_CAPACITY, "batch larger than the context's max_batch");
+    if (c->dp.W != w || c->dp.H != h) fill_dev_params(c, w, h);
+    return SSM_OK;
+}
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)); }
+
+static void free_all(ssm_ctx* c)
+{
+    void* ptrs[] = {c->d_left, c->d_right, c->d_recL, c->d_recR, c->d_C, c->d_S, c->d_disp_raw, c->d_disp_lr, c->d_disp_med,
+                    c->d_disp, c->d_disp2key, c->d_cc_label, c->d_cc_size, c->d_depth, c->d_label, c->d_mask, c->d_sem,
+                    c->d_rgb, c->d_pose, c->d_min_disp, c->d_points, c->d_blk_count, c->d_counters, c->d_table, c->d_send,
+                    c->d_recv, c->d_send_counts};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+}
+
+// stage timing helpers
+static inline void mark(ssm_ctx* c, int i, cudaStream_t s)
+{
+    if (c->timing) cudaEventRecord(c->ev[i], s);
+}
+
+// the stereo half on device buffers: prefilter -> cost volume -> 5-path aggregation -> selection -> post-filters
+static int run_sgbm(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, int16_t* d_out, cudaStream_t s)
+{
+    int rc;
+    mark(c, 0, s);
+    if ((rc = launch_prefilter(c, B, dL, dR, s))) return rc;
+    if ((rc = launch_cost_volume(c, B, s))) return rc;
+    mark(c, 1, s);
+    if ((rc = launch_aggregate(c, B, s))) return rc;
+    mark(c, 2, s);
+    if ((rc = launch_select(c, B, s))) return rc;
+    mark(c, 3, s);
+    if ((rc = launch_post(c, B, d_out, s))) return rc;
+    mark(c, 4, s);
+    return SSM_OK;
+}
+
+// the mapper half on device buffers
+static int run_map(ssm_ctx* c, int B, const int16_t* d_disp, const uint8_t* d_sem, const uint8_t* d_rgb,
+                   const double* d_pose, cudaStream_t s)
+{
+    int rc;
+    if ((rc = launch_depth(c, B, d_disp, c->d_depth, s))) return rc;
+    if ((rc = launch_labels_mask(c, B, d_sem, s))) return rc;
+    if (c->nranks > 1) {
+        if ((rc = launch_points(c, B, c->d_depth, d_sem, d_rgb, d_pose, false, s))) return rc;
+        mark(c, 5, s);
+        if ((rc = route_and_fuse(c, s))) return rc;
+    } else {
+        mark(c, 5, s);   // single GPU: points are fused as they are generated, one kernel
+        if ((rc = launch_points(c, B, c->d_depth, d_sem, d_rgb, d_pose, true, s))) return rc;
+    }
+    mark(c, 6, s);
+    if (c->timing) c->ev_recorded = true;
+    return SSM_OK;
+}
+
+static int finish_timing(ssm_ctx* c)
+{
+    if (!c->timing || !c->ev_recorded) return SSM_OK;
+    SSM_CUDA(cudaEventSynchronize(c->ev[SSM_STAGE_COUNT]));
+    for (int i = 0; i < SSM_STAGE_COUNT; ++i) SSM_CUDA(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    return SSM_OK;
+}
+
+static int check_overflow(ssm_ctx* c, cudaStream_t s, uint64_t* n_voxels)
+{
+    uint32_t h[4];
+    SSM_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+    SSM_CUDA(cudaStreamSynchronize(s));
+    if (h[2] & 1u) return fail(SSM_ERR_CAPACITY, "voxel hash table is full (raise ssm_params.map_capacity)");
+    if (h[2] & 2u) return fail(SSM_ERR_CAPACITY, "point outside the 21-bit voxel coordinate range");
+    if (n_voxels) *n_voxels = h[1];
+    return SSM_OK;
+}
+
+}  // namespace ssm
+
+using namespace ssm;
+
+// =================================================================================================
+extern "C" {
+
+void ssm_default_params(ssm_params* p)
+{
+    memset(p, 0, sizeof(*p));
+    // src/stereo.cpp:16-28
+    p->min_disparity = 0; p->num_disparities = 80; p->block_size = 11;
+    p->p1 = 4 * 11 * 11; p->p2 = 32 * 11 * 11;
+    p->disp12_max_diff = 1; p->pre_filter_cap = 63; p->uniqueness_ratio = 10;
+    p->speckle_window_size = 100; p->speckle_range = 32;
+    // parameters.txt:37-41,50-54,63
+    p->cx = 607.1928; p->cy = 185.2157; p->fx = 718.8560; p->fy = 718.8560; p->baseline = 0.532331858; p->scale = 1000.0;
+    p->roix = 20; p->roiy = 5; p->roiz = 40;
+    // parameters.txt:97-98
+    p->resolution = 0.1; p->max_distance = 40;
+    // src/mapper.cpp:42-54
+    static const uint8_t pal[12][3] = {{128, 128, 128}, {0, 0, 128}, {128, 192, 192}, {0, 69, 255}, {128, 64, 128}, {222, 40, 60},
+                                       {0, 128, 128}, {128, 128, 192}, {128, 64, 64}, {128, 0, 64}, {0, 64, 64}, {192, 128, 0}};
+    p->num_labels = 12;
+    memcpy(p->palette_bgr, pal, sizeof(pal));
+    p->drop_mask = (1u << 0) | (1u << 2) | (1u << 11);
+    p->dynamic_mask = (1u << 10) | (1u << 11);
+    p->dilate_iterations = 2; p->colour_source = 0;
+    p->max_width = 1241; p->max_height = 376; p->max_batch = 1;
+    p->map_capacity = 1ull << 22;
+}
+
+const char* ssm_last_error(void) { return g_err.c_str(); }
+const char* ssm_version(void) { return "semantic_slam_mapping_b200 0.1 (sm_100a)"; }
+uint64_t ssm_kernel_launches(const ssm_ctx* c) { return c ? c->launches : 0; }
+
+int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
+{
+    if (!p || !out) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    int rc = validate(*p);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(SSM_ERR_NO_DEVICE, "no CUDA device available: libssm has no CPU fallback");
+    }
+    cudaDeviceProp prop;
+    SSM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(SSM_ERR_NO_DEVICE, "libssm is built for sm_100a (B200) only");
+    SSM_CUDA(cudaSetDevice(device));
+
+    ssm_ctx* c = new ssm_ctx();
+    c->p = *p;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cap_w = p->max_width; c->cap_h = p->max_height; c->cap_b = p->max_batch;
+    const size_t npix = (size_t)c->cap_w * c->cap_h * c->cap_b;
+    const size_t ncell = (size_t)(c->cap_w - p->num_disparities) * c->cap_h * c->cap_b * p->num_disparities;
+    uint64_t slots = 1024;
+    while (slots < p->map_capacity) slots <<= 1;
+    c->table_slots = slots;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    A(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& ev : c->ev) A(cudaEventCreate(&ev));
+    A(dalloc(&c->d_left, npix)); A(dalloc(&c->d_right, npix));
+    A(dalloc(&c->d_recL, npix)); A(dalloc(&c->d_recR, npix));
+    A(dalloc(&c->d_C, ncell)); A(dalloc(&c->d_S, ncell));
+    c->d_hs = c->d_S;   // horizontal sums are dead once C exists; S is written afterwards
+    A(dalloc(&c->d_disp_raw, npix)); A(dalloc(&c->d_disp_lr, npix)); A(dalloc(&c->d_disp_med, npix)); A(dalloc(&c->d_disp, npix));
+    A(dalloc(&c->d_disp2key, npix)); A(dalloc(&c->d_cc_label, npix)); A(dalloc(&c->d_cc_size, npix));
+    A(dalloc(&c->d_depth, npix)); A(dalloc(&c->d_label, npix)); A(dalloc(&c->d_mask, npix));
+    A(dalloc(&c->d_sem, npix * 3)); A(dalloc(&c->d_rgb, npix * 3));
+    A(dalloc(&c->d_pose, (size_t)16 * c->cap_b)); A(dalloc(&c->d_min_disp, (size_t)c->cap_b));
+    A(dalloc(&c->d_points, npix)); A(dalloc(&c->d_blk_count, npix / 1024 + 2)); A(dalloc(&c->d_counters, 8));
+    A(dalloc(&c->d_table, slots));
+    if (e != cudaSuccess) {
+        free_all(c);
+        delete c;
+        return cuda_fail(e, "ssm_create allocation");
+    }
+    fill_dev_params(c, c->cap_w, c->cap_h);
+    rc = launch_map_clear(c, c->stream);
+    if (rc == SSM_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "ssm_create");
+    if (rc) {
+        free_all(c);
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return SSM_OK;
+}
+
+void ssm_destroy(ssm_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    ssm_comm_destroy(c);
+    free_all(c);
+    delete c;
+}
+
+int ssm_set_stage_timing(ssm_ctx* c, int enabled)
+{
+    if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
+    c->timing = enabled != 0;
+    return SSM_OK;
+}
+int ssm_stage_time_ms(ssm_ctx* c, int stage, float* ms)
+{
+    if (!c || !ms || stage < 0 || stage >= SSM_STAGE_COUNT) return fail(SSM_ERR_INVALID_ARGUMENT, "bad stage");
+    if (!c->timing || !c->ev_recorded) return fail(SSM_ERR_INVALID_ARGUMENT, "stage timing is off or no pipeline call was timed");
+    int rc = finish_timing(c);   // waits for the last timed pipeline call
+    if (rc) return rc;
+    *ms = c->stage_ms[stage];
+    return SSM_OK;
+}
+int ssm_synchronize(ssm_ctx* c)
+{
+    if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
+    SSM_CUDA(cudaStreamSynchronize(c->stream));
+    return SSM_OK;
+}
+
+// ---- stereo.h -------------------------------------------------------------------------------------
+int ssm_sgbm_batch_device(ssm_ctx* c, int batch, const uint8_t* dL, const uint8_t* dR, int w, int h, int16_t* d_disp, void* stream)
+{
+    if (!c || !dL || !dR || !d_disp) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = set_shape(c, w, h, batch);
+    if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    return run_sgbm(c, batch, dL, dR, d_disp, s);
+}
+
+int ssm_sgbm(ssm_ctx* c, const uint8_t* left, const uint8_t* right, int w, int h, size_t stride, int16_t* disp, size_t disp_stride)
+{
+    if (!c || !left || !right || !disp) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (stride < (size_t)w || disp_stride < (size_t)w * 2) return fail(SSM_ERR_INVALID_ARGUMENT, "stride smaller than a row");
+    int rc = set_shape(c, w, h, 1);
+    if (rc) return rc;
+    SSM_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    SSM_CUDA(cudaMemcpy2DAsync(c->d_left, w, left, stride, w, h, cudaMemcpyHostToDevice, s));
+    SSM_CUDA(cudaMemcpy2DAsync(c->d_right, w, right, stride, w, h, cudaMemcpyHostToDevice, s));
+    if ((rc = run_sgbm(c, 1, c->d_left, c->d_right, c->d_disp, s))) return rc;
+    SSM_CUDA(cudaMemcpy2DAsync(disp, disp_stride, c->d_disp, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, s));
+    SSM_CUDA(cudaStreamSynchronize(s));
+    return SSM_OK;
+}
+
+int ssm_debug_copy_volume(ssm_ctx* c, int which, int bi, void* dst, size_t bytes)
+{
+    if (!c || !dst || bi < 0 || bi >= c->cap_b) return fail(SSM_ERR_INVALID_ARGUMENT, "bad argument");
+    const DevParams& p = c->dp;
+    const size_t cells = (size_t)p.H * p.W1 * p.D, npix = (size_t)p.H * p.W;
+    const void* src = nullptr;
+    size_t need = 0;
+    switch (which) {
+        case 0: src = c->d_C + cells * bi; need = cells * 2; break;
+        case 1: src = c->d_S + cells * bi; need = cells * 2; break;
+        case 2: src = c->d_disp_lr + npix * bi; need = npix * 2; break;
+        case 3: src = c->d_disp_med + npix * bi; need = npix * 2; break;
+        default: return fail(SSM_ERR_INVALID_ARGUMENT, "unknown volume id");
+    }
+    if (bytes < need) return fail(SSM_ERR_INVALID_ARGUMENT, "destination too small");
+    SSM_CUDA(cudaStreamSynchronize(c->stream));
+    SSM_CUDA(cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
+    return SSM_OK;
+}
+
+// ---- glue: disparity -> depth ------------------------------------------------------------------------
+int ssm_disparity_to_depth(ssm_ctx* c, const int16_t* disp, int w, int h, size_t disp_stride, uint16_t* depth, size_t depth_stride)
+{
+    if (!c || !disp || !depth) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = set_shape(c, w, h, 1);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    SSM_CUDA(cudaMemcpy2DAsync(c->d_disp, (size_t)w * 2, disp, disp_stride, (size_t)w * 2, h, cudaMemcpyHostToDevice, s));
+    if ((rc = launch_depth(c, 1, c->d_disp, c->d_depth, s))) return rc;
+    SSM_CUDA(cudaMemcpy2DAsync(depth, depth_stride, c->d_depth, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, s));
+    SSM_CUDA(cudaStreamSynchronize(s));
+    return SSM_OK;
+}
+
+// ---- mapper.h ----------------------------------------------------------------------------------------
+int ssm_semantic_motion_fuse(ssm_ctx* c, const uint8_t* sem, int w, int h, size_t stride, uint8_t* mask, size_t mask_stride)
+{
+    if (!c || !sem || !mask) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = set_shape(c, w, h, 1);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    SSM_CUDA(cudaMemcpy2DAsync(c->d_sem, (size_t)w * 3, sem, stride, (size_t)w * 3, h, cudaMemcpyHostToDevice, s));
+    if ((rc = launch_labels_mask(c, 1, c->d_sem, s))) return rc;
+    SSM_CUDA(cudaMemcpy2DAsync(mask, mask_stride, c->d_mask, w, w, h, cudaMemcpyDeviceToHost, s));
+    SSM_CUDA(cudaStreamSynchronize(s));
+    return SSM_OK;
+}
+
+static int upload_frame(ssm_ctx* c, const uint16_t* depth, const uint8_t* sem, const uint8_t* rgb, int w, int h, const double* T,
+                        cudaStream_t s)
+{
+    const size_t npix = (size_t)w * h;
+    SSM_CUDA(cudaMemcpyAsync(c->d_depth, depth, npix * 2, cudaMemcpyHostToDevice, s));
+    SSM_CUDA(cudaMemcpyAsync(c->d_sem, sem, npix * 3, cudaMemcpyHostToDevice, s));
+    SSM_CUDA(cudaMemcpyAsync(c->d_rgb, rgb, npix * 3, cudaMemcpyHostToDevice, s));
+    SSM_CUDA(cudaMemcpyAsync(c->d_pose, T, 16 * sizeof(double), cudaMemcpyHostToDevice, s));
+    return SSM_OK;
+}
+
+int ssm_generate_point_cloud(ssm_ctx* c, const uint16_t* depth, const uint8_t* sem, const uint8_t* rgb, int w, int h,
+                             const double* T, float* xyz, uint32_t* rgba, uint8_t* label, int max_points, int* n_points)
+{
+    if (!c || !depth || !sem || !rgb || !T || !n_points) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = set_shape(c, w, h, 1);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    if ((rc = upload_frame(c, depth, sem, rgb, w, h, T, s))) return rc;
+    if ((rc = launch_labels_mask(c, 1, c->d_sem, s))) return rc;
+    if ((rc = launch_points(c, 1, c->d_depth, c->d_sem, c->d_rgb, c->d_pose, false, s))) return rc;
+    uint32_t n = 0;
+    SSM_CUDA(cudaMemcpyAsync(&n, c->d_counters, sizeof(n), cudaMemcpyDeviceToHost, s));
+    SSM_CUDA(cudaStreamSynchronize(s));
+    *n_points = (int)n;
+    const uint32_t m = std::min<uint32_t>(n, (uint32_t)std::max(max_points, 0));
+    if (m && (xyz || rgba || label)) {
+        std::vector<Point> pts(m);
+        SSM_CUDA(cudaMemcpy(pts.data(), c->d_points, sizeof(Point) * m, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < m; ++i) {
+            if (xyz) { xyz[3 * i] = pts[i].x; xyz[3 * i + 1] = pts[i].y; xyz[3 * i + 2] = pts[i].z; }
+            if (rgba) rgba[i] = pts[i].rgba;
+            if (label) label[i] = (uint8_t)pts[i].label;
+        }
+    }
+    return SSM_OK;
+}
+
+int ssm_map_integrate_frame(ssm_ctx* c, const uint16_t* depth, const uint8_t* sem, const uint8_t* rgb, int w, int h, const double* T)
+{
+    if (!c || !depth || !sem || !rgb || !T) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = set_shape(c, w, h, 1);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    if ((rc = upload_frame(c, depth, sem, rgb, w, h, T, s))) return rc;
+    if ((rc = launch_labels_mask(c, 1, c->d_sem, s))) return rc;
+    if (c->nranks > 1) {
+        if ((rc = launch_points(c, 1, c->d_depth, c->d_sem, c->d_rgb, c->d_pose, false, s))) return rc;
+        if ((rc = route_and_fuse(c, s))) return rc;
+    } else if ((rc = launch_points(c, 1, c->d_depth, c->d_sem, c->d_rgb, c->d_pose, true, s))) {
+        return rc;
+    }
+    return check_overflow(c, s, nullptr);
+}
+
+int ssm_map_integrate_points(ssm_ctx* c, const float* xyz, const uint32_t* rgba, const uint8_t* label, int n)
+{
+    if (!c || (n > 0 && (!xyz || !rgba || !label)) || n < 0) return fail(SSM_ERR_INVALID_ARGUMENT, "bad argument");
+    const size_t cap = (size_t)c->cap_w * c->cap_h * c->cap_b;
+    cudaStream_t s = c->stream;
+    std::vector<Point> pts;
+    for (size_t base = 0; base < (size_t)n; base += cap) {
+        const size_t m = std::min(cap, (size_t)n - base);
+        pts.resize(m);
+        for (size_t i = 0; i < m; ++i) {
+            const size_t q = base + i;
+            pts[i] = Point{xyz[3 * q], xyz[3 * q + 1], xyz[3 * q + 2], rgba[q] & 0xffffffu, (uint32_t)label[q]};
+        }
+        SSM_CUDA(cudaMemcpyAsync(c->d_points, pts.data(), sizeof(Point) * m, cudaMemcpyHostToDevice, s));
+        int rc;
+        if (c->nranks > 1) {
+            const uint32_t mm = (uint32_t)m;
+            SSM_CUDA(cudaMemcpyAsync(c->d_counters, &mm, sizeof(mm), cudaMemcpyHostToDevice, s));
+            if ((rc = route_and_fuse(c, s))) return rc;
+        } else if ((rc = launch_fuse_points(c, c->d_points, nullptr, (uint32_t)m, s))) {
+            return rc;
+        }
+        SSM_CUDA(cudaStreamSynchronize(s));
+    }
+    return check_overflow(c, s, nullptr);
+}
+
+int ssm_map_clear(ssm_ctx* c)
+{
+    if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
+    int rc = launch_map_clear(c, c->stream);
+    if (rc) return rc;
+    SSM_CUDA(cudaStreamSynchronize(c->stream));
+    return SSM_OK;
+}
+
+int ssm_map_size(ssm_ctx* c, uint64_t* n)
+{
+    if (!c || !n) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    return check_overflow(c, c->stream, n);
+}
+
+static int export_records(ssm_ctx* c, std::vector<Voxel>& recs, bool sorted)
+{
+    uint64_t n = 0;
+    int rc = check_overflow(c, c->stream, &n);
+    if (rc) return rc;
+    recs.resize(n);
+    if (n == 0) return SSM_OK;
+    Voxel* d_out = nullptr;
+    SSM_CUDA(cudaMalloc(&d_out, sizeof(Voxel) * n));
+    rc = launch_export(c, d_out, (uint32_t)n, c->stream);
+    if (rc == SSM_OK && cudaMemcpyAsync(recs.data(), d_out, sizeof(Voxel) * n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+        rc = cuda_fail(cudaGetLastError(), "export copy");
+    if (rc == SSM_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "export sync");
+    cudaFree(d_out);
+    if (rc) return rc;
+    if (sorted) {
+        // pcl::VoxelGrid orders by idx = i + j*dx + k*dx*dy  <=>  lexicographic (k, j, i)
+        std::sort(recs.begin(), recs.end(), [](const Voxel& a, const Voxel& b) {
+            int ai, aj, ak, bi, bj, bk;
+            unpack_key(a.key, ai, aj, ak);
+            unpack_key(b.key, bi, bj, bk);
+            if (ak != bk) return ak < bk;
+            if (aj != bj) return aj < bj;
+            return ai < bi;
+        });
+    }
+    return SSM_OK;
+}
+
+static void finalize_voxel(const ssm_ctx* c, const Voxel& v, float xyz[3], uint32_t* rgba, uint8_t* label)
+{
+    const double n = (double)v.n;
+    xyz[0] = (float)((double)(long long)v.sx / kFixScale / n);
+    xyz[1] = (float)((double)(long long)v.sy / kFixScale / n);
+    xyz[2] = (float)((double)(long long)v.sz / kFixScale / n);
+    // PCL: centroid /= float(n); rgb = int(r)<<16 | int(g)<<8 | int(b)  (truncation, alpha 0)
+    const float fn = (float)v.n;
+    const float r = (float)v.sr / fn, g = (float)v.sg / fn, b = (float)v.sb / fn;
+    *rgba = ((uint32_t)(int)r << 16) | ((uint32_t)(int)g << 8) | (uint32_t)(int)b;
+    uint32_t bestv = 0;
+    int bestl = SSM_LABEL_UNKNOWN;
+    for (int l = 0; l < c->p.num_labels; ++l)
+        if (v.votes[l] > bestv) { bestv = v.votes[l]; bestl = l; }
+    *label = (uint8_t)bestl;
+}
+
+int ssm_map_export(ssm_ctx* c, const ssm_voxel_export* out, uint64_t max_voxels, int sorted, uint64_t* n_out)
+{
+    if (!c || !out || !n_out) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<Voxel> recs;
+    int rc = export_records(c, recs, sorted != 0);
+    if (rc) return rc;
+    const uint64_t n = std::min<uint64_t>(recs.size(), max_voxels);
+    const int L = c->p.num_labels;
+    for (uint64_t q = 0; q < n; ++q) {
+        const Voxel& v = recs[q];
+        float xyz[3];
+        uint32_t rgba;
+        uint8_t label;
+        finalize_voxel(c, v, xyz, &rgba, &label);
+        if (out->ijk) { int i, j, k; unpack_key(v.key, i, j, k); out->ijk[3 * q] = i; out->ijk[3 * q + 1] = j; out->ijk[3 * q + 2] = k; }
+        if (out->xyz) { out->xyz[3 * q] = xyz[0]; out->xyz[3 * q + 1] = xyz[1]; out->xyz[3 * q + 2] = xyz[2]; }
+        if (out->rgba) out->rgba[q] = rgba;
+        if (out->label) out->label[q] = label;
+        if (out->count) out->count[q] = v.n;
+        if (out->votes) for (int l = 0; l < L; ++l) out->votes[q * L + l] = v.votes[l];
+    }
+    *n_out = recs.size();
+    return SSM_OK;
+}
+
+int ssm_map_save_pcd(ssm_ctx* c, const char* path)
+{
+    if (!c || !path) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<Voxel> recs;
+    int rc = export_records(c, recs, true);
+    if (rc) return rc;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(SSM_ERR_INVALID_ARGUMENT, std::string("cannot open ") + path);
+    // pcl::PCDWriter::write (ASCII header, binary body) for PointXYZRGBA: x y z rgba
+    fprintf(f, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z rgba\nSIZE 4 4 4 4\nTYPE F F F U\n"
+               "COUNT 1 1 1 1\nWIDTH %zu\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %zu\nDATA binary\n", recs.size(), recs.size());
+    for (const Voxel& v : recs) {
+        float xyz[3];
+        uint32_t rgba;
+        uint8_t label;
+        finalize_voxel(c, v, xyz, &rgba, &label);
+        fwrite(xyz, sizeof(float), 3, f);
+        fwrite(&rgba, sizeof(uint32_t), 1, f);
+    }
+    fclose(f);
+    return SSM_OK;
+}
+
+// ---- the whole path, batched --------------------------------------------------------------------------
+int ssm_pipeline_batch_device(ssm_ctx* c, int batch, const uint8_t* dL, const uint8_t* dR, const uint8_t* d_sem,
+                              const uint8_t* d_rgb, const double* d_poses, int w, int h, int16_t* d_disp_out, void* stream)
+{
+    if (!c || !dL || !dR || !d_sem || !d_rgb || !d_poses) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = set_shape(c, w, h, batch);
+    if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    int16_t* d_disp = d_disp_out ? d_disp_out : c->d_disp;
+    if ((rc = run_sgbm(c, batch, dL, dR, d_disp, s))) return rc;
+    if ((rc = run_map(c, batch, d_disp, d_sem, d_rgb, d_poses, s))) return rc;
+    return SSM_OK;
+}
+
+int ssm_pipeline_batch_host(ssm_ctx* c, int batch, const uint8_t* left, const uint8_t* right, const uint8_t* sem,
+                            const uint8_t* rgb, const double* poses, int w, int h, int16_t* disp_out, uint64_t* n_voxels_out)
+{
+    if (!c || !left || !right || !sem || !rgb || !poses) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = set_shape(c, w, h, batch);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    const size_t npix = (size_t)w * h * batch;
+    SSM_CUDA(cudaMemcpyAsync(c->d_left, left, npix, cudaMemcpyHostToDevice, s));
+    SSM_CUDA(cudaMemcpyAsync(c->d_right, right, npix, cudaMemcpyHostToDevice, s));
+    SSM_CUDA(cudaMemcpyAsync(c->d_sem, sem, npix * 3, cudaMemcpyHostToDevice, s));
+    SSM_CUDA(cudaMemcpyAsync(c->d_rgb, rgb, npix * 3, cudaMemcpyHostToDevice, s));
+    SSM_CUDA(cudaMemcpyAsync(c->d_pose, poses, sizeof(double) * 16 * batch, cudaMemcpyHostToDevice, s));
+    if ((rc = run_sgbm(c, batch, c->d_left, c->d_right, c->d_disp, s))) return rc;
+    if ((rc = run_map(c, batch, c->d_disp, c->d_sem, c->d_rgb, c->d_pose, s))) return rc;
+    if (disp_out) SSM_CUDA(cudaMemcpyAsync(disp_out, c->d_disp, npix * 2, cudaMemcpyDeviceToHost, s));
+    return check_overflow(c, s, n_voxels_out);
+}
+
+}  // extern "C"

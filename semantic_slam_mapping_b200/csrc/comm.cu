@@ -1,0 +1,227 @@
+// comm.cu -- multi-GPU voxel fusion: spatially owned hash, NCCL all-to-all point routing.
+//
+// The reference has no distributed code.  Frames are sharded across ranks by the host; every rank turns its
+// frames into labelled world-frame points (mapper.cu), buckets them by the owner rank of their voxel brick
+// (voxel_owner: 8^3-voxel bricks hashed over the ranks), exchanges the buckets with one grouped
+// ncclSend/ncclRecv all-to-all over NVLink, and fuses what it receives into its own table.  Counts, votes
+// and the fixed-point centroid sums are integers, so the fused map is identical for any rank count.
+//
+// NCCL is resolved with dlopen at ssm_comm_init time (the process usually already holds torch's
+// libnccl.so.2); libssm.so itself has no link-time NCCL dependency and single-GPU use never touches it.
+#include <dlfcn.h>
+
+#include <vector>
+
+#include "ssm_internal.cuh"
+
+namespace ssm {
+
+// ---- minimal NCCL surface (matches nccl.h 2.x) ---------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclUint8 = 1, ncclUint32 = 3 };
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl()
+{
+    if (g_nccl.lib) return SSM_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        set_error(std::string("cannot load libnccl.so.2: ") + dlerror());
+        return SSM_ERR_COMM;
+    }
+#define SSM_SYM(field, name)                                                           \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name));           \
+    if (!g_nccl.field) { set_error("libnccl lacks " name); return SSM_ERR_COMM; }
+    SSM_SYM(GetUniqueId, "ncclGetUniqueId")
+    SSM_SYM(CommInitRank, "ncclCommInitRank")
+    SSM_SYM(CommDestroy, "ncclCommDestroy")
+    SSM_SYM(AllGather, "ncclAllGather")
+    SSM_SYM(Send, "ncclSend")
+    SSM_SYM(Recv, "ncclRecv")
+    SSM_SYM(GroupStart, "ncclGroupStart")
+    SSM_SYM(GroupEnd, "ncclGroupEnd")
+    SSM_SYM(GetErrorString, "ncclGetErrorString")
+#undef SSM_SYM
+    g_nccl.lib = h;
+    return SSM_OK;
+}
+
+static int nccl_fail(ncclResult_t r, const char* what)
+{
+    set_error(std::string("NCCL error: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?") + " at " + what);
+    return SSM_ERR_COMM;
+}
+#define SSM_NCCL(expr)                                         \
+    do {                                                       \
+        ncclResult_t _r = (expr);                              \
+        if (_r != 0) return nccl_fail(_r, #expr);              \
+    } while (0)
+
+// ---- bucketing kernels ---------------------------------------------------------------------------
+constexpr int kMaxRanks = 64;
+
+__device__ __forceinline__ int owner_of(const Point& pt, float inv_leaf, int nranks)
+{
+    if (!isfinite(pt.x) || !isfinite(pt.y) || !isfinite(pt.z)) return 0;   // dropped by the fuse kernel anyway
+    const int i = (int)floorf(__fmul_rn(pt.x, inv_leaf));
+    const int j = (int)floorf(__fmul_rn(pt.y, inv_leaf));
+    const int k = (int)floorf(__fmul_rn(pt.z, inv_leaf));
+    return voxel_owner(i, j, k, nranks);
+}
+
+// counts[r] += number of points owned by r (shared-memory histogram per CTA, one global atomic per rank per CTA)
+__global__ void __launch_bounds__(256) k_route_count(const Point* __restrict__ pts, const uint32_t* __restrict__ n_ptr,
+                                                     uint32_t max_n, float inv_leaf, int nranks, uint32_t* __restrict__ counts)
+{
+    __shared__ uint32_t h[kMaxRanks];
+    if (threadIdx.x < kMaxRanks) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n = min(*n_ptr, max_n);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&h[owner_of(pts[i], inv_leaf, nranks)], 1u);
+    __syncthreads();
+    if (threadIdx.x < nranks && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], h[threadIdx.x]);
+}
+// counts[0..R) -> offsets[R..2R), cursors[2R..3R)
+__global__ void k_route_offsets(uint32_t* __restrict__ c, int nranks)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t acc = 0;
+    for (int r = 0; r < nranks; ++r) {
+        c[nranks + r] = acc;
+        c[2 * nranks + r] = acc;
+        acc += c[r];
+    }
+}
+__global__ void __launch_bounds__(256) k_route_scatter(const Point* __restrict__ pts, const uint32_t* __restrict__ n_ptr,
+                                                       uint32_t max_n, float inv_leaf, int nranks, uint32_t* __restrict__ c,
+                                                       Point* __restrict__ send)
+{
+    const uint32_t n = min(*n_ptr, max_n);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Point pt = pts[i];
+        const int r = owner_of(pt, inv_leaf, nranks);
+        send[atomicAdd(&c[2 * nranks + r], 1u)] = pt;
+    }
+}
+
+int launch_route_bucket(ssm_ctx* c, uint32_t max_points, cudaStream_t s)
+{
+    const int R = c->nranks;
+    SSM_CUDA(cudaMemsetAsync(c->d_send_counts, 0, sizeof(uint32_t) * 3 * R, s));
+    const unsigned grid = (unsigned)c->sm_count * 8;
+    k_route_count<<<grid, 256, 0, s>>>(c->d_points, c->d_counters, max_points, c->dp.inv_leaf, R, c->d_send_counts);
+    SSM_LAUNCH_CHECK(c);
+    k_route_offsets<<<1, 32, 0, s>>>(c->d_send_counts, R);
+    SSM_LAUNCH_CHECK(c);
+    k_route_scatter<<<grid, 256, 0, s>>>(c->d_points, c->d_counters, max_points, c->dp.inv_leaf, R, c->d_send_counts, c->d_send);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+// d_points[0..counters[0]) -> owners' tables
+int route_and_fuse(ssm_ctx* c, cudaStream_t s)
+{
+    if (!c->comm) {
+        set_error("ssm_comm_init has not been called on this context");
+        return SSM_ERR_COMM;
+    }
+    const int R = c->nranks, me = c->rank;
+    const uint32_t cap = (uint32_t)((size_t)c->cap_w * c->cap_h * c->cap_b);
+    int rc = launch_route_bucket(c, cap, s);
+    if (rc) return rc;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    uint32_t* d_all = c->d_send_counts + 3 * R;   // [R][R] gathered counts
+    SSM_NCCL(g_nccl.AllGather(c->d_send_counts, d_all, R, ncclUint32, comm, s));
+    std::vector<uint32_t> all((size_t)R * R), mine(3 * R);
+    SSM_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(uint32_t) * R * R, cudaMemcpyDeviceToHost, s));
+    SSM_CUDA(cudaMemcpyAsync(mine.data(), c->d_send_counts, sizeof(uint32_t) * 3 * R, cudaMemcpyDeviceToHost, s));
+    SSM_CUDA(cudaStreamSynchronize(s));
+    size_t total_recv = 0;
+    for (int r = 0; r < R; ++r) total_recv += all[(size_t)r * R + me];
+    if (total_recv > c->route_cap) {   // grow the receive buffer (rare: sized for 2x a full local batch at init)
+        if (c->d_recv) SSM_CUDA(cudaFree(c->d_recv));
+        c->d_recv = nullptr;
+        c->route_cap = total_recv + total_recv / 4;
+        SSM_CUDA(cudaMalloc(&c->d_recv, sizeof(Point) * c->route_cap));
+    }
+    SSM_NCCL(g_nccl.GroupStart());
+    size_t roff = 0;
+    for (int r = 0; r < R; ++r) {
+        const uint32_t scnt = mine[r], soff = mine[R + r], rcnt = all[(size_t)r * R + me];
+        if (scnt) SSM_NCCL(g_nccl.Send(c->d_send + soff, (size_t)scnt * sizeof(Point), ncclUint8, r, comm, s));
+        if (rcnt) SSM_NCCL(g_nccl.Recv(c->d_recv + roff, (size_t)rcnt * sizeof(Point), ncclUint8, r, comm, s));
+        roff += rcnt;
+    }
+    SSM_NCCL(g_nccl.GroupEnd());
+    return launch_fuse_points(c, c->d_recv, nullptr, (uint32_t)total_recv, s);
+}
+
+}  // namespace ssm
+
+using namespace ssm;
+
+extern "C" {
+
+int ssm_voxel_owner(int32_t i, int32_t j, int32_t k, int nranks) { return voxel_owner(i, j, k, nranks); }
+
+int ssm_comm_get_unique_id(uint8_t id[SSM_UNIQUE_ID_BYTES])
+{
+    int rc = load_nccl();
+    if (rc) return rc;
+    ncclUniqueId u;
+    SSM_NCCL(g_nccl.GetUniqueId(&u));
+    memcpy(id, u.internal, SSM_UNIQUE_ID_BYTES);
+    return SSM_OK;
+}
+
+int ssm_comm_init(ssm_ctx* c, const uint8_t id[SSM_UNIQUE_ID_BYTES], int rank, int nranks)
+{
+    if (!c || !id || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) {
+        set_error("bad rank / nranks");
+        return SSM_ERR_INVALID_ARGUMENT;
+    }
+    int rc = load_nccl();
+    if (rc) return rc;
+    SSM_CUDA(cudaSetDevice(c->device));
+    ncclUniqueId u;
+    memcpy(u.internal, id, SSM_UNIQUE_ID_BYTES);
+    ncclComm_t comm = nullptr;
+    SSM_NCCL(g_nccl.CommInitRank(&comm, nranks, u, rank));
+    c->comm = comm;
+    c->rank = rank;
+    c->nranks = nranks;
+    const size_t cap = (size_t)c->cap_w * c->cap_h * c->cap_b;
+    SSM_CUDA(cudaMalloc(&c->d_send, sizeof(Point) * cap));
+    c->route_cap = 2 * cap;
+    SSM_CUDA(cudaMalloc(&c->d_recv, sizeof(Point) * c->route_cap));
+    SSM_CUDA(cudaMalloc(&c->d_send_counts, sizeof(uint32_t) * (3 * nranks + (size_t)nranks * nranks)));
+    return SSM_OK;
+}
+
+int ssm_comm_destroy(ssm_ctx* c)
+{
+    if (!c || !c->comm) return SSM_OK;
+    g_nccl.CommDestroy((ncclComm_t)c->comm);
+    c->comm = nullptr;
+    c->rank = 0;
+    c->nranks = 1;
+    return SSM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,380 @@
+// mapper.cu -- disparity -> depth -> labelled cloud -> voxel-hash fusion, sm_100a.
+//
+// Replaces, for the drop-in path:
+//   FrameReader::next depth loop              /root/reference src/rgbdframe.cpp:85-116   (k_min_disp, k_depth)
+//   Mapper::semantic_motion_fuse              src/mapper.cpp:189-216                     (k_labels, k_moving_mask)
+//   Mapper::generatePointCloud                src/mapper.cpp:12-94                       (k_points_*)
+//   RGBDFrame::project2dTo3d                  include/rgbdframe.h:63-75
+//   pcl::transformPointCloud(Matrix4d)        src/mapper.cpp:90-91
+//   pcl::VoxelGrid<PointXYZRGBA>::filter      src/mapper.cpp:106-107,154-155 (k_fuse, k_export)
+// fp64 expressions use explicit __dmul_rn/__dadd_rn/__ddiv_rn so that no FMA contraction can change a bit
+// relative to the reference's (unfused) double arithmetic.
+#include <algorithm>
+
+#include "ssm_internal.cuh"
+
+namespace ssm {
+
+// DevParams travels as a __grid_constant__ kernel argument (constant bank, no global state between contexts).
+#define SSM_DP const __grid_constant__ DevParams p
+
+// ------------------------------------------------------------------------------------------------
+// rgbdframe.cpp:85  cv::minMaxIdx(disp_sgbm, &minDisparity)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_min_disp(const int16_t* __restrict__ disp, int* __restrict__ min_disp,
+                                                  size_t per_frame, int B)
+{
+    const int b = blockIdx.y;
+    if (b >= B) return;
+    int m = 32767;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_frame; i += (size_t)gridDim.x * blockDim.x)
+        m = min(m, (int)disp[(size_t)b * per_frame + i]);
+    m = __reduce_min_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMin(&min_disp[b], m);
+}
+
+// rgbdframe.cpp:97-116
+__global__ void __launch_bounds__(256) k_depth(const int16_t* __restrict__ disp, const int* __restrict__ min_disp,
+                                               uint16_t* __restrict__ depth, size_t total, SSM_DP)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int u = (int)(idx % p.W);
+    const size_t r = idx / p.W;
+    const int v = (int)(r % p.H);
+    const int b = (int)(r / p.H);
+    const int d = disp[idx];
+    uint16_t out = 0;
+    if (d != 0 && d != min_disp[b]) {
+        const double pw = __ddiv_rn(p.baseline, (double)d);
+        const double px = __dmul_rn(__dmul_rn(__dsub_rn((double)u, p.cx), pw), 16.0);
+        const double py = __dmul_rn(__dmul_rn(__dsub_rn((double)v, p.cy), pw), 16.0);
+        const double pz = __dmul_rn(__dmul_rn(p.fx, pw), 16.0);
+        if (fabs(px) < p.roix && fabs(py) < p.roiy && fabs(pz) < p.roiz && pz > 0)
+            out = (uint16_t)(int)__dmul_rn(pz, p.scale);   // truncation, pz*scale < 65536 because roiz*scale is checked at create
+    }
+    depth[idx] = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// semantic BGR -> class id (palette lookup), then the dilated dynamic-object mask
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int label_of(const DevParams& p, uint32_t bgr)
+{
+    int l = SSM_LABEL_UNKNOWN;
+#pragma unroll 4
+    for (int i = p.num_labels - 1; i >= 0; --i)
+        if (p.palette[i] == bgr) l = i;   // lowest matching id wins, like the oracle's first-match scan
+    return l;
+}
+
+__global__ void __launch_bounds__(256) k_labels(const uint8_t* __restrict__ sem, uint8_t* __restrict__ label, size_t total, SSM_DP)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const uint8_t* s = sem + idx * 3;
+    label[idx] = (uint8_t)label_of(p, (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16));
+}
+
+// cv::dilate(img, img, ones(3,3), anchor centre, iterations) == (2*it+1)^2 max filter, out-of-image ignored
+__global__ void __launch_bounds__(256) k_moving_mask(const uint8_t* __restrict__ label, uint8_t* __restrict__ mask, size_t total, SSM_DP)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = (int)(idx % p.W);
+    const size_t r = idx / p.W;
+    const int y = (int)(r % p.H);
+    const uint8_t* img = label + (r / p.H) * (size_t)p.W * p.H;
+    const int R = p.dilate_radius;
+    bool hit = false;
+    for (int dy = -R; dy <= R; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= p.H) continue;
+        for (int dx = -R; dx <= R; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= p.W) continue;
+            const int l = img[(size_t)yy * p.W + xx];
+            hit |= (l != SSM_LABEL_UNKNOWN) && ((p.dynamic_mask >> l) & 1u);
+        }
+    }
+    mask[idx] = hit ? 255 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-pixel point generation (mapper.cpp:22-86 + rgbdframe.h:63-75 + transformPointCloud)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool make_point(const DevParams& p, size_t idx, const uint16_t* __restrict__ depth, const uint8_t* __restrict__ label,
+                                           const uint8_t* __restrict__ mask, const uint8_t* __restrict__ sem,
+                                           const uint8_t* __restrict__ rgb, const double* __restrict__ pose, Point& out)
+{
+    const int d = depth[idx];
+    if (d == 0) return false;                                  // mapper.cpp:28
+    if ((double)d > p.max_depth_units) return false;           // :30  d > max_distance * camera.scale
+    if (mask[idx] == 255) return false;                        // :32
+    const int l = label[idx];
+    if (l != SSM_LABEL_UNKNOWN && ((p.drop_mask >> l) & 1u)) return false;   // :41-55
+    const int u = (int)(idx % p.W);
+    const size_t r = idx / p.W;
+    const int v = (int)(r % p.H);
+    const double* T = pose + (r / p.H) * 16;
+    // rgbdframe.h:71-73 -- each component is rounded to float on assignment
+    const float z = (float)__ddiv_rn((double)d, p.scale);
+    const float x = (float)__ddiv_rn(__dmul_rn(__dsub_rn((double)u, p.cx), (double)z), p.fx);
+    const float y = (float)__ddiv_rn(__dmul_rn(__dsub_rn((double)v, p.cy), (double)z), p.fy);
+    // Eigen Affine3d * Vector3d, evaluated left to right without contraction
+    float w[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double acc = __dmul_rn(T[4 * k], (double)x);
+        acc = __dadd_rn(acc, __dmul_rn(T[4 * k + 1], (double)y));
+        acc = __dadd_rn(acc, __dmul_rn(T[4 * k + 2], (double)z));
+        acc = __dadd_rn(acc, T[4 * k + 3]);
+        w[k] = (float)acc;
+    }
+    const uint8_t* c = (p.colour_source == 0 ? rgb : sem) + idx * 3;   // mapper.cpp:72-84 vs mapper.cpp~:60
+    out.x = w[0]; out.y = w[1]; out.z = w[2];
+    out.rgba = ((uint32_t)c[2] << 16) | ((uint32_t)c[1] << 8) | (uint32_t)c[0];
+    out.label = (uint32_t)l;
+    return true;
+}
+
+// ---- voxel hash insert -------------------------------------------------------------------------
+__device__ __forceinline__ void fuse_point(const DevParams& p, Voxel* __restrict__ table, uint64_t mask, const Point& pt, uint32_t* counters)
+{
+    if (!isfinite(pt.x) || !isfinite(pt.y) || !isfinite(pt.z)) return;   // cloud.is_dense == false (mapper.cpp:92)
+    // pcl::VoxelGrid: ijk = floor(coord * inverse_leaf_size) in fp32
+    const int i = (int)floorf(__fmul_rn(pt.x, p.inv_leaf));
+    const int j = (int)floorf(__fmul_rn(pt.y, p.inv_leaf));
+    const int k = (int)floorf(__fmul_rn(pt.z, p.inv_leaf));
+    if (i < -(1 << 20) || i >= (1 << 20) || j < -(1 << 20) || j >= (1 << 20) || k < -(1 << 20) || k >= (1 << 20)) {
+        atomicOr(&counters[2], 2u);   // coordinate outside the 21-bit key range
+        return;
+    }
+    const unsigned long long key = pack_key(i, j, k);
+    uint64_t slot = mix64(key) & mask;
+    for (uint64_t probe = 0; probe <= mask; ++probe, slot = (slot + 1) & mask) {
+        Voxel* v = table + slot;
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&v->key);
+        if (cur == kEmptyKey) {
+            cur = atomicCAS(&v->key, kEmptyKey, key);
+            if (cur == kEmptyKey) {
+                atomicAdd(&counters[1], 1u);
+                cur = key;
+            }
+        }
+        if (cur == key) {
+            atomicAdd(&v->sx, (unsigned long long)__double2ll_rn(__dmul_rn((double)pt.x, kFixScale)));
+            atomicAdd(&v->sy, (unsigned long long)__double2ll_rn(__dmul_rn((double)pt.y, kFixScale)));
+            atomicAdd(&v->sz, (unsigned long long)__double2ll_rn(__dmul_rn((double)pt.z, kFixScale)));
+            atomicAdd(&v->n, 1u);
+            atomicAdd(&v->sr, (pt.rgba >> 16) & 255u);
+            atomicAdd(&v->sg, (pt.rgba >> 8) & 255u);
+            atomicAdd(&v->sb, pt.rgba & 255u);
+            if (pt.label < (uint32_t)p.num_labels) atomicAdd(&v->votes[pt.label], 1u);
+            return;
+        }
+    }
+    atomicOr(&counters[2], 1u);   // table full
+}
+
+// FUSE mode: straight from pixels into the hash (single-GPU pipeline)
+__global__ void __launch_bounds__(256) k_points_fuse(const uint16_t* __restrict__ depth, const uint8_t* __restrict__ label,
+                                                     const uint8_t* __restrict__ mask, const uint8_t* __restrict__ sem,
+                                                     const uint8_t* __restrict__ rgb, const double* __restrict__ pose,
+                                                     Voxel* __restrict__ table, uint64_t slot_mask, uint32_t* counters,
+                                                     size_t total, SSM_DP)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    Point pt;
+    if (make_point(p, idx, depth, label, mask, sem, rgb, pose, pt)) {
+        fuse_point(p, table, slot_mask, pt, counters);
+        atomicAdd(&counters[0], 1u);
+    }
+}
+
+// COMPACT mode (ordered, row-major like the reference's push_back loop): count per block, scan, scatter
+constexpr int kCompactBlock = 1024;
+__global__ void __launch_bounds__(kCompactBlock) k_points_count(const uint16_t* __restrict__ depth, const uint8_t* __restrict__ label,
+                                                               const uint8_t* __restrict__ mask, uint32_t* __restrict__ blk_count,
+                                                               size_t total, SSM_DP)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (idx < total) {
+        const int d = depth[idx];
+        const int l = label[idx];
+        ok = d != 0 && !((double)d > p.max_depth_units) && mask[idx] != 255 &&
+             !(l != SSM_LABEL_UNKNOWN && ((p.drop_mask >> l) & 1u));
+    }
+    const int c = __syncthreads_count(ok);
+    if (threadIdx.x == 0) blk_count[blockIdx.x] = (uint32_t)c;
+}
+// single-CTA exclusive scan over the per-block counts; total goes to counters[0]
+__global__ void __launch_bounds__(1024) k_scan_blocks(uint32_t* __restrict__ blk, int n, uint32_t* __restrict__ counters)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < n ? blk[i] : 0u;
+        uint32_t s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+            if ((threadIdx.x & 31) >= o) s += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_sums[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += t;
+            }
+            warp_sums[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const uint32_t before = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0u;
+        if (i < n) blk[i] = carry + before + s - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counters[0] = carry;
+}
+__global__ void __launch_bounds__(kCompactBlock) k_points_scatter(const uint16_t* __restrict__ depth, const uint8_t* __restrict__ label,
+                                                                 const uint8_t* __restrict__ mask, const uint8_t* __restrict__ sem,
+                                                                 const uint8_t* __restrict__ rgb, const double* __restrict__ pose,
+                                                                 const uint32_t* __restrict__ blk_off, Point* __restrict__ out,
+                                                                 size_t total, SSM_DP)
+{
+    __shared__ uint32_t warp_off[32];
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Point pt;
+    const bool ok = idx < total && make_point(p, idx, depth, label, mask, sem, rgb, pose, pt);
+    const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_off[warp] = __popc(ballot);
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_off[lane], s = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        warp_off[lane] = s - w;
+    }
+    __syncthreads();
+    if (ok) out[blk_off[blockIdx.x] + warp_off[warp] + __popc(ballot & ((1u << lane) - 1u))] = pt;
+}
+
+// fuse an explicit list of points (host-provided clouds, or points received from other ranks)
+__global__ void __launch_bounds__(256) k_fuse_list(const Point* __restrict__ pts, const uint32_t* __restrict__ count,
+                                                   uint32_t max_count, Voxel* __restrict__ table, uint64_t slot_mask,
+                                                   uint32_t* counters, SSM_DP)
+{
+    const uint32_t n = count ? min(*count, max_count) : max_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        fuse_point(p, table, slot_mask, pts[i], counters);
+}
+
+__global__ void __launch_bounds__(256) k_table_clear(Voxel* __restrict__ table, size_t words16)
+{
+    uint4* t = reinterpret_cast<uint4*>(table);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words16; i += (size_t)gridDim.x * blockDim.x) {
+        // key = all ones, everything else zero; the key is the first 8 bytes of each 128-byte record
+        t[i] = (i & 7) == 0 ? make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// export: compact occupied records (unordered; the host sorts when PCL order is requested)
+__global__ void __launch_bounds__(256) k_export(const Voxel* __restrict__ table, uint64_t slots, Voxel* __restrict__ out,
+                                                uint32_t* __restrict__ counters, uint32_t max_out)
+{
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (uint64_t)gridDim.x * blockDim.x) {
+        if (table[s].key == kEmptyKey) continue;
+        const uint32_t o = atomicAdd(&counters[3], 1u);
+        if (o < max_out) out[o] = table[s];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+int launch_depth(ssm_ctx* c, int B, const int16_t* d_disp, uint16_t* d_depth, cudaStream_t s)
+{
+    const DevParams& p = c->dp;
+    const size_t per_frame = (size_t)p.W * p.H, total = per_frame * B;
+    SSM_CUDA(cudaMemsetAsync(c->d_min_disp, 0x7f, sizeof(int) * B, s));
+    k_min_disp<<<dim3(64, B), 256, 0, s>>>(d_disp, c->d_min_disp, per_frame, B);
+    SSM_LAUNCH_CHECK(c);
+    k_depth<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_disp, c->d_min_disp, d_depth, total, p);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+int launch_labels_mask(ssm_ctx* c, int B, const uint8_t* d_sem, cudaStream_t s)
+{
+    const DevParams& p = c->dp;
+    const size_t total = (size_t)p.W * p.H * B;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    k_labels<<<grid, 256, 0, s>>>(d_sem, c->d_label, total, p);
+    SSM_LAUNCH_CHECK(c);
+    k_moving_mask<<<grid, 256, 0, s>>>(c->d_label, c->d_mask, total, p);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+int launch_points(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t* d_sem, const uint8_t* d_rgb,
+                  const double* d_pose, bool fuse_into_map, cudaStream_t s)
+{
+    const DevParams& p = c->dp;
+    const size_t total = (size_t)p.W * p.H * B;
+    SSM_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t), s));   // counters[0] = points of this call
+    if (fuse_into_map) {
+        k_points_fuse<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_depth, c->d_label, c->d_mask, d_sem, d_rgb, d_pose,
+                                                                      c->d_table, c->table_slots - 1, c->d_counters, total, p);
+        SSM_LAUNCH_CHECK(c);
+        return SSM_OK;
+    }
+    const int nblk = (int)((total + kCompactBlock - 1) / kCompactBlock);
+    k_points_count<<<nblk, kCompactBlock, 0, s>>>(d_depth, c->d_label, c->d_mask, c->d_blk_count, total, p);
+    SSM_LAUNCH_CHECK(c);
+    k_scan_blocks<<<1, 1024, 0, s>>>(c->d_blk_count, nblk, c->d_counters);
+    SSM_LAUNCH_CHECK(c);
+    k_points_scatter<<<nblk, kCompactBlock, 0, s>>>(d_depth, c->d_label, c->d_mask, d_sem, d_rgb, d_pose, c->d_blk_count,
+                                                    c->d_points, total, p);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+int launch_fuse_points(ssm_ctx* c, const Point* d_pts, const uint32_t* d_count, uint32_t max_count, cudaStream_t s)
+{
+    if (max_count == 0) return SSM_OK;
+    const unsigned grid = (unsigned)std::min<size_t>(((size_t)max_count + 255) / 256, (size_t)c->sm_count * 16);
+    k_fuse_list<<<grid, 256, 0, s>>>(d_pts, d_count, max_count, c->d_table, c->table_slots - 1, c->d_counters, c->dp);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+int launch_map_clear(ssm_ctx* c, cudaStream_t s)
+{
+    const size_t words16 = c->table_slots * (sizeof(Voxel) / 16);
+    k_table_clear<<<c->sm_count * 8, 256, 0, s>>>(c->d_table, words16);
+    SSM_LAUNCH_CHECK(c);
+    SSM_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(uint32_t), s));
+    return SSM_OK;
+}
+
+int launch_export(ssm_ctx* c, Voxel* d_out, uint32_t max_out, cudaStream_t s)
+{
+    SSM_CUDA(cudaMemsetAsync(c->d_counters + 3, 0, sizeof(uint32_t), s));
+    k_export<<<c->sm_count * 8, 256, 0, s>>>(c->d_table, c->table_slots, d_out, c->d_counters, max_out);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+}  // namespace ssm

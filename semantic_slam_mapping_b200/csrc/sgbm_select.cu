@@ -1,0 +1,244 @@
+// sgbm_select.cu -- disparity selection and post-filters, sm_100a.
+//
+// Replaces the tail of cv::StereoSGBM (called from /root/reference src/stereo.cpp:30):
+//   k_select      winner-take-all (first minimum), uniqueness test, parabola sub-pixel with C-truncating
+//                 division, and the right-image disparity disp2 via atomicMin on a packed (cost, column) key
+//   k_lrcheck     left-right consistency (A-6); also writes the always-invalid columns [0, D)
+//   k_median3     cv::medianBlur(disp, 3) on int16 with replicate border
+//   k_cc_*        cv::filterSpeckles == connected components under |a-b| <= maxDiff; union-find with atomicMin
+#include "ssm_internal.cuh"
+
+namespace ssm {
+
+// ------------------------------------------------------------------------------------------------
+// WTA: one warp per pixel (b, y, x'), lanes own 2*NR consecutive disparities of S.
+// ------------------------------------------------------------------------------------------------
+template <int NR>
+__global__ void __launch_bounds__(256) k_select(const uint16_t* __restrict__ S, int16_t* __restrict__ disp_raw,
+                                                uint32_t* __restrict__ disp2key, int W, int H, int D, int uniq,
+                                                size_t total /* B*H*W1 */)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t pix = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pix >= total) return;
+    const int W1 = W - D;
+    const int xp = (int)(pix % W1);
+    const size_t row = pix / W1;  // b*H + y
+    const uint16_t* Sp = S + pix * D;
+    const int d0 = lane * 2 * NR;
+    const bool active = d0 < D;
+
+    uint32_t v[2 * NR];
+    uint32_t key = 0xffffffffu;
+    if (active) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(Sp + d0);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const uint32_t w = src[r];
+            v[2 * r] = w & 0xffffu;
+            v[2 * r + 1] = w >> 16;
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * NR; ++i) key = min(key, (v[i] << 16) | (uint32_t)(d0 + i));  // first minimum wins ties
+    }
+    key = __reduce_min_sync(0xffffffffu, key);
+    const int minS = (int)(key >> 16), best = (int)(key & 0xffffu);
+    bool reject = false;
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 2 * NR; ++i)
+            reject |= ((int)v[i] * (100 - uniq) < minS * 100) && (abs(best - (d0 + i)) > 1);
+    }
+    reject = __any_sync(0xffffffffu, reject);
+    if (lane != 0) return;
+    const int x = xp + D;
+    int out = kInvalidDisp;
+    if (!reject) {
+        // disp2: smallest cost wins, ties keep the larger x (the reference visits x from right to left, strict >)
+        atomicMin(&disp2key[row * W + (x - best)], ((uint32_t)minS << 16) | (uint32_t)(0xffff - x));
+        int d16 = best * kDispScale;
+        if (best > 0 && best < D - 1) {
+            const int sm = Sp[best - 1], sp = Sp[best + 1];
+            const int denom2 = max(sm + sp - 2 * minS, 1);
+            d16 += ((sm - sp) * kDispScale + denom2) / (denom2 * 2);   // truncation toward zero, as in C
+        }
+        out = d16;
+    }
+    disp_raw[row * W + x] = (int16_t)out;
+}
+
+__global__ void __launch_bounds__(256) k_lrcheck(const int16_t* __restrict__ disp_raw, const uint32_t* __restrict__ disp2key,
+                                                 int16_t* __restrict__ disp_lr, int W, int D, int d12, size_t total)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = (int)(idx % W);
+    const size_t rowbase = idx - x;
+    int out = kInvalidDisp;
+    if (x >= D) {
+        const int d1 = disp_raw[idx];
+        out = d1;
+        if (d1 != kInvalidDisp) {
+            const int dlo = d1 >> 4, dhi = (d1 + kDispScale - 1) >> 4;
+            const int xlo = x - dlo, xhi = x - dhi;
+            bool bad_lo = false, bad_hi = false;
+            if (xlo >= 0 && xlo < W) {
+                const uint32_t k = disp2key[rowbase + xlo];
+                if (k != 0xffffffffu) bad_lo = abs((0xffff - (int)(k & 0xffffu)) - xlo - dlo) > d12;
+            }
+            if (xhi >= 0 && xhi < W) {
+                const uint32_t k = disp2key[rowbase + xhi];
+                if (k != 0xffffffffu) bad_hi = abs((0xffff - (int)(k & 0xffffu)) - xhi - dhi) > d12;
+            }
+            if (bad_lo && bad_hi) out = kInvalidDisp;
+        }
+    }
+    disp_lr[idx] = (int16_t)out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 median, replicate border (9-element sorting network, min/max only)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cswap(int& a, int& b)
+{
+    const int lo = min(a, b), hi = max(a, b);
+    a = lo; b = hi;
+}
+__global__ void __launch_bounds__(256) k_median3(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int W, int H,
+                                                 size_t total)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = (int)(idx % W);
+    const size_t r = idx / W;
+    const int y = (int)(r % H);
+    const int16_t* img = src + (r / H) * (size_t)W * H;
+    const int xm = max(x - 1, 0), xq = min(x + 1, W - 1);
+    const int16_t* r0 = img + (size_t)max(y - 1, 0) * W;
+    const int16_t* r1 = img + (size_t)y * W;
+    const int16_t* r2 = img + (size_t)min(y + 1, H - 1) * W;
+    int p0 = r0[xm], p1 = r0[x], p2 = r0[xq], p3 = r1[xm], p4 = r1[x], p5 = r1[xq], p6 = r2[xm], p7 = r2[x], p8 = r2[xq];
+    cswap(p1, p2); cswap(p4, p5); cswap(p7, p8); cswap(p0, p1); cswap(p3, p4); cswap(p6, p7);
+    cswap(p1, p2); cswap(p4, p5); cswap(p7, p8); cswap(p0, p3); cswap(p5, p8); cswap(p4, p7);
+    cswap(p3, p6); cswap(p1, p4); cswap(p2, p5); cswap(p4, p7); cswap(p4, p2); cswap(p6, p4);
+    cswap(p4, p2);
+    dst[idx] = (int16_t)p4;
+}
+
+// ------------------------------------------------------------------------------------------------
+// speckle filter: label = smallest linear index of the component (lock-free union-find)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cc_find(int* label, int x)
+{
+    int p = __ldcg(label + x);   // L2 reads: parents change under concurrent atomicMin hooks
+    while (p != x) {
+        x = p;
+        p = __ldcg(label + x);
+    }
+    return x;
+}
+__device__ __forceinline__ void cc_union(int* label, int a, int b)
+{
+    while (true) {
+        a = cc_find(label, a);
+        b = cc_find(label, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }   // a > b: hook the larger root under the smaller
+        const int old = atomicMin(&label[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+__global__ void __launch_bounds__(256) k_cc_init(const int16_t* __restrict__ img, int* __restrict__ label,
+                                                 int* __restrict__ size, size_t total)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    label[idx] = img[idx] == kInvalidDisp ? -1 : (int)idx;
+    size[idx] = 0;
+}
+__global__ void __launch_bounds__(256) k_cc_merge(const int16_t* __restrict__ img, int* __restrict__ label, int W, int H,
+                                                  int max_diff, size_t total)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int v = img[idx];
+    if (v == kInvalidDisp) return;
+    const int x = (int)(idx % W);
+    const int y = (int)((idx / W) % H);
+    if (x + 1 < W) {
+        const int u = img[idx + 1];
+        if (u != kInvalidDisp && abs(u - v) <= max_diff) cc_union(label, (int)idx, (int)idx + 1);
+    }
+    if (y + 1 < H) {
+        const int u = img[idx + W];
+        if (u != kInvalidDisp && abs(u - v) <= max_diff) cc_union(label, (int)idx, (int)idx + W);
+    }
+}
+__global__ void __launch_bounds__(256) k_cc_count(int* __restrict__ label, int* __restrict__ size, size_t total)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    if (label[idx] < 0) return;
+    const int root = cc_find(label, (int)idx);
+    label[idx] = root;   // path compression; roots are fixed points, so concurrent finds stay correct
+    atomicAdd(&size[root], 1);
+}
+__global__ void __launch_bounds__(256) k_cc_apply(const int16_t* __restrict__ img, const int* __restrict__ label,
+                                                  const int* __restrict__ size, int16_t* __restrict__ out, int max_size,
+                                                  size_t total)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int v = img[idx];
+    const int l = label[idx];
+    if (l >= 0 && size[cc_find(const_cast<int*>(label), l)] <= max_size) v = kInvalidDisp;
+    out[idx] = (int16_t)v;
+}
+
+// ------------------------------------------------------------------------------------------------
+int launch_select(ssm_ctx* c, int B, cudaStream_t s)
+{
+    const DevParams& p = c->dp;
+    const size_t npix = (size_t)B * p.H * p.W;
+    SSM_CUDA(cudaMemsetAsync(c->d_disp2key, 0xff, npix * sizeof(uint32_t), s));
+    const size_t total = (size_t)B * p.H * p.W1;
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((total + wpb - 1) / wpb);
+    const int nr = p.D <= 64 ? 1 : (p.D <= 128 ? 2 : (p.D <= 256 ? 4 : 8));
+    switch (nr) {
+        case 1: k_select<1><<<grid, wpb * 32, 0, s>>>(c->d_S, c->d_disp_raw, c->d_disp2key, p.W, p.H, p.D, p.uniq, total); break;
+        case 2: k_select<2><<<grid, wpb * 32, 0, s>>>(c->d_S, c->d_disp_raw, c->d_disp2key, p.W, p.H, p.D, p.uniq, total); break;
+        case 4: k_select<4><<<grid, wpb * 32, 0, s>>>(c->d_S, c->d_disp_raw, c->d_disp2key, p.W, p.H, p.D, p.uniq, total); break;
+        default: k_select<8><<<grid, wpb * 32, 0, s>>>(c->d_S, c->d_disp_raw, c->d_disp2key, p.W, p.H, p.D, p.uniq, total); break;
+    }
+    SSM_LAUNCH_CHECK(c);
+    k_lrcheck<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(c->d_disp_raw, c->d_disp2key, c->d_disp_lr, p.W, p.D, p.d12, npix);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+int launch_post(ssm_ctx* c, int B, int16_t* d_out, cudaStream_t s)
+{
+    const DevParams& p = c->dp;
+    const size_t npix = (size_t)B * p.H * p.W;
+    const unsigned grid = (unsigned)((npix + 255) / 256);
+    k_median3<<<grid, 256, 0, s>>>(c->d_disp_lr, c->d_disp_med, p.W, p.H, npix);
+    SSM_LAUNCH_CHECK(c);
+    if (p.speckle_win <= 0) {
+        SSM_CUDA(cudaMemcpyAsync(d_out, c->d_disp_med, npix * sizeof(int16_t), cudaMemcpyDeviceToDevice, s));
+        return SSM_OK;
+    }
+    // labels are linear indices over the whole batch, but merges never cross a frame (x/y bounds are per frame)
+    k_cc_init<<<grid, 256, 0, s>>>(c->d_disp_med, c->d_cc_label, c->d_cc_size, npix);
+    SSM_LAUNCH_CHECK(c);
+    k_cc_merge<<<grid, 256, 0, s>>>(c->d_disp_med, c->d_cc_label, p.W, p.H, p.speckle_diff, npix);
+    SSM_LAUNCH_CHECK(c);
+    k_cc_count<<<grid, 256, 0, s>>>(c->d_cc_label, c->d_cc_size, npix);
+    SSM_LAUNCH_CHECK(c);
+    k_cc_apply<<<grid, 256, 0, s>>>(c->d_disp_med, c->d_cc_label, c->d_cc_size, d_out, p.speckle_win, npix);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+}  // namespace ssm

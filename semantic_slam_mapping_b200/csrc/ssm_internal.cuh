@@ -1,0 +1,177 @@
+// ssm_internal.cuh -- shared declarations of libssm.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/ssm.h"
+
+namespace ssm {
+
+// ---------------------------------------------------------------------------------------------
+// constants of the SGBM chain
+// ---------------------------------------------------------------------------------------------
+constexpr int kDispScale = 16;
+constexpr int kInvalidDisp = -16;           // (minDisparity - 1) * 16 with minDisparity == 0
+constexpr int kMaxCost = 32767;
+constexpr uint32_t kBig = 0xC000u;          // "+inf" for 16-bit path costs held in unsigned lanes
+constexpr uint32_t kBigW = 0xC000C000u;
+constexpr uint32_t kSatW = 0x7fff7fffu;     // saturation bound of S, both lanes
+
+// ---------------------------------------------------------------------------------------------
+// voxel record: one 128-byte line per voxel (key + all accumulators), SURVEY section 8a-K8
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxVotes = 20;
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr double kFixScale = 16777216.0;    // 2^24 fixed-point metres for centroid sums
+struct __align__(128) Voxel {
+    unsigned long long key;                 // 21-bit biased i | j<<21 | k<<42
+    unsigned long long sx, sy, sz;          // sum of llrint(coord * 2^24), two's complement
+    uint32_t n;                             // points fused
+    uint32_t sr, sg, sb;                    // colour sums
+    uint32_t votes[kMaxVotes];              // label histogram
+};
+static_assert(sizeof(Voxel) == 128, "voxel record must be one 128-byte line");
+
+__host__ __device__ inline uint64_t pack_key(int i, int j, int k)
+{
+    return (uint64_t)(uint32_t)(i + (1 << 20)) | ((uint64_t)(uint32_t)(j + (1 << 20)) << 21) |
+           ((uint64_t)(uint32_t)(k + (1 << 20)) << 42);
+}
+__host__ __device__ inline void unpack_key(uint64_t key, int& i, int& j, int& k)
+{
+    i = (int)(key & 0x1FFFFF) - (1 << 20);
+    j = (int)((key >> 21) & 0x1FFFFF) - (1 << 20);
+    k = (int)((key >> 42) & 0x1FFFFF) - (1 << 20);
+}
+__host__ __device__ inline uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+// spatial ownership: 8^3-voxel bricks hashed over the ranks
+constexpr int kBrickShift = 3;
+__host__ __device__ inline int voxel_owner(int i, int j, int k, int nranks)
+{
+    if (nranks <= 1) return 0;
+    const uint64_t b = pack_key(i >> kBrickShift, j >> kBrickShift, k >> kBrickShift);
+    return (int)(mix64(b ^ 0x9E3779B97F4A7C15ull) % (uint64_t)nranks);
+}
+
+// device-side constants of one context
+struct DevParams {
+    int W, H, D, W1;
+    int bs, P1, P2, uniq, d12, ftzero, speckle_win, speckle_diff;
+    double cx, cy, fx, fy, baseline, scale, roix, roiy, roiz, max_depth_units;
+    float inv_leaf;
+    int num_labels;
+    uint32_t palette[SSM_MAX_LABELS];       // b | g<<8 | r<<16
+    uint32_t drop_mask, dynamic_mask;
+    int dilate_radius, colour_source;
+};
+
+struct Point {                              // routed between ranks, 20 bytes
+    float x, y, z;
+    uint32_t rgba;                          // 0x00RRGGBB
+    uint32_t label;
+};
+
+}  // namespace ssm
+
+// ---------------------------------------------------------------------------------------------
+// the context
+// ---------------------------------------------------------------------------------------------
+struct ssm_ctx {
+    ssm_params p;
+    ssm::DevParams dp;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[SSM_STAGE_COUNT + 1] = {};
+    float stage_ms[SSM_STAGE_COUNT] = {};
+    bool ev_recorded = false;
+
+    int cap_w = 0, cap_h = 0, cap_b = 0;
+    // stereo
+    uint8_t *d_left = nullptr, *d_right = nullptr;   // [B][H][W] staging for host calls
+    uint4 *d_recL = nullptr, *d_recR = nullptr;      // [B][H][W] prefilter + BT records
+    uint16_t* d_hs = nullptr;                        // [B][H][W1][D] horizontal window sums (aliases d_S)
+    int16_t* d_C = nullptr;                          // [B][H][W1][D] matching cost
+    uint16_t* d_S = nullptr;                         // [B][H][W1][D] aggregated cost
+    int16_t *d_disp_raw = nullptr, *d_disp_lr = nullptr, *d_disp_med = nullptr, *d_disp = nullptr;  // [B][H][W]
+    uint32_t* d_disp2key = nullptr;                  // [B][H][W]
+    int32_t *d_cc_label = nullptr, *d_cc_size = nullptr;  // speckle filter
+    // mapper
+    uint16_t* d_depth = nullptr;                     // [B][H][W]
+    uint8_t *d_label = nullptr, *d_mask = nullptr;   // [B][H][W]
+    uint8_t *d_sem = nullptr, *d_rgb = nullptr;      // [B][H][W][3] staging
+    double* d_pose = nullptr;                        // [B][16]
+    int32_t* d_min_disp = nullptr;                   // [B]
+    ssm::Point* d_points = nullptr;                  // [B*H*W] compacted cloud
+    uint32_t* d_blk_count = nullptr;                 // per-block counts / offsets for ordered compaction
+    uint32_t* d_counters = nullptr;                  // [8] misc device counters (0: n_points, 1: n_voxels, 2: overflow flag, 3: export count)
+    // voxel hash
+    ssm::Voxel* d_table = nullptr;
+    uint64_t table_slots = 0;
+    // multi-GPU
+    void* comm = nullptr;                            // ncclComm_t
+    int rank = 0, nranks = 1;
+    ssm::Point *d_send = nullptr, *d_recv = nullptr; // routing buffers
+    uint32_t *d_send_counts = nullptr;               // [nranks] + offsets
+    size_t route_cap = 0;
+};
+
+namespace ssm {
+
+void set_error(const std::string& s);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define SSM_CUDA(expr)                                                      \
+    do {                                                                    \
+        cudaError_t _e = (expr);                                            \
+        if (_e != cudaSuccess) return ::ssm::cuda_fail(_e, #expr);          \
+    } while (0)
+
+#define SSM_LAUNCH_CHECK(ctx)                                               \
+    do {                                                                    \
+        (ctx)->launches++;                                                  \
+        cudaError_t _e = cudaGetLastError();                                \
+        if (_e != cudaSuccess) return ::ssm::cuda_fail(_e, "kernel launch"); \
+    } while (0)
+
+// stage launchers (each returns an ssm_status); all buffers densely packed
+int launch_prefilter(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, cudaStream_t s);
+int launch_cost_volume(ssm_ctx* c, int B, cudaStream_t s);
+int launch_aggregate(ssm_ctx* c, int B, cudaStream_t s);
+int launch_select(ssm_ctx* c, int B, cudaStream_t s);
+int launch_post(ssm_ctx* c, int B, int16_t* d_out, cudaStream_t s);
+int launch_depth(ssm_ctx* c, int B, const int16_t* d_disp, uint16_t* d_depth, cudaStream_t s);
+int launch_labels_mask(ssm_ctx* c, int B, const uint8_t* d_sem, cudaStream_t s);
+int launch_points(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t* d_sem, const uint8_t* d_rgb,
+                  const double* d_pose, bool fuse_into_map, cudaStream_t s);
+int launch_fuse_points(ssm_ctx* c, const Point* d_pts, const uint32_t* d_count, uint32_t max_count, cudaStream_t s);
+int launch_map_clear(ssm_ctx* c, cudaStream_t s);
+int launch_export(ssm_ctx* c, Voxel* d_out, uint32_t max_out, cudaStream_t s);
+int launch_route_bucket(ssm_ctx* c, uint32_t max_points, cudaStream_t s);   // d_points -> d_send grouped by owner rank
+int route_and_fuse(ssm_ctx* c, cudaStream_t s);   // multi-GPU: bucket by owner, NCCL all-to-all, fuse received
+
+// packed 16x2 helpers --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dup16(int v) { return (uint32_t)(v & 0xffff) * 0x10001u; }
+__device__ __forceinline__ uint32_t fsl16(uint32_t lo_word, uint32_t hi_word)
+{   // elements (lo_word.hi, hi_word.lo): shifts the pair stream by one 16-bit element towards higher d
+    return __funnelshift_l(lo_word, hi_word, 16);
+}
+__device__ __forceinline__ uint32_t fsr16(uint32_t lo_word, uint32_t hi_word)
+{   // elements (lo_word.hi, hi_word.lo) as well, expressed with the right funnel
+    return __funnelshift_r(lo_word, hi_word, 16);
+}
+
+}  // namespace ssm

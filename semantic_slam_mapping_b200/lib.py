@@ -1,0 +1,268 @@
+"""ctypes binding of libssm.so (include/ssm.h).  No CPU fallback: loading or creating a context fails
+loudly when the CUDA extension or a B200 is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .params import CParams, Params
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libssm.so")
+
+STAGES = ("cost", "aggregate", "select", "post", "points", "fuse")
+
+# every symbol include/ssm.h declares (tests/test_boundary.py checks the .so exports all of them)
+SYMBOLS = [
+    "ssm_default_params", "ssm_create", "ssm_destroy", "ssm_last_error", "ssm_version", "ssm_kernel_launches",
+    "ssm_set_stage_timing", "ssm_stage_time_ms", "ssm_sgbm", "ssm_sgbm_batch_device", "ssm_debug_copy_volume",
+    "ssm_disparity_to_depth", "ssm_semantic_motion_fuse", "ssm_generate_point_cloud", "ssm_map_integrate_frame",
+    "ssm_map_integrate_points", "ssm_map_clear", "ssm_map_size", "ssm_map_export", "ssm_map_save_pcd",
+    "ssm_pipeline_batch_device", "ssm_pipeline_batch_host", "ssm_synchronize", "ssm_comm_get_unique_id",
+    "ssm_comm_init", "ssm_comm_destroy", "ssm_voxel_owner",
+]
+
+
+class SsmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libssm error {code}: {msg}")
+        self.code = code
+
+
+class _VoxelExport(C.Structure):
+    _fields_ = [("ijk", C.c_void_p), ("xyz", C.c_void_p), ("rgba", C.c_void_p), ("label", C.c_void_p),
+                ("count", C.c_void_p), ("votes", C.c_void_p)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree libssm.so.  Raises if it has not been built (`python -m semantic_slam_mapping_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} is missing: build it with __graft_entry__.build(); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i, sz, u64 = C.c_void_p, C.c_int, C.c_size_t, C.c_uint64
+    L.ssm_default_params.argtypes = [C.POINTER(CParams)]
+    L.ssm_default_params.restype = None
+    L.ssm_create.argtypes = [C.POINTER(CParams), i, C.POINTER(vp)]
+    L.ssm_destroy.argtypes = [vp]
+    L.ssm_destroy.restype = None
+    L.ssm_last_error.restype = C.c_char_p
+    L.ssm_version.restype = C.c_char_p
+    L.ssm_kernel_launches.argtypes = [vp]
+    L.ssm_kernel_launches.restype = u64
+    L.ssm_set_stage_timing.argtypes = [vp, i]
+    L.ssm_stage_time_ms.argtypes = [vp, i, C.POINTER(C.c_float)]
+    L.ssm_sgbm.argtypes = [vp, vp, vp, i, i, sz, vp, sz]
+    L.ssm_sgbm_batch_device.argtypes = [vp, i, vp, vp, i, i, vp, vp]
+    L.ssm_debug_copy_volume.argtypes = [vp, i, i, vp, sz]
+    L.ssm_disparity_to_depth.argtypes = [vp, vp, i, i, sz, vp, sz]
+    L.ssm_semantic_motion_fuse.argtypes = [vp, vp, i, i, sz, vp, sz]
+    L.ssm_generate_point_cloud.argtypes = [vp, vp, vp, vp, i, i, vp, vp, vp, vp, i, C.POINTER(i)]
+    L.ssm_map_integrate_frame.argtypes = [vp, vp, vp, vp, i, i, vp]
+    L.ssm_map_integrate_points.argtypes = [vp, vp, vp, vp, i]
+    L.ssm_map_clear.argtypes = [vp]
+    L.ssm_map_size.argtypes = [vp, C.POINTER(u64)]
+    L.ssm_map_export.argtypes = [vp, C.POINTER(_VoxelExport), u64, i, C.POINTER(u64)]
+    L.ssm_map_save_pcd.argtypes = [vp, C.c_char_p]
+    L.ssm_pipeline_batch_device.argtypes = [vp, i, vp, vp, vp, vp, vp, i, i, vp, vp]
+    L.ssm_pipeline_batch_host.argtypes = [vp, i, vp, vp, vp, vp, vp, i, i, vp, C.POINTER(u64)]
+    L.ssm_synchronize.argtypes = [vp]
+    L.ssm_comm_get_unique_id.argtypes = [vp]
+    L.ssm_comm_init.argtypes = [vp, vp, i, i]
+    L.ssm_comm_destroy.argtypes = [vp]
+    L.ssm_voxel_owner.argtypes = [C.c_int32, C.c_int32, C.c_int32, i]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """numpy array -> host pointer; torch tensor / int -> raw (device) pointer."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.data_ptr())
+
+
+def voxel_owner(i: int, j: int, k: int, nranks: int) -> int:
+    return int(load().ssm_voxel_owner(i, j, k, nranks))
+
+
+class Context:
+    """One `ssm_ctx` (one per GPU)."""
+
+    def __init__(self, params: Params | None = None, device: int = 0):
+        self.params = params or Params()
+        self._L = load()
+        self._h = C.c_void_p()
+        cp = self.params.c()
+        self._check(self._L.ssm_create(C.byref(cp), device, C.byref(self._h)))
+        self.device = device
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise SsmError(rc, self._L.ssm_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.ssm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- stereo.h ---------------------------------------------------------------------------------------
+    def sgbm(self, left: np.ndarray, right: np.ndarray) -> np.ndarray:
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        if left.ndim != 2 or left.shape != right.shape:
+            raise ValueError("left/right must be 2-D uint8 images of equal shape")
+        h, w = left.shape
+        disp = np.empty((h, w), np.int16)
+        self._check(self._L.ssm_sgbm(self._h, _ptr(left), _ptr(right), w, h, w, _ptr(disp), w * 2))
+        return disp
+
+    def sgbm_batch_device(self, d_left, d_right, d_disp, batch: int, w: int, h: int, stream=None):
+        self._check(self._L.ssm_sgbm_batch_device(self._h, batch, _ptr(d_left), _ptr(d_right), w, h, _ptr(d_disp),
+                                                  C.c_void_p(stream) if stream else None))
+
+    def debug_volume(self, which: str, w: int, h: int, batch_index: int = 0) -> np.ndarray:
+        D = self.params.num_disparities
+        ids = {"C": 0, "S": 1, "disp_raw": 2, "disp_median": 3}
+        shape = (h, w - D, D) if which in ("C", "S") else (h, w)
+        out = np.empty(shape, np.int16)
+        self._check(self._L.ssm_debug_copy_volume(self._h, ids[which], batch_index, _ptr(out), out.nbytes))
+        return out
+
+    # -- glue ---------------------------------------------------------------------------------------------
+    def disparity_to_depth(self, disp: np.ndarray) -> np.ndarray:
+        disp = np.ascontiguousarray(disp, np.int16)
+        h, w = disp.shape
+        depth = np.empty((h, w), np.uint16)
+        self._check(self._L.ssm_disparity_to_depth(self._h, _ptr(disp), w, h, w * 2, _ptr(depth), w * 2))
+        return depth
+
+    # -- mapper.h -----------------------------------------------------------------------------------------
+    def semantic_motion_fuse(self, semantic_bgr: np.ndarray) -> np.ndarray:
+        sem = np.ascontiguousarray(semantic_bgr, np.uint8)
+        h, w = sem.shape[:2]
+        mask = np.empty((h, w), np.uint8)
+        self._check(self._L.ssm_semantic_motion_fuse(self._h, _ptr(sem), w, h, w * 3, _ptr(mask), w))
+        return mask
+
+    def generate_point_cloud(self, depth, semantic_bgr, rgb_bgr, T):
+        depth = np.ascontiguousarray(depth, np.uint16)
+        sem = np.ascontiguousarray(semantic_bgr, np.uint8)
+        rgb = np.ascontiguousarray(rgb_bgr, np.uint8)
+        T = np.ascontiguousarray(T, np.float64).reshape(16)
+        h, w = depth.shape
+        n = h * w
+        xyz = np.empty((n, 3), np.float32)
+        rgba = np.empty(n, np.uint32)
+        label = np.empty(n, np.uint8)
+        k = C.c_int(0)
+        self._check(self._L.ssm_generate_point_cloud(self._h, _ptr(depth), _ptr(sem), _ptr(rgb), w, h, _ptr(T), _ptr(xyz),
+                                                     _ptr(rgba), _ptr(label), n, C.byref(k)))
+        return {"xyz": xyz[: k.value].copy(), "rgba": rgba[: k.value].copy(), "label": label[: k.value].copy()}
+
+    def map_integrate_frame(self, depth, semantic_bgr, rgb_bgr, T):
+        depth = np.ascontiguousarray(depth, np.uint16)
+        sem = np.ascontiguousarray(semantic_bgr, np.uint8)
+        rgb = np.ascontiguousarray(rgb_bgr, np.uint8)
+        T = np.ascontiguousarray(T, np.float64).reshape(16)
+        h, w = depth.shape
+        self._check(self._L.ssm_map_integrate_frame(self._h, _ptr(depth), _ptr(sem), _ptr(rgb), w, h, _ptr(T)))
+
+    def map_integrate_points(self, xyz, rgba, label):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        rgba = np.ascontiguousarray(rgba, np.uint32)
+        label = np.ascontiguousarray(label, np.uint8)
+        self._check(self._L.ssm_map_integrate_points(self._h, _ptr(xyz), _ptr(rgba), _ptr(label), xyz.shape[0]))
+
+    def map_clear(self):
+        self._check(self._L.ssm_map_clear(self._h))
+
+    def map_size(self) -> int:
+        n = C.c_uint64(0)
+        self._check(self._L.ssm_map_size(self._h, C.byref(n)))
+        return int(n.value)
+
+    def map_export(self, sorted: bool = True) -> dict:
+        n = self.map_size()
+        L = self.params.num_labels
+        out = {
+            "ijk": np.empty((n, 3), np.int32), "xyz": np.empty((n, 3), np.float32), "rgba": np.empty(n, np.uint32),
+            "label": np.empty(n, np.uint8), "count": np.empty(n, np.uint32), "votes": np.empty((n, L), np.uint32),
+        }
+        ex = _VoxelExport(*[_ptr(out[k]) for k in ("ijk", "xyz", "rgba", "label", "count", "votes")])
+        got = C.c_uint64(0)
+        self._check(self._L.ssm_map_export(self._h, C.byref(ex), n, 1 if sorted else 0, C.byref(got)))
+        assert got.value == n
+        return out
+
+    def map_save_pcd(self, path: str):
+        self._check(self._L.ssm_map_save_pcd(self._h, path.encode()))
+
+    # -- whole path ---------------------------------------------------------------------------------------
+    def pipeline_batch_host(self, left, right, semantic, rgb, poses, want_disp: bool = False):
+        """left/right [B][H][W] u8, semantic/rgb [B][H][W][3] u8, poses [B][4][4] f64 (host or pinned)."""
+        b, h, w = left.shape
+        disp = np.empty((b, h, w), np.int16) if want_disp else None
+        nvox = C.c_uint64(0)
+        self._check(self._L.ssm_pipeline_batch_host(self._h, b, _ptr(left), _ptr(right), _ptr(semantic), _ptr(rgb), _ptr(poses),
+                                                    w, h, _ptr(disp), C.byref(nvox)))
+        return int(nvox.value), disp
+
+    def pipeline_batch_device(self, d_left, d_right, d_sem, d_rgb, d_poses, batch: int, w: int, h: int, d_disp=None, stream=None):
+        self._check(self._L.ssm_pipeline_batch_device(self._h, batch, _ptr(d_left), _ptr(d_right), _ptr(d_sem), _ptr(d_rgb),
+                                                      _ptr(d_poses), w, h, _ptr(d_disp), C.c_void_p(stream) if stream else None))
+
+    def synchronize(self):
+        self._check(self._L.ssm_synchronize(self._h))
+
+    # -- instrumentation ------------------------------------------------------------------------------------
+    def kernel_launches(self) -> int:
+        return int(self._L.ssm_kernel_launches(self._h))
+
+    def set_stage_timing(self, on: bool):
+        self._check(self._L.ssm_set_stage_timing(self._h, 1 if on else 0))
+
+    def stage_times_ms(self) -> dict:
+        out = {}
+        for i, name in enumerate(STAGES):
+            ms = C.c_float(0)
+            self._check(self._L.ssm_stage_time_ms(self._h, i, C.byref(ms)))
+            out[name] = float(ms.value)
+        return out
+
+    # -- multi-GPU --------------------------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> np.ndarray:
+        L = load()
+        uid = np.zeros(128, np.uint8)
+        rc = L.ssm_comm_get_unique_id(_ptr(uid))
+        if rc != 0:
+            raise SsmError(rc, L.ssm_last_error().decode())
+        return uid
+
+    def comm_init(self, unique_id: np.ndarray, rank: int, nranks: int):
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        self._check(self._L.ssm_comm_init(self._h, _ptr(uid), rank, nranks))

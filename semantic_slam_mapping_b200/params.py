@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 from dataclasses import dataclass, field
 
-SSM_MAX_LABELS = 32
+SSM_MAX_LABELS = 20
 LABEL_UNKNOWN = 255
 
 SEGNET12_NAMES = ["sky", "building", "pole", "road_marking", "road", "pavement", "tree", "sign_symbol",

@@ -1,0 +1,137 @@
+"""-m gpu parity tests of the mapper half and the whole path vs the CPU oracle."""
+import numpy as np
+import pytest
+
+import oracle
+from semantic_slam_mapping_b200 import Context, Params, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _mp(p: Params):
+    return oracle.MapParams(cx=p.cx, cy=p.cy, fx=p.fx, fy=p.fy, baseline=p.baseline, scale=p.scale, roix=p.roix,
+                            roiy=p.roiy, roiz=p.roiz, max_distance=p.max_distance, palette_bgr=list(p.palette_bgr),
+                            drop_mask=p.drop_mask, dynamic_mask=p.dynamic_mask, dilate_iterations=p.dilate_iterations,
+                            colour_source=p.colour_source)
+
+
+def _op(p: Params):
+    return oracle.SgbmParams(num_disparities=p.num_disparities)
+
+
+def _frame(H, W, D, seed, p):
+    L, R, _ = synth.stereo_pair(H, W, D, seed)
+    _, sem = synth.label_mask(H, W, p.num_labels, seed, cell=16)
+    rgb = np.repeat(L[..., None], 3, axis=-1)
+    return L, R, sem, rgb
+
+
+def _compare_maps(got, want, tol=1e-5):
+    assert got["ijk"].shape == want["ijk"].shape
+    assert (got["ijk"] == want["ijk"]).all()
+    assert (got["count"] == want["count"]).all()
+    assert (got["votes"] == want["votes"]).all()
+    assert (got["label"] == want["label"]).all()
+    assert (got["rgba"] == want["rgba"]).all()
+    ref = want["centroid_d"]
+    err = np.abs(got["xyz"].astype(np.float64) - ref)
+    assert (err <= tol * np.maximum(np.abs(ref), 1.0)).all()      # 1e-5 relative (absolute below 1 m)
+    err32 = np.abs(got["xyz"].astype(np.float64) - want["centroid"].astype(np.float64))
+    assert (err32 <= 1e-4 * np.maximum(np.abs(ref), 1.0)).all()   # PCL-style fp32 sequential sums, looser
+
+
+def test_depth_mask_cloud_bit_exact():
+    H, W, D = 120, 400, 64
+    p = Params(num_disparities=D, max_width=W, max_height=H)
+    mp = _mp(p)
+    L, R, sem, rgb = _frame(H, W, D, 3, p)
+    disp = oracle.sgbm(L, R, _op(p))
+    T = synth.poses(4, 1)[3]
+    with Context(p) as ctx:
+        depth = ctx.disparity_to_depth(disp)
+        assert (depth == oracle.disparity_to_depth(disp, mp)).all()
+        assert (ctx.semantic_motion_fuse(sem) == oracle.moving_mask(sem, mp)).all()
+        pc = ctx.generate_point_cloud(depth, sem, rgb, T)
+    want = oracle.generate_point_cloud(depth, sem, rgb, mp, T)
+    assert len(want["xyz"]) > 1000
+    assert pc["xyz"].shape == want["xyz"].shape
+    assert (pc["xyz"].view(np.uint32) == want["xyz"].view(np.uint32)).all()   # fp32 coordinates bit for bit
+    assert (pc["rgba"] == want["rgba"]).all() and (pc["label"] == want["label"]).all()
+
+
+def test_semantic_colour_variant_and_unknown_colours():
+    H, W, D = 60, 200, 32
+    p = Params(num_disparities=D, max_width=W, max_height=H, colour_source=1)
+    mp = _mp(p)
+    rng = np.random.default_rng(0)
+    depth = rng.integers(0, 45000, (H, W)).astype(np.uint16)
+    _, sem = synth.label_mask(H, W, 12, 5, cell=8)
+    sem[rng.random((H, W)) < 0.05] = (1, 2, 3)   # colours outside the palette -> label 255, still mapped
+    rgb = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    with Context(p) as ctx:
+        pc = ctx.generate_point_cloud(depth, sem, rgb, np.eye(4))
+    want = oracle.generate_point_cloud(depth, sem, rgb, mp, np.eye(4))
+    assert (pc["xyz"].view(np.uint32) == want["xyz"].view(np.uint32)).all()
+    assert (pc["rgba"] == want["rgba"]).all() and (pc["label"] == want["label"]).all()
+    assert (pc["label"] == 255).any()
+
+
+@pytest.mark.parametrize("leaf", [0.1, 0.05, 0.02])
+def test_voxel_fusion_counts_votes_exact(leaf):
+    H, W, D, n = 96, 320, 64, 4
+    p = Params(num_disparities=D, max_width=W, max_height=H, resolution=leaf, map_capacity=1 << 18)
+    mp = _mp(p)
+    poses = synth.poses(n, 2)
+    vm = oracle.VoxelMap(leaf, p.num_labels)
+    with Context(p) as ctx:
+        for i in range(n):
+            L, R, sem, rgb = _frame(H, W, D, 40 + i, p)
+            depth = oracle.disparity_to_depth(oracle.sgbm(L, R, _op(p)), mp)
+            ctx.map_integrate_frame(depth, sem, rgb, poses[i])
+            pc = oracle.generate_point_cloud(depth, sem, rgb, mp, poses[i])
+            vm.insert(pc["xyz"], pc["rgba"], pc["label"])
+        assert ctx.map_size() == len(vm)
+        got = ctx.map_export(sorted=True)
+        # idempotent clear + explicit-cloud integration gives the same table
+        ctx.map_clear()
+        assert ctx.map_size() == 0
+    want = vm.export()
+    assert want["count"].sum() > 5000
+    _compare_maps(got, want)
+
+
+def test_whole_path_batch_host_vs_oracle(tmp_path):
+    H, W, D, B = 96, 320, 64, 3
+    p = Params(num_disparities=D, max_width=W, max_height=H, max_batch=B, resolution=0.05, map_capacity=1 << 18)
+    mp = _mp(p)
+    seq = synth.sequence(B, H, W, D, 12, seed=3)
+    vm = oracle.VoxelMap(p.resolution, p.num_labels)
+    disps = []
+    for i in range(B):
+        d = oracle.sgbm(seq["left"][i], seq["right"][i], _op(p))
+        disps.append(d)
+        depth = oracle.disparity_to_depth(d, mp)
+        pc = oracle.generate_point_cloud(depth, seq["semantic"][i], seq["rgb"][i], mp, seq["pose"][i])
+        vm.insert(pc["xyz"], pc["rgba"], pc["label"])
+    with Context(p) as ctx:
+        nvox, disp = ctx.pipeline_batch_host(seq["left"], seq["right"], seq["semantic"], seq["rgb"], seq["pose"], want_disp=True)
+        got = ctx.map_export()
+        path = str(tmp_path / "map.pcd")
+        ctx.map_save_pcd(path)
+        assert ctx.kernel_launches() > 0
+    assert int((disp != np.stack(disps)).sum()) == 0
+    assert nvox == len(vm)
+    _compare_maps(got, vm.export())
+    head = open(path, "rb").read(200).decode("ascii", "ignore")
+    assert "FIELDS x y z rgba" in head and f"POINTS {nvox}" in head
+
+
+def test_table_full_is_reported():
+    from semantic_slam_mapping_b200 import SsmError
+    p = Params(num_disparities=32, max_width=200, max_height=60, resolution=0.02, map_capacity=1024)
+    rng = np.random.default_rng(1)
+    xyz = rng.uniform(-20, 20, (20000, 3)).astype(np.float32)
+    with Context(p) as ctx:
+        with pytest.raises(SsmError) as e:
+            ctx.map_integrate_points(xyz, np.zeros(20000, np.uint32), np.zeros(20000, np.uint8))
+        assert e.value.code == -4

@@ -1,0 +1,114 @@
+"""-m gpu parity tests of the stereo half: CUDA path (through the C ABI) vs the CPU oracle and the cv2 goldens."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from semantic_slam_mapping_b200 import Context, Params, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(D, W, H, **kw):
+    return Params(num_disparities=D, max_width=W, max_height=H, **kw)
+
+
+def _oparams(p: Params):
+    return oracle.SgbmParams(num_disparities=p.num_disparities, block_size=p.block_size, p1=p.p1, p2=p.p2,
+                             disp12_max_diff=p.disp12_max_diff, pre_filter_cap=p.pre_filter_cap,
+                             uniqueness_ratio=p.uniqueness_ratio, speckle_window_size=p.speckle_window_size,
+                             speckle_range=p.speckle_range)
+
+
+@pytest.mark.parametrize("H,W,D,seed", [(48, 96, 32, 1), (64, 160, 48, 2), (100, 300, 80, 3), (120, 400, 128, 4),
+                                         (37, 53, 16, 8), (70, 350, 256, 9)])
+def test_stages_bit_exact_vs_oracle(H, W, D, seed):
+    L, R, _ = synth.stereo_pair(H, W, D, seed)
+    p = _params(D, W, H)
+    want, vols = oracle.sgbm(L, R, _oparams(p), want_volumes=True)
+    with Context(p) as ctx:
+        got = ctx.sgbm(L, R)
+        C = ctx.debug_volume("C", W, H)
+        S = ctx.debug_volume("S", W, H)
+        raw = ctx.debug_volume("disp_raw", W, H)
+        med = ctx.debug_volume("disp_median", W, H)
+    assert int((C != vols["C"]).sum()) == 0, "matching cost"
+    assert int((S != vols["S"]).sum()) == 0, "aggregated cost"
+    assert int((raw != vols["disp_raw"]).sum()) == 0, "WTA / uniqueness / sub-pixel / L-R check"
+    assert int((med != vols["disp_median"]).sum()) == 0, "median"
+    assert int((got != want).sum()) == 0, "speckle filter / final disparity"
+
+
+def test_small_goldens_from_cv2(golden_dir):
+    z = np.load(os.path.join(golden_dir, "sgbm_small.npz"))
+    names = sorted({k.split("/")[0] for k in z.files})
+    for n in names:
+        D, bs, uniq, spw, spr, d12, cap = [int(v) for v in z[f"{n}/params"]]
+        L, R = z[f"{n}/left"], z[f"{n}/right"]
+        p = _params(D, L.shape[1], L.shape[0], block_size=bs, p1=4 * bs * bs, p2=32 * bs * bs, uniqueness_ratio=uniq,
+                    speckle_window_size=spw, speckle_range=spr, disp12_max_diff=d12, pre_filter_cap=cap)
+        with Context(p) as ctx:
+            got = ctx.sgbm(L, R)
+        assert int((got != z[f"{n}/disp"]).sum()) == 0, n
+
+
+def test_kitti_d128_golden_from_cv2(golden_dir):
+    z = np.load(os.path.join(golden_dir, "sgbm_kitti_d128.npz"))
+    L, R, _ = synth.stereo_pair(376, 1241, 128, 0)
+    with Context(_params(128, 1241, 376)) as ctx:
+        got = ctx.sgbm(L, R)
+    assert got.shape == (376, 1241) and got.dtype == np.int16
+    assert int((got != z["disp"]).sum()) == 0
+
+
+def test_reference_default_d80_full_frame():
+    """The reference's own setting (src/stereo.cpp:18: 80 disparities) at KITTI size, vs the oracle."""
+    L, R, _ = synth.stereo_pair(376, 1241, 80, 21)
+    p = _params(80, 1241, 376)
+    want = oracle.sgbm(L, R, _oparams(p))
+    with Context(p) as ctx:
+        got = ctx.sgbm(L, R)
+    assert int((got != want).sum()) == 0
+
+
+def test_batch_equals_single_frames():
+    import torch
+    H, W, D, B = 96, 320, 64, 5
+    p = _params(D, W, H, max_batch=B)
+    Ls, Rs = zip(*[synth.stereo_pair(H, W, D, 100 + i)[:2] for i in range(B)])
+    dL = torch.from_numpy(np.stack(Ls)).cuda()
+    dR = torch.from_numpy(np.stack(Rs)).cuda()
+    dD = torch.empty((B, H, W), dtype=torch.int16, device="cuda")
+    with Context(p) as ctx:
+        ctx.sgbm_batch_device(dL, dR, dD, B, W, H, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        batch = dD.cpu().numpy()
+        for i in range(B):
+            assert int((ctx.sgbm(Ls[i], Rs[i]) != batch[i]).sum()) == 0
+    op = _oparams(p)
+    assert int((oracle.sgbm(Ls[2], Rs[2], op) != batch[2]).sum()) == 0
+
+
+def test_noise_and_constant_inputs():
+    rng = np.random.default_rng(5)
+    L = rng.integers(0, 256, (60, 200), dtype=np.uint8)
+    R = rng.integers(0, 256, (60, 200), dtype=np.uint8)
+    p = _params(64, 200, 60)
+    with Context(p) as ctx:
+        assert int((ctx.sgbm(L, R) != oracle.sgbm(L, R, _oparams(p))).sum()) == 0
+        flat = np.full((60, 200), 77, np.uint8)
+        assert int((ctx.sgbm(flat, flat) != oracle.sgbm(flat, flat, _oparams(p))).sum()) == 0
+
+
+def test_error_behaviour():
+    from semantic_slam_mapping_b200 import SsmError
+    with pytest.raises(SsmError):
+        Context(Params(num_disparities=24))
+    with pytest.raises(SsmError):
+        Context(Params(block_size=13))
+    with Context(_params(32, 100, 50)) as ctx:
+        with pytest.raises(SsmError):
+            ctx.sgbm(np.zeros((60, 100), np.uint8), np.zeros((60, 100), np.uint8))  # taller than the context
+        with pytest.raises(SsmError):
+            ctx.sgbm(np.zeros((10, 30), np.uint8), np.zeros((10, 30), np.uint8))    # W <= D
