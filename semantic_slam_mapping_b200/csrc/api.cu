@@ -89,15 +89,16 @@ static void free_all(ssm_ctx* c)
                     c->d_recv, c->d_send_counts};
     for (void* q : ptrs)
         if (q) cudaFree(q);
-    for (auto& e : c->ev)
-        if (e) cudaEventDestroy(e);
+    for (auto& set : c->ev)
+        for (auto& e : set)
+            if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 
 // stage timing helpers
 static inline void mark(ssm_ctx* c, int i, cudaStream_t s)
 {
-    if (c->timing) cudaEventRecord(c->ev[i], s);
+    if (c->timing) cudaEventRecord(c->ev[c->ev_set][i], s);
 }
 
 // the stereo half on device buffers: prefilter -> cost volume -> 5-path aggregation -> selection -> post-filters
@@ -133,15 +134,28 @@ static int run_map(ssm_ctx* c, int B, const int16_t* d_disp, const uint8_t* d_se
         if ((rc = launch_points(c, B, c->d_depth, d_sem, d_rgb, d_pose, true, s))) return rc;
     }
     mark(c, 6, s);
-    if (c->timing) c->ev_recorded = true;
+    if (c->timing) {
+        c->ev_used = std::min(c->ev_used + 1, (int)ssm_ctx::kEvSets);
+        c->ev_set = (c->ev_set + 1) % ssm_ctx::kEvSets;
+    }
     return SSM_OK;
 }
 
 static int finish_timing(ssm_ctx* c)
 {
-    if (!c->timing || !c->ev_recorded) return SSM_OK;
-    SSM_CUDA(cudaEventSynchronize(c->ev[SSM_STAGE_COUNT]));
-    for (int i = 0; i < SSM_STAGE_COUNT; ++i) SSM_CUDA(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    // mean per-call stage time over the timed pipeline calls recorded so far
+    if (!c->timing || c->ev_used == 0) return SSM_OK;
+    double acc[SSM_STAGE_COUNT] = {};
+    for (int k = 0; k < c->ev_used; ++k) {
+        const int set = (c->ev_set - 1 - k + 2 * ssm_ctx::kEvSets) % ssm_ctx::kEvSets;
+        SSM_CUDA(cudaEventSynchronize(c->ev[set][SSM_STAGE_COUNT]));
+        for (int i = 0; i < SSM_STAGE_COUNT; ++i) {
+            float ms = 0.f;
+            SSM_CUDA(cudaEventElapsedTime(&ms, c->ev[set][i], c->ev[set][i + 1]));
+            acc[i] += ms;
+        }
+    }
+    for (int i = 0; i < SSM_STAGE_COUNT; ++i) c->stage_ms[i] = (float)(acc[i] / c->ev_used);
     return SSM_OK;
 }
 
@@ -221,7 +235,8 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     A(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (auto& ev : c->ev) A(cudaEventCreate(&ev));
+    for (auto& set : c->ev)
+        for (auto& ev : set) A(cudaEventCreate(&ev));
     A(dalloc(&c->d_left, npix)); A(dalloc(&c->d_right, npix));
     A(dalloc(&c->d_recL, npix)); A(dalloc(&c->d_recR, npix));
     A(dalloc(&c->d_C, ncell)); A(dalloc(&c->d_S, ncell));
@@ -264,12 +279,14 @@ int ssm_set_stage_timing(ssm_ctx* c, int enabled)
 {
     if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
     c->timing = enabled != 0;
+    c->ev_used = 0;
+    c->ev_set = 0;
     return SSM_OK;
 }
 int ssm_stage_time_ms(ssm_ctx* c, int stage, float* ms)
 {
     if (!c || !ms || stage < 0 || stage >= SSM_STAGE_COUNT) return fail(SSM_ERR_INVALID_ARGUMENT, "bad stage");
-    if (!c->timing || !c->ev_recorded) return fail(SSM_ERR_INVALID_ARGUMENT, "stage timing is off or no pipeline call was timed");
+    if (!c->timing || c->ev_used == 0) return fail(SSM_ERR_INVALID_ARGUMENT, "stage timing is off or no pipeline call was timed");
     int rc = finish_timing(c);   // waits for the last timed pipeline call
     if (rc) return rc;
     *ms = c->stage_ms[stage];

@@ -95,9 +95,12 @@ struct ssm_ctx {
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
     bool timing = false;
-    cudaEvent_t ev[SSM_STAGE_COUNT + 1] = {};
+    // stage timing: a ring of event sets, one per timed pipeline call; read back (averaged) by ssm_stage_time_ms
+    static constexpr int kEvSets = 64;
+    cudaEvent_t ev[kEvSets][SSM_STAGE_COUNT + 1] = {};
+    int ev_set = 0;          // set used by the call being enqueued
+    int ev_used = 0;         // sets recorded since the last ssm_set_stage_timing(1)
     float stage_ms[SSM_STAGE_COUNT] = {};
-    bool ev_recorded = false;
 
     int cap_w = 0, cap_h = 0, cap_b = 0;
     // stereo
