@@ -149,14 +149,33 @@ __device__ __forceinline__ void cc_union(int* label, int a, int b)
         a = old;
     }
 }
-__global__ void __launch_bounds__(256) k_cc_init(const int16_t* __restrict__ img, int* __restrict__ label,
-                                                 int* __restrict__ size, size_t total)
+__device__ __forceinline__ bool cc_conn(int a, int b, int max_diff)
 {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    label[idx] = img[idx] == kInvalidDisp ? -1 : (int)idx;
-    size[idx] = 0;
+    return a != kInvalidDisp && b != kInvalidDisp && abs(a - b) <= max_diff;
 }
+// initial label = start of the pixel's horizontal run inside its 32-pixel segment (one warp per segment)
+__global__ void __launch_bounds__(256) k_cc_init(const int16_t* __restrict__ img, int* __restrict__ label,
+                                                 int* __restrict__ size, int W, int max_diff, int segs_per_row,
+                                                 size_t total_segs)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t seg = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (seg >= total_segs) return;
+    const size_t row = seg / segs_per_row;
+    const int x0 = (int)(seg % segs_per_row) * 32, x = x0 + lane;
+    const size_t idx = row * W + x;
+    const int v = x < W ? (int)img[idx] : kInvalidDisp;
+    const int vl = __shfl_up_sync(0xffffffffu, v, 1);
+    const bool head = v != kInvalidDisp && !(lane > 0 && cc_conn(v, vl, max_diff));
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    if (x < W) {
+        const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+        label[idx] = v == kInvalidDisp ? -1 : (int)(row * W + x0 + start);
+        size[idx] = 0;
+    }
+}
+// unions: across segment boundaries in a row, and between rows -- skipping a vertical edge whenever the
+// left neighbour's vertical edge plus the two horizontal edges already connect the same pair
 __global__ void __launch_bounds__(256) k_cc_merge(const int16_t* __restrict__ img, int* __restrict__ label, int W, int H,
                                                   int max_diff, size_t total)
 {
@@ -166,23 +185,40 @@ __global__ void __launch_bounds__(256) k_cc_merge(const int16_t* __restrict__ im
     if (v == kInvalidDisp) return;
     const int x = (int)(idx % W);
     const int y = (int)((idx / W) % H);
-    if (x + 1 < W) {
-        const int u = img[idx + 1];
-        if (u != kInvalidDisp && abs(u - v) <= max_diff) cc_union(label, (int)idx, (int)idx + 1);
-    }
-    if (y + 1 < H) {
-        const int u = img[idx + W];
-        if (u != kInvalidDisp && abs(u - v) <= max_diff) cc_union(label, (int)idx, (int)idx + W);
+    const int vl = x > 0 ? (int)img[idx - 1] : kInvalidDisp;
+    const bool cl = cc_conn(v, vl, max_diff);
+    if (cl && (x & 31) == 0) cc_union(label, (int)idx, (int)idx - 1);
+    if (y > 0) {
+        const int vu = img[idx - W];
+        if (cc_conn(v, vu, max_diff)) {
+            bool skip = false;
+            if (cl) {
+                const int vul = img[idx - W - 1];
+                skip = cc_conn(vl, vul, max_diff) && cc_conn(vul, vu, max_diff);
+            }
+            if (!skip) cc_union(label, (int)idx, (int)idx - W);
+        }
     }
 }
-__global__ void __launch_bounds__(256) k_cc_count(int* __restrict__ label, int* __restrict__ size, size_t total)
+// component sizes, only as far as the decision "size <= max_size" needs them: one atomic per run of equal roots
+// inside a warp, and none once the counter is already past the threshold
+__global__ void __launch_bounds__(256) k_cc_count(int* __restrict__ label, int* __restrict__ size, int max_size, size_t total)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    if (label[idx] < 0) return;
-    const int root = cc_find(label, (int)idx);
-    label[idx] = root;   // path compression; roots are fixed points, so concurrent finds stay correct
-    atomicAdd(&size[root], 1);
+    const int lane = threadIdx.x & 31;
+    int root = -1;
+    if (idx < total && label[idx] >= 0) {
+        root = cc_find(label, (int)idx);
+        label[idx] = root;   // path compression; roots are fixed points, so concurrent finds stay correct
+    }
+    const int rp = __shfl_up_sync(0xffffffffu, root, 1);
+    const bool head = lane == 0 || root != rp;
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    if (root >= 0 && head) {
+        const uint32_t after = lane == 31 ? 0u : (heads >> (lane + 1));
+        const int run = after ? __ffs(after) : 32 - lane;
+        if (__ldcg(size + root) <= max_size) atomicAdd(&size[root], run);
+    }
 }
 __global__ void __launch_bounds__(256) k_cc_apply(const int16_t* __restrict__ img, const int* __restrict__ label,
                                                   const int* __restrict__ size, int16_t* __restrict__ out, int max_size,
@@ -230,11 +266,14 @@ int launch_post(ssm_ctx* c, int B, int16_t* d_out, cudaStream_t s)
         return SSM_OK;
     }
     // labels are linear indices over the whole batch, but merges never cross a frame (x/y bounds are per frame)
-    k_cc_init<<<grid, 256, 0, s>>>(c->d_disp_med, c->d_cc_label, c->d_cc_size, npix);
+    const int segs_per_row = (p.W + 31) / 32;
+    const size_t total_segs = (size_t)B * p.H * segs_per_row;
+    k_cc_init<<<(unsigned)((total_segs + 7) / 8), 256, 0, s>>>(c->d_disp_med, c->d_cc_label, c->d_cc_size, p.W, p.speckle_diff,
+                                                             segs_per_row, total_segs);
     SSM_LAUNCH_CHECK(c);
     k_cc_merge<<<grid, 256, 0, s>>>(c->d_disp_med, c->d_cc_label, p.W, p.H, p.speckle_diff, npix);
     SSM_LAUNCH_CHECK(c);
-    k_cc_count<<<grid, 256, 0, s>>>(c->d_cc_label, c->d_cc_size, npix);
+    k_cc_count<<<grid, 256, 0, s>>>(c->d_cc_label, c->d_cc_size, p.speckle_win, npix);
     SSM_LAUNCH_CHECK(c);
     k_cc_apply<<<grid, 256, 0, s>>>(c->d_disp_med, c->d_cc_label, c->d_cc_size, d_out, p.speckle_win, npix);
     SSM_LAUNCH_CHECK(c);
