@@ -107,8 +107,9 @@ int ssm_sgbm(ssm_ctx* ctx, const uint8_t* left, const uint8_t* right, int w, int
 /* Device, async.  Densely packed [batch][h][w] buffers. */
 int ssm_sgbm_batch_device(ssm_ctx* ctx, int batch, const uint8_t* d_left, const uint8_t* d_right, int w, int h,
                           int16_t* d_disp, void* stream);
-/* Debug/parity taps (device buffers, valid after ssm_sgbm*, batch item 0..): matching cost C and
- * aggregated cost S, both [batch][h][w-D][D] int16; raw WTA disparity before median/speckle. */
+/* Debug/parity taps (device buffers, valid after ssm_sgbm*, batch item 0..): matching cost C and the
+ * aggregated cost S_f = sat(L0+L1+L2+L3) (the fifth path is added in registers only), both
+ * [batch][h][w-D][D] int16; raw WTA disparity after the L-R check; disparity after the median. */
 int ssm_debug_copy_volume(ssm_ctx* ctx, int which /*0=C,1=S,2=disp_raw,3=disp_median*/, int batch_index,
                           void* host_dst, size_t bytes);
 

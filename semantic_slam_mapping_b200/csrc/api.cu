@@ -37,6 +37,7 @@ static int validate(const ssm_params& p)
     if (p.num_labels < 1 || p.num_labels > SSM_MAX_LABELS) return fail(SSM_ERR_INVALID_ARGUMENT, "num_labels must be in [1, 20]");
     if (!(p.resolution > 0) || !(p.scale > 0) || !(p.fx != 0) || !(p.fy != 0))
         return fail(SSM_ERR_INVALID_ARGUMENT, "resolution, scale, fx, fy must be non-zero/positive");
+    if (p.uniqueness_ratio > 100) return fail(SSM_ERR_INVALID_ARGUMENT, "uniqueness_ratio must be <= 100");
     if (p.dilate_iterations < 0 || p.dilate_iterations > 8) return fail(SSM_ERR_INVALID_ARGUMENT, "dilate_iterations in [0, 8]");
     if (p.map_capacity < 1024) return fail(SSM_ERR_INVALID_ARGUMENT, "map_capacity must be >= 1024 slots");
     return SSM_OK;
@@ -84,7 +85,7 @@ static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<
 static void free_all(ssm_ctx* c)
 {
     void* ptrs[] = {c->d_left, c->d_right, c->d_recL, c->d_recR, c->d_C, c->d_S, c->d_disp_raw, c->d_disp_lr, c->d_disp_med,
-                    c->d_disp, c->d_disp2key, c->d_cc_label, c->d_cc_size, c->d_depth, c->d_label, c->d_mask, c->d_sem,
+                    c->d_disp, c->d_disp2key, c->d_wta_rec, c->d_uniq_thr, c->d_cc_label, c->d_cc_size, c->d_depth, c->d_label, c->d_mask, c->d_sem,
                     c->d_rgb, c->d_pose, c->d_min_disp, c->d_points, c->d_blk_count, c->d_counters, c->d_table, c->d_send,
                     c->d_recv, c->d_send_counts};
     for (void* q : ptrs)
@@ -242,7 +243,7 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
     A(dalloc(&c->d_C, ncell)); A(dalloc(&c->d_S, ncell));
     c->d_hs = c->d_S;   // horizontal sums are dead once C exists; S is written afterwards
     A(dalloc(&c->d_disp_raw, npix)); A(dalloc(&c->d_disp_lr, npix)); A(dalloc(&c->d_disp_med, npix)); A(dalloc(&c->d_disp, npix));
-    A(dalloc(&c->d_disp2key, npix)); A(dalloc(&c->d_cc_label, npix)); A(dalloc(&c->d_cc_size, npix));
+    A(dalloc(&c->d_disp2key, npix)); A(dalloc(&c->d_wta_rec, npix)); A(dalloc(&c->d_uniq_thr, (size_t)32768)); A(dalloc(&c->d_cc_label, npix)); A(dalloc(&c->d_cc_size, npix));
     A(dalloc(&c->d_depth, npix)); A(dalloc(&c->d_label, npix)); A(dalloc(&c->d_mask, npix));
     A(dalloc(&c->d_sem, npix * 3)); A(dalloc(&c->d_rgb, npix * 3));
     A(dalloc(&c->d_pose, (size_t)16 * c->cap_b)); A(dalloc(&c->d_min_disp, (size_t)c->cap_b));
@@ -254,6 +255,19 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
         return cuda_fail(e, "ssm_create allocation");
     }
     fill_dev_params(c, c->cap_w, c->cap_h);
+    {   // uniqueness: S[d]*(100-u) < minS*100  <=>  S[d] < thr[minS]   (exact integer threshold, capped at 32768)
+        std::vector<uint32_t> thr(32768);
+        const int u = c->dp.uniq;
+        for (int ms = 0; ms < 32768; ++ms) {
+            long long t = u >= 100 ? (ms > 0 ? 32768 : 0) : ((long long)ms * 100 + (100 - u) - 1) / (100 - u);
+            thr[ms] = (uint32_t)std::min<long long>(t, 32768);
+        }
+        if (cudaMemcpy(c->d_uniq_thr, thr.data(), thr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            free_all(c);
+            delete c;
+            return cuda_fail(cudaGetLastError(), "uniqueness table upload");
+        }
+    }
     rc = launch_map_clear(c, c->stream);
     if (rc == SSM_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "ssm_create");
     if (rc) {

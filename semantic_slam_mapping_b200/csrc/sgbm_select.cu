@@ -1,71 +1,13 @@
 // sgbm_select.cu -- disparity selection and post-filters, sm_100a.
 //
 // Replaces the tail of cv::StereoSGBM (called from /root/reference src/stereo.cpp:30):
-//   k_select      winner-take-all (first minimum), uniqueness test, parabola sub-pixel with C-truncating
-//                 division, and the right-image disparity disp2 via atomicMin on a packed (cost, column) key
+//   (winner-take-all itself is fused into the horizontal sweep, sgbm_hsweep.cu)
 //   k_lrcheck     left-right consistency (A-6); also writes the always-invalid columns [0, D)
 //   k_median3     cv::medianBlur(disp, 3) on int16 with replicate border
 //   k_cc_*        cv::filterSpeckles == connected components under |a-b| <= maxDiff; union-find with atomicMin
 #include "ssm_internal.cuh"
 
 namespace ssm {
-
-// ------------------------------------------------------------------------------------------------
-// WTA: one warp per pixel (b, y, x'), lanes own 2*NR consecutive disparities of S.
-// ------------------------------------------------------------------------------------------------
-template <int NR>
-__global__ void __launch_bounds__(256) k_select(const uint16_t* __restrict__ S, int16_t* __restrict__ disp_raw,
-                                                uint32_t* __restrict__ disp2key, int W, int H, int D, int uniq,
-                                                size_t total /* B*H*W1 */)
-{
-    const int lane = threadIdx.x & 31;
-    const size_t pix = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (pix >= total) return;
-    const int W1 = W - D;
-    const int xp = (int)(pix % W1);
-    const size_t row = pix / W1;  // b*H + y
-    const uint16_t* Sp = S + pix * D;
-    const int d0 = lane * 2 * NR;
-    const bool active = d0 < D;
-
-    uint32_t v[2 * NR];
-    uint32_t key = 0xffffffffu;
-    if (active) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(Sp + d0);
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const uint32_t w = src[r];
-            v[2 * r] = w & 0xffffu;
-            v[2 * r + 1] = w >> 16;
-        }
-#pragma unroll
-        for (int i = 0; i < 2 * NR; ++i) key = min(key, (v[i] << 16) | (uint32_t)(d0 + i));  // first minimum wins ties
-    }
-    key = __reduce_min_sync(0xffffffffu, key);
-    const int minS = (int)(key >> 16), best = (int)(key & 0xffffu);
-    bool reject = false;
-    if (active) {
-#pragma unroll
-        for (int i = 0; i < 2 * NR; ++i)
-            reject |= ((int)v[i] * (100 - uniq) < minS * 100) && (abs(best - (d0 + i)) > 1);
-    }
-    reject = __any_sync(0xffffffffu, reject);
-    if (lane != 0) return;
-    const int x = xp + D;
-    int out = kInvalidDisp;
-    if (!reject) {
-        // disp2: smallest cost wins, ties keep the larger x (the reference visits x from right to left, strict >)
-        atomicMin(&disp2key[row * W + (x - best)], ((uint32_t)minS << 16) | (uint32_t)(0xffff - x));
-        int d16 = best * kDispScale;
-        if (best > 0 && best < D - 1) {
-            const int sm = Sp[best - 1], sp = Sp[best + 1];
-            const int denom2 = max(sm + sp - 2 * minS, 1);
-            d16 += ((sm - sp) * kDispScale + denom2) / (denom2 * 2);   // truncation toward zero, as in C
-        }
-        out = d16;
-    }
-    disp_raw[row * W + x] = (int16_t)out;
-}
 
 __global__ void __launch_bounds__(256) k_lrcheck(const int16_t* __restrict__ disp_raw, const uint32_t* __restrict__ disp2key,
                                                  int16_t* __restrict__ disp_lr, int W, int D, int d12, size_t total)
@@ -238,17 +180,8 @@ int launch_select(ssm_ctx* c, int B, cudaStream_t s)
     const DevParams& p = c->dp;
     const size_t npix = (size_t)B * p.H * p.W;
     SSM_CUDA(cudaMemsetAsync(c->d_disp2key, 0xff, npix * sizeof(uint32_t), s));
-    const size_t total = (size_t)B * p.H * p.W1;
-    const int wpb = 8;
-    const unsigned grid = (unsigned)((total + wpb - 1) / wpb);
-    const int nr = p.D <= 64 ? 1 : (p.D <= 128 ? 2 : (p.D <= 256 ? 4 : 8));
-    switch (nr) {
-        case 1: k_select<1><<<grid, wpb * 32, 0, s>>>(c->d_S, c->d_disp_raw, c->d_disp2key, p.W, p.H, p.D, p.uniq, total); break;
-        case 2: k_select<2><<<grid, wpb * 32, 0, s>>>(c->d_S, c->d_disp_raw, c->d_disp2key, p.W, p.H, p.D, p.uniq, total); break;
-        case 4: k_select<4><<<grid, wpb * 32, 0, s>>>(c->d_S, c->d_disp_raw, c->d_disp2key, p.W, p.H, p.D, p.uniq, total); break;
-        default: k_select<8><<<grid, wpb * 32, 0, s>>>(c->d_S, c->d_disp_raw, c->d_disp2key, p.W, p.H, p.D, p.uniq, total); break;
-    }
-    SSM_LAUNCH_CHECK(c);
+    int rc = launch_wta_finalize(c, B, s);
+    if (rc) return rc;
     k_lrcheck<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(c->d_disp_raw, c->d_disp2key, c->d_disp_lr, p.W, p.D, p.d12, npix);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;

@@ -111,6 +111,8 @@ struct ssm_ctx {
     uint16_t* d_S = nullptr;                         // [B][H][W1][D] aggregated cost
     int16_t *d_disp_raw = nullptr, *d_disp_lr = nullptr, *d_disp_med = nullptr, *d_disp = nullptr;  // [B][H][W]
     uint32_t* d_disp2key = nullptr;                  // [B][H][W]
+    uint64_t* d_wta_rec = nullptr;                   // [B][H][W1] winner-take-all records (minS, S[best-1], S[best+1], best, reject)
+    uint32_t* d_uniq_thr = nullptr;                  // [32768] uniqueness threshold per minS
     int32_t *d_cc_label = nullptr, *d_cc_size = nullptr;  // speckle filter
     // mapper
     uint16_t* d_depth = nullptr;                     // [B][H][W]
@@ -155,6 +157,8 @@ int launch_prefilter(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, cu
 int launch_cost_volume(ssm_ctx* c, int B, cudaStream_t s);
 int launch_aggregate(ssm_ctx* c, int B, cudaStream_t s);
 int launch_select(ssm_ctx* c, int B, cudaStream_t s);
+int launch_hsweep(ssm_ctx* c, int B, cudaStream_t s);
+int launch_wta_finalize(ssm_ctx* c, int B, cudaStream_t s);
 int launch_post(ssm_ctx* c, int B, int16_t* d_out, cudaStream_t s);
 int launch_depth(ssm_ctx* c, int B, const int16_t* d_disp, uint16_t* d_depth, cudaStream_t s);
 int launch_labels_mask(ssm_ctx* c, int B, const uint8_t* d_sem, cudaStream_t s);

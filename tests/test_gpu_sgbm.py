@@ -30,11 +30,11 @@ def test_stages_bit_exact_vs_oracle(H, W, D, seed):
     with Context(p) as ctx:
         got = ctx.sgbm(L, R)
         C = ctx.debug_volume("C", W, H)
-        S = ctx.debug_volume("S", W, H)
+        Sf = ctx.debug_volume("S", W, H)   # the device keeps S_f = sat(L0+L1+L2+L3); the final S lives in registers only
         raw = ctx.debug_volume("disp_raw", W, H)
         med = ctx.debug_volume("disp_median", W, H)
     assert int((C != vols["C"]).sum()) == 0, "matching cost"
-    assert int((S != vols["S"]).sum()) == 0, "aggregated cost"
+    assert int((Sf != vols["Sf"]).sum()) == 0, "aggregated cost (four forward paths)"
     assert int((raw != vols["disp_raw"]).sum()) == 0, "WTA / uniqueness / sub-pixel / L-R check"
     assert int((med != vols["disp_median"]).sum()) == 0, "median"
     assert int((got != want).sum()) == 0, "speckle filter / final disparity"
