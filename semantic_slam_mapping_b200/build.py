@@ -49,5 +49,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+
+def build_host_driver(out: str | None = None) -> str:
+    """g++ the C++ host layer (host/host.cpp) + tests/cpp/host_driver.cpp against libssm.so (no GPU needed to build)."""
+    build()
+    root = os.path.dirname(HERE)
+    out = out or os.path.join(HERE, "build", "host_driver")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cuda_lib = os.environ.get("CUDA_LIB", "/usr/local/cuda/lib64")
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-pthread", os.path.join(root, "tests", "cpp", "host_driver.cpp"),
+           os.path.join(HERE, "host", "host.cpp"), "-L" + HERE, "-lssm", "-Wl,-rpath," + HERE, "-L" + cuda_lib,
+           "-Wl,-rpath," + cuda_lib, "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
