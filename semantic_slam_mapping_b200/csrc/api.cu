@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of include/ssm.h: context, buffers, host/device entry points, the batched path.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -227,6 +228,17 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
     c->p = *p;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    c->max_cluster = 16;
+    {
+        const char* e = getenv("SSM_LEGACY_VERTICAL");
+        c->force_legacy_vertical = e && e[0] == '1';
+        const char* lc = getenv("SSM_LEGACY_COST");
+        c->force_legacy_cost = lc && lc[0] == '1';
+        const char* m = getenv("SSM_MAX_CLUSTER");
+        if (m && atoi(m) > 0) c->max_cluster = atoi(m);
+        const char* n = getenv("SSM_MIN_CLUSTER");
+        if (n && atoi(n) > 0) c->min_cluster = atoi(n);
+    }
     c->cap_w = p->max_width; c->cap_h = p->max_height; c->cap_b = p->max_batch;
     const size_t npix = (size_t)c->cap_w * c->cap_h * c->cap_b;
     const size_t ncell = (size_t)(c->cap_w - p->num_disparities) * c->cap_h * c->cap_b * p->num_disparities;

@@ -23,6 +23,7 @@ struct AggrArgs {
     int first;     // 1: S = L, 0: S = sat(S + L)
     int npaths;    // per frame
     int total;     // npaths * batch
+    uint32_t one;  // 1 (opaque to the compiler, see PathLane)
 };
 
 template <int NR>
@@ -52,7 +53,8 @@ __global__ void __launch_bounds__(256) k_aggr_path(AggrArgs a)
     }
     const int d0 = lane * 2 * NR;
     const bool active = d0 < a.D;
-    const uint32_t P1w = (uint32_t)a.P1 * 0x10001u;
+    const PathLane pl = make_path_lane(lane, a.one);
+    const uint32_t P1w = (uint32_t)a.P1 * 0x10001u, P2w = (uint32_t)a.P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)a.P2) * 0x10001u;
     const size_t frame = (size_t)b * a.H * a.W1;
     const ptrdiff_t stride = ((ptrdiff_t)dy * a.W1 + dx) * a.D;
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(256) k_aggr_path(AggrArgs a)
     if (active) load_words<NR>(a.C + off, Cw);
     for (int t = 0; t < len; ++t) {
         if (active && t + 1 < len) load_words<NR>(a.C + off + stride, Cn);   // prefetch the next pixel of the path
-        m = path_step<NR>(L, Cw, m, P1w, (uint32_t)a.P2, lane);
+        m = path_step<NR>(L, Cw, m, P1w, P2w, pl);
         if (active) {
             if (a.first) {
                 store_words<NR>(a.S + off, L);
@@ -87,9 +89,14 @@ int launch_aggregate(ssm_ctx* c, int B, cudaStream_t s)
 {
     const DevParams& p = c->dp;
     AggrArgs a;
-    a.C = c->d_C; a.S = c->d_S; a.W1 = p.W1; a.H = p.H; a.D = p.D; a.P1 = p.P1; a.P2 = p.P2;
+    a.C = c->d_C; a.S = c->d_S; a.W1 = p.W1; a.H = p.H; a.D = p.D; a.P1 = p.P1; a.P2 = p.P2; a.one = 1u;
     const int nr = p.D <= 64 ? 1 : (p.D <= 128 ? 2 : (p.D <= 256 ? 4 : 8));
-    // the three top-down directions walk one warp per path; the horizontal pair + WTA is k_hsweep
+    // preferred: all three top-down directions in one cluster launch (sgbm_vertical.cu)
+    bool done = false;
+    int rc = launch_vertical(c, B, s, &done);
+    if (rc) return rc;
+    if (done) return launch_hsweep(c, B, s);
+    // fallback: the three top-down directions walk one warp per path; the horizontal pair + WTA is k_hsweep
     const int order[3] = {2, 1, 3};
     for (int i = 0; i < 3; ++i) {
         a.dir = order[i];

@@ -7,6 +7,8 @@
 //                 shared-memory tile, then the bs-wide horizontal window sum hs[y][x'][d] (A-2, A-3 first half)
 //   k_vsum        bs-tall running window sum down the rows -> C[y][x'][d] int16 (A-3 second half)
 // All arithmetic is integer and bit-exact with the oracle.
+#include <algorithm>
+
 #include "ssm_internal.cuh"
 
 namespace ssm {
@@ -203,6 +205,215 @@ __global__ void __launch_bounds__(256) k_vsum(const uint16_t* __restrict__ hs, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1 fused: pixel cost + horizontal window sum + vertical window sum -> C, one launch, no intermediate volume.
+//
+// CTA = (tile of TX output columns, band of rows, frame); TX * D/2 = 2048 packed words, 256 threads.  The CTA
+// marches down its band (plus `radius` rows above and below); per image row:
+//   phase 0  the row's prefilter records -> shared tables: right image {lo, hi, v} x {Sobel, raw} as s16x2 words in
+//            two copies (element-aligned and shifted by one, so that the pair (d, d+1) <-> right pixels
+//            (x-d, x-d-1) is ONE aligned 32-bit word for every x and d), left image 8 pre-combined words per pixel
+//   phase 1  Birchfield-Tomasi cost of (pixel, word) items, 16 lanes per pixel on consecutive words (bank-conflict
+//            free: the two copies sit 16 banks apart), 4 VIADDMNMX.S16x2 + 1 VIMNMX per channel and word;
+//            negated operands are formed as K - x by IMAD (FMA pipe) instead of being loaded  -> pix tile (shared)
+//   phase 2  thread = (8 consecutive columns, one word): 18 loads feed eight bs-wide window sums held in registers;
+//            vertical running sum C_run += hs - hs[bs rows ago] against a bs-row ring of hs in shared memory;
+//            one coalesced store of C per column once the window is full
+// Clamping is relative to the valid region [0, W1) x [0, H); rows beyond the image edge re-use
+// the previous row's window sums.  All lanes stay < 2^15, so 32-bit adds never carry between the halves.
+// ------------------------------------------------------------------------------------------------
+constexpr int kKb = 0x4000;                 // bias that keeps K - x positive in both halves
+constexpr uint32_t kKw = 0x40004000u;
+
+// compile-time geometry of one tile width (TX * D / 2 = 2048 packed words per CTA row)
+template <int TX>
+struct CostGeom {
+    static constexpr int D = 4096 / TX;
+    static constexpr int WPP = D / 2;                        // packed words per pixel
+    static constexpr int NE = TX + 2 * kMaxR;                // pixels whose cost a CTA computes per row (at most)
+    static constexpr int NR_MAX = NE + D - 1;                // right-image pixels it needs
+    static constexpr int TW = ((NE + D) / 2 + 2 + 31) / 32 * 32 + 16;   // words per (quantity, copy) table, = 16 mod 32
+    static constexpr int PS = WPP + 16;                      // pix row stride in words
+    static constexpr int LPP = WPP < 16 ? WPP : 16;          // lanes per pixel in phase 1
+    static constexpr int WPL = WPP / LPP;                    // words per lane
+    static constexpr int RPT = (NR_MAX + 255) / 256;         // right records per thread
+    static constexpr int LPT = (NE + 255) / 256;             // left records per thread
+    static constexpr size_t smem_words(int bs) { return (size_t)12 * TW + NE * 8 + (size_t)NE * PS + (size_t)bs * TX * WPP; }
+};
+
+template <int TX, int RAD /* block_size / 2, or -1: run-time radius (slow generic window sums) */>
+__global__ void __launch_bounds__(256, 2) k_cost_fused(const uint4* __restrict__ recL, const uint4* __restrict__ recR,
+                                                       int16_t* __restrict__ C, int W, int H, int radius, int band_rows,
+                                                       uint32_t mone /* 0xffffffff, opaque: x * mone + K is one IMAD */)
+{
+    using G = CostGeom<TX>;
+    constexpr int D = G::D, WPP = G::WPP, TW = G::TW, PS = G::PS, LPP = G::LPP, WPL = G::WPL;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int W1 = W - D;
+    const int t0 = blockIdx.x * TX, b = blockIdx.z;
+    const int y0 = blockIdx.y * band_rows, y1 = min(H, y0 + band_rows);
+    const int e_lo = max(t0 - radius, 0), e_hi = min(t0 + TX - 1 + radius, W1 - 1);
+    const int n_e = e_hi - e_lo + 1;
+    const int n_r = n_e + D - 1;                     // right-image pixels [e_lo + 1, e_hi + D], stored reversed
+    const int bs = 2 * radius + 1;
+
+    uint32_t* Rt = smem;                             // [6 quantities][2 copies][TW]
+    uint32_t* Lt = Rt + 12 * TW;                     // [NE][8]
+    uint32_t* pix = Lt + G::NE * 8;                  // [NE][PS]
+    uint32_t* ring = pix + G::NE * PS;               // [bs][TX][WPP]
+    for (int i = threadIdx.x; i < bs * TX * WPP; i += 256) ring[i] = 0u;
+
+    // phase-2 identity: 8 consecutive columns x one word; (TX / 8) groups x WPP words = 256 threads exactly
+    const int cgp = threadIdx.x / WPP;
+    const int w2 = threadIdx.x - cgp * WPP;
+    const int c0 = t0 + cgp * 8;                     // first of my 8 output columns
+    const bool interior = RAD >= 0 && c0 - RAD >= 0 && c0 + 7 + RAD <= W1 - 1;
+    uint32_t crun[8], hs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { crun[i] = 0u; hs[i] = 0u; }
+
+    // records of the next fresh row, prefetched one row ahead
+    uint4 qr[G::RPT], ql[G::LPT];
+    auto fetch = [&](int r) {
+        const size_t rowbase = ((size_t)b * H + r) * W;
+#pragma unroll
+        for (int k = 0; k < G::RPT; ++k) {
+            const int i = threadIdx.x + k * 256;
+            if (i < n_r) qr[k] = recR[rowbase + (e_hi + D - i)];
+        }
+#pragma unroll
+        for (int k = 0; k < G::LPT; ++k) {
+            const int i = threadIdx.x + k * 256;
+            if (i < n_e) ql[k] = recL[rowbase + (e_lo + i + D)];
+        }
+    };
+    const int j_begin = y0 - radius, j_end = y1 + radius;
+    fetch(min(max(j_begin, 0), H - 1));
+
+    int slot = 0, prev_r = -1;
+    for (int j = j_begin; j < j_end; ++j) {
+        const int r = min(max(j, 0), H - 1);
+        const bool fresh = r != prev_r;              // CTA-uniform
+        prev_r = r;
+        if (fresh) {
+            // ---- phase 0: tables from the prefetched records.  element i of the reversed right tables <-> pixel e_hi + D - i
+#pragma unroll
+            for (int k = 0; k < G::RPT; ++k) {
+                const int i = threadIdx.x + k * 256;
+                if (i < n_r) {
+                    const uint4 q = qr[k];
+                    // record: x = v | (-v) << 16, y = lo | (-hi) << 16 (Sobel); z, w the same for the raw channel
+                    const uint16_t val[6] = {(uint16_t)(q.y & 0xffffu), (uint16_t)(0u - (q.y >> 16)), (uint16_t)(q.x & 0xffffu),
+                                             (uint16_t)(q.w & 0xffffu), (uint16_t)(0u - (q.w >> 16)), (uint16_t)(q.z & 0xffffu)};
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) {
+                        uint16_t* a0 = reinterpret_cast<uint16_t*>(Rt + (2 * t) * TW);
+                        uint16_t* a1 = reinterpret_cast<uint16_t*>(Rt + (2 * t + 1) * TW);
+                        a0[i] = val[t];
+                        if (i > 0) a1[i - 1] = val[t];
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < G::LPT; ++k) {
+                const int i = threadIdx.x + k * 256;
+                if (i < n_e) {
+                    const uint4 q = ql[k];
+                    // per channel: dup(-u), dup(u - K), dup(-hi), dup(lo - K)
+                    const uint32_t ug = q.x & 0xffffu, nug = q.x >> 16, log_ = q.y & 0xffffu, nhig = q.y >> 16;
+                    const uint32_t ur = q.z & 0xffffu, nur = q.z >> 16, lor = q.w & 0xffffu, nhir = q.w >> 16;
+                    uint4* dst = reinterpret_cast<uint4*>(Lt + i * 8);
+                    dst[0] = make_uint4(nug * 0x10001u, ((ug - kKb) & 0xffffu) * 0x10001u, nhig * 0x10001u, ((log_ - kKb) & 0xffffu) * 0x10001u);
+                    dst[1] = make_uint4(nur * 0x10001u, ((ur - kKb) & 0xffffu) * 0x10001u, nhir * 0x10001u, ((lor - kKb) & 0xffffu) * 0x10001u);
+                }
+            }
+            // the records of the next distinct row travel while this row is processed
+            {
+                const int rn = min(r + 1, H - 1);
+                if (rn != r && j + 1 < j_end) fetch(rn);
+            }
+            __syncthreads();
+            // ---- phase 1: pixel costs of (pixel, lane-in-pixel) items; lane jl takes words jl, jl + LPP, ...
+            const int items = n_e * LPP;
+            for (int it = threadIdx.x; it < items; it += 256) {
+                const int el = it / LPP, jl = it % LPP;
+                const uint4 la = reinterpret_cast<const uint4*>(Lt + el * 8)[0];
+                const uint4 lb = reinterpret_cast<const uint4*>(Lt + el * 8)[1];
+                const int i0 = n_e - 1 - el;             // reversed index of d = 0 at pixel e_lo + el
+                const uint32_t* q = Rt + (i0 & 1) * TW + (i0 >> 1) + jl;
+                uint32_t* out = pix + el * PS + jl;
+#pragma unroll
+                for (int k = 0; k < WPL; ++k) {
+                    const uint32_t loG = q[k * LPP], hiG = q[k * LPP + 2 * TW], vG = q[k * LPP + 4 * TW];
+                    const uint32_t loR = q[k * LPP + 6 * TW], hiR = q[k * LPP + 8 * TW], vR = q[k * LPP + 10 * TW];
+                    const uint32_t nhiG = hiG * mone + kKw, nvG = vG * mone + kKw;   // K - x per half
+                    const uint32_t nhiR = hiR * mone + kKw, nvR = vR * mone + kKw;
+                    // c0 = max(0, u - hiR, loR - u), c1 = max(0, v - hiL, loL - v), cost = min(c0, c1)
+                    const uint32_t g0 = __viaddmax_s16x2(nhiG, la.y, __viaddmax_s16x2(loG, la.x, 0u));
+                    const uint32_t g1 = __viaddmax_s16x2(nvG, la.w, __viaddmax_s16x2(vG, la.z, 0u));
+                    const uint32_t r0 = __viaddmax_s16x2(nhiR, lb.y, __viaddmax_s16x2(loR, lb.x, 0u));
+                    const uint32_t r1 = __viaddmax_s16x2(nvR, lb.w, __viaddmax_s16x2(vR, lb.z, 0u));
+                    const uint32_t cgv = __vmins2(g0, g1), crv = __vmins2(r0, r1);
+                    out[k * LPP] = cgv + ((crv >> 2) & 0x3fff3fffu);
+                }
+            }
+            __syncthreads();
+            // ---- phase 2a: horizontal window sums of my 8 columns (registers)
+            if (c0 < W1) {
+                if constexpr (RAD >= 0) {
+                    uint32_t v[8 + 2 * RAD];
+                    if (interior) {
+                        const uint32_t* src = pix + (c0 - RAD - e_lo) * PS + w2;
+#pragma unroll
+                        for (int i = 0; i < 8 + 2 * RAD; ++i) v[i] = src[i * PS];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8 + 2 * RAD; ++i) {
+                            const int e = min(max(c0 + i - RAD, 0), W1 - 1) - e_lo;
+                            v[i] = pix[e * PS + w2];
+                        }
+                    }
+                    uint32_t acc = 0u;
+#pragma unroll
+                    for (int i = 0; i < 2 * RAD + 1; ++i) acc += v[i];
+                    hs[0] = acc;
+#pragma unroll
+                    for (int c = 1; c < 8; ++c) {
+                        acc = acc + v[c + 2 * RAD] - v[c - 1];
+                        hs[c] = acc;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) hs[c] = 0u;
+                    for (int off = -radius; off <= 7 + radius; ++off) {
+                        const int e = min(max(c0 + off, 0), W1 - 1) - e_lo;
+                        const uint32_t val = pix[e * PS + w2];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (off >= c - radius && off <= c + radius) hs[c] += val;
+                    }
+                }
+            }
+        }
+        // ---- phase 2b: vertical running sum against the ring, output
+        if (c0 < W1) {
+            uint32_t* rg = ring + (slot * TX + cgp * 8) * WPP + w2;
+            const int yout = j - radius;
+            int16_t* dst = C + (((size_t)b * H + max(yout, 0)) * W1 + c0) * D + 2 * w2;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t old = rg[c * WPP];
+                rg[c * WPP] = hs[c];
+                crun[c] = crun[c] + hs[c] - old;
+                if (yout >= y0 && c0 + c < W1) *reinterpret_cast<uint32_t*>(dst + (size_t)c * D) = crun[c];
+            }
+        }
+        slot = slot + 1 == bs ? 0 : slot + 1;
+        // hazards: the next row's tables are written after every thread has left phase 1 (second barrier); the pix
+        // tile is re-written only after the next row's first barrier, which every thread reaches after its phase 2
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 int launch_prefilter(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, cudaStream_t s)
 {
     const DevParams& p = c->dp;
@@ -213,9 +424,40 @@ int launch_prefilter(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, cu
     return SSM_OK;
 }
 
+template <int TX, int RAD>
+static int launch_cost_fused_t(ssm_ctx* c, int B, cudaStream_t s)
+{
+    const DevParams& p = c->dp;
+    const int radius = p.bs / 2;
+    const size_t smem = sizeof(uint32_t) * CostGeom<TX>::smem_words(p.bs);
+    SSM_CUDA(cudaFuncSetAttribute(k_cost_fused<TX, RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // bands: enough CTAs to fill the machine a few times over, but tall enough to amortise the 2*radius halo rows
+    const int tiles = (p.W1 + TX - 1) / TX;
+    int bands = std::max(1, std::min(p.H / 32, (c->sm_count * 8 + tiles * B - 1) / (tiles * B)));
+    const int band_rows = (p.H + bands - 1) / bands;
+    bands = (p.H + band_rows - 1) / band_rows;
+    dim3 grid(tiles, bands, B);
+    k_cost_fused<TX, RAD><<<grid, 256, smem, s>>>(c->d_recL, c->d_recR, c->d_C, p.W, p.H, radius, band_rows, 0xffffffffu);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
 int launch_cost_volume(ssm_ctx* c, int B, cudaStream_t s)
 {
     const DevParams& p = c->dp;
+    if (!c->force_legacy_cost) {
+        // TX * D/2 = 2048 words per CTA row
+        const bool r5 = p.bs == 11;   // the reference's block size gets the compile-time window; others the generic one
+        switch (p.D) {
+            case 16: return r5 ? launch_cost_fused_t<256, 5>(c, B, s) : launch_cost_fused_t<256, -1>(c, B, s);
+            case 32: return r5 ? launch_cost_fused_t<128, 5>(c, B, s) : launch_cost_fused_t<128, -1>(c, B, s);
+            case 64: return r5 ? launch_cost_fused_t<64, 5>(c, B, s) : launch_cost_fused_t<64, -1>(c, B, s);
+            case 128: return r5 ? launch_cost_fused_t<32, 5>(c, B, s) : launch_cost_fused_t<32, -1>(c, B, s);
+            case 256: return r5 ? launch_cost_fused_t<16, 5>(c, B, s) : launch_cost_fused_t<16, -1>(c, B, s);
+            case 512: return r5 ? launch_cost_fused_t<8, 5>(c, B, s) : launch_cost_fused_t<8, -1>(c, B, s);
+            default: break;   // other multiples of 16: the two-kernel path below
+        }
+    }
     const int radius = p.bs / 2;
     const int tw = (kTX + 2 * kMaxR + p.D) / 2 + 4;
     const size_t smem = sizeof(uint32_t) * ((size_t)16 * tw + (kTX + 2 * kMaxR) * 8 + (size_t)(kTX + 2 * kMaxR) * (p.D / 2));

@@ -48,7 +48,7 @@ __device__ __forceinline__ uint32_t pick(const uint32_t (&w)[NR], int idx)
 
 template <int NR>
 __global__ void __launch_bounds__(128) k_hsweep(const int16_t* __restrict__ C, uint16_t* S /* read and written: no restrict */, uint2* __restrict__ rec,
-                                                const uint32_t* __restrict__ uniq_thr, int W1, int D, int P1, int P2, int nrows)
+                                                const uint32_t* __restrict__ uniq_thr, int W1, int D, int P1, int P2, int nrows, uint32_t one)
 {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(128) k_hsweep(const int16_t* __restrict__ C, u
     constexpr int LOG_DPL = NR == 1 ? 1 : (NR == 2 ? 2 : (NR == 4 ? 3 : 4));
     const int d0 = lane * 2 * NR;
     const bool active = d0 < D;
-    const uint32_t P1w = (uint32_t)P1 * 0x10001u;
+    const PathLane pl = make_path_lane(lane, one);
+    const uint32_t P1w = (uint32_t)P1 * 0x10001u, P2w = (uint32_t)P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)P2) * 0x10001u;
     const uint16_t* Crow = reinterpret_cast<const uint16_t*>(C) + (size_t)row * W1 * D + d0;
     uint16_t* Srow = S + (size_t)row * W1 * D + d0;
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(128) k_hsweep(const int16_t* __restrict__ C, u
             for (int j = 0; j < kPF; ++j) {
                 const int x = g * kPF + j;
                 if (x < W1) {
-                    m = path_step<NR>(L, Ca[j], m, P1w, (uint32_t)P2, lane);
+                    m = path_step<NR>(L, Ca[j], m, P1w, P2w, pl);
                     if (active) {
                         uint32_t o[NR];
 #pragma unroll
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(128) k_hsweep(const int16_t* __restrict__ C, u
             for (int j = 0; j < kPF; ++j) {
                 const int x = (g + 1) * kPF + j;
                 if (x < W1) {
-                    m = path_step<NR>(L, Cb[j], m, P1w, (uint32_t)P2, lane);
+                    m = path_step<NR>(L, Cb[j], m, P1w, P2w, pl);
                     if (active) {
                         uint32_t o[NR];
 #pragma unroll
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(128) k_hsweep(const int16_t* __restrict__ C, u
             for (int j = 0; j < kPF; ++j) {
                 const int t = g * kPF + j;
                 if (t < W1) {
-                    m = path_step<NR>(L, Ca[j], m, P1w, (uint32_t)P2, lane);
+                    m = path_step<NR>(L, Ca[j], m, P1w, P2w, pl);
                     wta(Sa[j], W1 - 1 - t);
                 }
             }
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(128) k_hsweep(const int16_t* __restrict__ C, u
             for (int j = 0; j < kPF; ++j) {
                 const int t = (g + 1) * kPF + j;
                 if (t < W1) {
-                    m = path_step<NR>(L, Cb[j], m, P1w, (uint32_t)P2, lane);
+                    m = path_step<NR>(L, Cb[j], m, P1w, P2w, pl);
                     wta(Sb[j], W1 - 1 - t);
                 }
             }
@@ -206,10 +207,10 @@ int launch_hsweep(ssm_ctx* c, int B, cudaStream_t s)
     const unsigned grid = (unsigned)((nrows + wpb - 1) / wpb);
     uint2* rec = reinterpret_cast<uint2*>(c->d_wta_rec);
     switch (nr) {
-        case 1: k_hsweep<1><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows); break;
-        case 2: k_hsweep<2><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows); break;
-        case 4: k_hsweep<4><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows); break;
-        default: k_hsweep<8><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows); break;
+        case 1: k_hsweep<1><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows, 1u); break;
+        case 2: k_hsweep<2><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows, 1u); break;
+        case 4: k_hsweep<4><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows, 1u); break;
+        default: k_hsweep<8><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows, 1u); break;
     }
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;

@@ -38,35 +38,64 @@ __device__ __forceinline__ void store_words(void* p, const uint32_t (&w)[NR])
     }
 }
 
-// One step of the recurrence for this lane's 2*NR disparities.  Returns the new warp-wide minimum.
-template <int NR>
-__device__ __forceinline__ uint32_t path_step(uint32_t (&L)[NR], const uint32_t (&Cw)[NR], uint32_t m, uint32_t P1w,
-                                              uint32_t P2, int lane)
+// Per-lane constants of path_step.  `one` is the integer 1 passed in as a kernel argument: the compiler cannot
+// fold a multiplication by it, so `a * one + b` is emitted as IMAD, which issues on the FMA pipe.  The aggregation
+// kernels are bound by the ALU pipe (IADD3 / LOP3 / SHF / SEL / VIMNMX / VIADDMNMX issue one warp instruction per
+// two cycles per scheduler); every add, select and shift that can be phrased as a multiply-add moves there.
+struct PathLane {
+    uint32_t one;      // 1
+    uint32_t sh16;     // 65536
+    uint32_t keep0;    // lane 0: 0, else 1          -- d = -1 reads "+inf": up = shfl * keep0 + add0
+    uint32_t add0;     // lane 0: kBig, else 0
+    uint32_t mul31;    // lane 31: 0, else 65536     -- d past the last lane reads "+inf": s = dn * mul31 + (hi + add31)
+    uint32_t add31;    // lane 31: kBig << 16, else 0
+};
+__device__ __forceinline__ PathLane make_path_lane(int lane, uint32_t one)
 {
-    uint32_t up = __shfl_up_sync(0xffffffffu, L[NR - 1], 1);
-    uint32_t dn = __shfl_down_sync(0xffffffffu, L[0], 1);
-    if (lane == 0) up = kBigW;
-    if (lane == 31) dn = kBigW;
-    const uint32_t mw = m * 0x10001u;
-    const uint32_t mP2w = (m + P2) * 0x10001u;
-    uint32_t Ln[NR];
+    PathLane p;
+    p.one = one;
+    p.sh16 = one << 16;
+    p.keep0 = lane == 0 ? 0u : one;
+    p.add0 = lane == 0 ? kBig : 0u;
+    p.mul31 = lane == 31 ? 0u : one << 16;
+    p.add31 = lane == 31 ? kBig << 16 : 0u;
+    return p;
+}
+
+// One step of the recurrence for this lane's 2*NR disparities.
+//   mw   packed (m, m): the warp-wide minimum of the incoming state, in both 16-bit halves
+//   P1w, P2w   packed penalties
+// Returns the packed minimum of the new state.  The NR+1 distinct "shifted by one disparity" words
+// s[k] = (w[k-1].hi, w[k].lo) are built once each as w[k] * 65536 + hi(w[k-1]); the lane minimum stays packed
+// (PRMT + VIMNMX.U16x2) so the REDUX result is directly the next step's mw.
+template <int NR>
+__device__ __forceinline__ uint32_t path_step(uint32_t (&L)[NR], const uint32_t (&Cw)[NR], uint32_t mw, uint32_t P1w,
+                                              uint32_t P2w, const PathLane& pl)
+{
+    uint32_t hi[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) hi[r] = L[r] >> 16;
+    const uint32_t up_hi = __shfl_up_sync(0xffffffffu, hi[NR - 1], 1) * pl.keep0 + pl.add0;
+    const uint32_t dn = __shfl_down_sync(0xffffffffu, L[0], 1);
+    uint32_t sft[NR + 1];
+    sft[0] = L[0] * pl.sh16 + up_hi;
+#pragma unroll
+    for (int r = 1; r < NR; ++r) sft[r] = L[r] * pl.sh16 + hi[r - 1];
+    sft[NR] = dn * pl.mul31 + (hi[NR - 1] * pl.one + pl.add31);
+    const uint32_t mP2w = mw * pl.one + P2w;
+    const uint32_t nmw = 0u - mw;
     uint32_t mn = 0xffffffffu;
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-        const uint32_t prev = r == 0 ? up : L[r - 1];
-        const uint32_t next = r == NR - 1 ? dn : L[r + 1];
-        const uint32_t lm1 = __funnelshift_l(prev, L[r], 16);   // (L[d-1], L[d]) for the pair (d, d+1)
-        const uint32_t lp1 = __funnelshift_r(L[r], next, 16);   // (L[d+1], L[d+2])
-        uint32_t t = __viaddmin_u16x2(lm1, P1w, L[r]);
-        t = __viaddmin_u16x2(lp1, P1w, t);
+        const uint32_t cm = Cw[r] * pl.one + nmw;                // C - m, off the critical path
+        uint32_t t = __viaddmin_u16x2(sft[r], P1w, L[r]);        // min(L[d-1] + P1, L[d])
+        t = __viaddmin_u16x2(sft[r + 1], P1w, t);                // min(L[d+1] + P1, .)
         t = __vminu2(t, mP2w);
-        Ln[r] = t - mw + Cw[r];                                 // every lane of t >= m: plain 32-bit arithmetic is exact
-        mn = r == 0 ? Ln[r] : __vminu2(mn, Ln[r]);
+        L[r] = t * pl.one + cm;                                  // every lane of t >= m: plain 32-bit arithmetic is exact
+        mn = r == 0 ? L[r] : __vminu2(mn, L[r]);
     }
-#pragma unroll
-    for (int r = 0; r < NR; ++r) L[r] = Ln[r];
-    const uint32_t lane_min = min(mn & 0xffffu, mn >> 16);
-    return __reduce_min_sync(0xffffffffu, lane_min);
+    mn = __vminu2(mn, __byte_perm(mn, 0, 0x1032));               // both halves = the lane minimum
+    return __reduce_min_sync(0xffffffffu, mn);
 }
 
 }  // namespace ssm

@@ -1,0 +1,247 @@
+// sgbm_vertical.cu -- the three top-down SGM paths (down, down-right, down-left) in ONE launch.
+//
+// Replaces three of the five path passes inside cv::StereoSGBM (called from /root/reference src/stereo.cpp:30).
+// The per-direction kernel (sgbm_aggregate.cu) streams C once per direction and read-modify-writes S twice:
+// 16N bytes of HBM traffic for 4N algorithmic bytes.  Here a thread-block CLUSTER owns one frame and walks it
+// row by row; each CTA owns a strip of T columns and keeps the D-wide state of all three directions for its
+// strip in shared memory (u16x2 words, one 64*NR-disparity line per column and direction), so every cost row is
+// read once and S_v = sat(L_down + L_dr + L_dl) is written once.
+//
+//   * a warp takes a column: one coalesced 2*D-byte load of C(y, x, .), three path_step recurrences (packed
+//     VIADDMNMX.U16x2, d+-1 by SHFL + funnel shift, min over d by one REDUX each), one coalesced store of S_v;
+//   * the diagonal directions are stored in a ring indexed by (x - y) mod T resp. (x + y) mod T, so that the
+//     predecessor of column x in the previous row sits in the very slot column x is about to overwrite:
+//     the update is in place, no second copy of the state;
+//   * the only cross-CTA dependency is one column of state per side and row: the owner writes it straight into
+//     the neighbour's halo buffer through distributed shared memory (st.shared::cluster), double-buffered by row
+//     parity; one barrier.cluster per row orders both the intra-CTA and the inter-CTA hand-over;
+//   * C rows are prefetched G columns ahead in registers (the next row's first group is in flight across the
+//     barrier).
+// Out-of-image predecessors are the all-zero state (m = 0), as in the per-direction kernel.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
+#include "sgbm_path.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ssm {
+
+template <int NR, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __restrict__ C, uint16_t* __restrict__ S, int W1, int H,
+                                                             int D, int P1, int P2, int T, uint32_t one)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int frame = blockIdx.x / CS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int LW = 32 * NR;                  // words per (column, direction) line
+    constexpr int LWB = LW * 4;                  // bytes per line
+
+    const int x0 = rank * T;
+    const int Tc = max(0, min(T, W1 - x0));      // columns of this CTA (the last strips may be shorter or empty)
+    const int R = Tc + 1;                        // ring length of the diagonal directions: one spare slot for the halo column
+    const bool has_left = rank > 0 && Tc > 0;
+    const bool has_right = Tc > 0 && (x0 + T < W1);
+    const int Tn = has_right ? min(T, W1 - (x0 + T)) : 0;   // columns of the right neighbour (the left one always has T)
+
+    // shared memory: st0 [T] lines (down), st1 / st2 [T+1] lines (rings), then the three arrays of packed minima
+    const int n_state = (3 * T + 2) * LW;
+    const int n_all = n_state + 3 * (T + 1);
+    for (int i = threadIdx.x; i < n_all; i += NWARPS * 32) smem[i] = 0u;
+    char* const sm = reinterpret_cast<char*>(smem);
+    const int b0 = lane * NR * 4, b1 = b0 + T * LWB, b2 = b1 + (T + 1) * LWB;   // byte offsets incl. this lane's words
+    const int mb0 = n_state * 4, mb1 = mb0 + T * 4, mb2 = mb1 + (T + 1) * 4;
+    char* const right_sm = has_right ? reinterpret_cast<char*>(cluster.map_shared_rank(smem, rank + 1)) : nullptr;
+    char* const left_sm = has_left ? reinterpret_cast<char*>(cluster.map_shared_rank(smem, rank - 1)) : nullptr;
+    cluster.sync();
+
+    const int d0 = lane * 2 * NR;
+    const bool active = d0 < D;
+    const uint32_t P1w = (uint32_t)P1 * 0x10001u, P2w = (uint32_t)P2 * 0x10001u;
+    const uint32_t padC = (kBig - (uint32_t)P2) * 0x10001u;
+    const PathLane pl = make_path_lane(lane, one);
+    const size_t rowbytes = (size_t)W1 * D * 2;
+    const char* Crow = reinterpret_cast<const char*>(C) + ((size_t)frame * H * W1 + x0) * D * 2 + d0 * 2;
+    char* Srow = reinterpret_cast<char*>(S) + ((size_t)frame * H * W1 + x0) * D * 2 + d0 * 2;
+    const int nk = Tc > warp ? (Tc - warp + NWARPS - 1) / NWARPS : 0;   // my columns: warp, warp + NWARPS, ...
+    const uint32_t cstep = (uint32_t)NWARPS * D * 2;                    // bytes between my consecutive columns
+    const int wl = Tc > 0 ? (Tc - 1) % NWARPS : -1;                     // the warp that owns the strip's last column
+
+    uint32_t Cw[NR], Cn[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { Cw[r] = padC; Cn[r] = padC; }
+    if (active && nk > 0) load_words<NR>(Crow + (size_t)warp * D * 2, Cw);
+
+    // ring phases: my column c lives in slot (c + o1) mod R of ring 1 and (c + o2) mod R of ring 2
+    int o1 = 0, o2 = 0;
+    int h1 = Tc;                                 // ring-1 slot of my halo column -1 written during this row: (-1 - y) mod R
+    int h2 = Tc;                                 // ring-2 slot of my halo column Tc written during this row: (Tc + y) mod R
+    int n1 = Tn;                                 // the same slot in the right neighbour's ring 1: (-1 - y) mod (Tn + 1)
+    int l2 = T;                                  // and in the left neighbour's ring 2: (T + y) mod (T + 1)
+    for (int y = 0; y < H; ++y) {
+        uint32_t off = (uint32_t)warp * D * 2;
+        int c = warp;
+        int s1 = c + o1; s1 = (int)min((unsigned)s1, (unsigned)(s1 - R));
+        int s2 = c + o2; s2 = (int)min((unsigned)s2, (unsigned)(s2 - R));
+        for (int k = 0; k < nk; ++k) {
+            // prefetch the cost of my next column (next row's first one at the end of the row)
+            if (active) {
+                if (k + 1 < nk) load_words<NR>(Crow + off + cstep, Cn);
+                else if (y + 1 < H) load_words<NR>(Crow + rowbytes + (size_t)warp * D * 2, Cn);
+            }
+            char* const p0 = sm + c * LWB + b0;
+            char* const p1 = sm + s1 * LWB + b1;
+            char* const p2 = sm + s2 * LWB + b2;
+            uint32_t* const q0 = reinterpret_cast<uint32_t*>(sm + mb0) + c;
+            uint32_t* const q1 = reinterpret_cast<uint32_t*>(sm + mb1) + s1;
+            uint32_t* const q2 = reinterpret_cast<uint32_t*>(sm + mb2) + s2;
+            uint32_t L0[NR], L1[NR], L2[NR];
+            load_words<NR>(p0, L0);
+            load_words<NR>(p1, L1);
+            load_words<NR>(p2, L2);
+            uint32_t m0 = *q0, m1 = *q1, m2 = *q2;
+            m0 = path_step<NR>(L0, Cw, m0, P1w, P2w, pl);
+            m1 = path_step<NR>(L1, Cw, m1, P1w, P2w, pl);
+            m2 = path_step<NR>(L2, Cw, m2, P1w, P2w, pl);
+            store_words<NR>(p0, L0);
+            store_words<NR>(p1, L1);
+            store_words<NR>(p2, L2);
+            if (lane == 0) { *q0 = m0; *q1 = m1; *q2 = m2; }
+            if (active) {
+                uint32_t o[NR];
+#pragma unroll
+                for (int r = 0; r < NR; ++r) o[r] = __viaddmin_u16x2(__viaddmin_u16x2(L0[r], L1[r], kSatW), L2[r], kSatW);
+                store_words<NR>(Srow + off, o);
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) Cw[r] = Cn[r];
+            off += cstep;
+            c += NWARPS;
+            s1 += NWARPS; s1 = (int)min((unsigned)s1, (unsigned)(s1 - R));
+            s2 += NWARPS; s2 = (int)min((unsigned)s2, (unsigned)(s2 - R));
+        }
+        // hand the strip's border columns to the neighbours (or feed zeros at the image border)
+        if (warp == wl) {
+            // my last column's down-right state is the right neighbour's halo column -1 for the next row
+            int sl = Tc - 1 + o1; sl = (int)min((unsigned)sl, (unsigned)(sl - R));
+            if (has_right) {
+                uint32_t Lx[NR];
+                load_words<NR>(sm + sl * LWB + b1, Lx);
+                store_words<NR>(right_sm + n1 * LWB + b1, Lx);
+                if (lane == 0) *(reinterpret_cast<uint32_t*>(right_sm + mb1) + n1) = *(reinterpret_cast<uint32_t*>(sm + mb1) + sl);
+            } else if (Tc > 0) {
+                // image border on the right: the down-left predecessor of my last column is the zero state
+                uint32_t Z[NR];
+#pragma unroll
+                for (int r = 0; r < NR; ++r) Z[r] = 0u;
+                store_words<NR>(sm + h2 * LWB + b2, Z);
+                if (lane == 0) *(reinterpret_cast<uint32_t*>(sm + mb2) + h2) = 0u;
+            }
+        }
+        if (warp == 0 && Tc > 0) {
+            if (has_left) {
+                uint32_t Lx[NR];
+                load_words<NR>(sm + o2 * LWB + b2, Lx);         // my column 0 lives in ring-2 slot (0 + o2)
+                store_words<NR>(left_sm + l2 * LWB + b2, Lx);
+                if (lane == 0) *(reinterpret_cast<uint32_t*>(left_sm + mb2) + l2) = *(reinterpret_cast<uint32_t*>(sm + mb2) + o2);
+            } else {
+                uint32_t Z[NR];
+#pragma unroll
+                for (int r = 0; r < NR; ++r) Z[r] = 0u;
+                store_words<NR>(sm + h1 * LWB + b1, Z);
+                if (lane == 0) *(reinterpret_cast<uint32_t*>(sm + mb1) + h1) = 0u;
+            }
+        }
+        Crow += rowbytes;
+        Srow += rowbytes;
+        // next row: ring 1 rotates one slot back, ring 2 one slot forward
+        o1 = o1 == 0 ? R - 1 : o1 - 1;
+        o2 = o2 + 1 == R ? 0 : o2 + 1;
+        h1 = h1 == 0 ? R - 1 : h1 - 1;
+        h2 = h2 + 1 == R ? 0 : h2 + 1;
+        n1 = n1 == 0 ? Tn : n1 - 1;
+        l2 = l2 == T ? 0 : l2 + 1;
+        cluster.sync();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct VerticalPlan {
+    int cluster = 0, T = 0;
+    size_t smem = 0;
+};
+
+template <int NR, int NWARPS>
+static int launch_vertical_t(ssm_ctx* c, int B, const VerticalPlan& plan, cudaStream_t s, bool* done)
+{
+    const DevParams& p = c->dp;
+    auto kern = k_vertical3<NR, NWARPS>;
+    SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    if (plan.cluster > 8) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * plan.cluster));
+    cfg.blockDim = dim3(NWARPS * 32);
+    cfg.dynamicSmemBytes = plan.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)plan.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
+        cudaGetLastError();      // this cluster shape cannot be co-scheduled on this device: fall back
+        return SSM_OK;
+    }
+    SSM_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int16_t*)c->d_C, c->d_S, p.W1, p.H, p.D, p.P1, p.P2, plan.T, 1u));
+    SSM_LAUNCH_CHECK(c);
+    *done = true;
+    return SSM_OK;
+}
+
+static size_t vertical_smem(int NR, int T)
+{
+    const int LW = 32 * NR;
+    return sizeof(uint32_t) * ((size_t)(3 * T + 2) * LW + 3 * (T + 1));
+}
+
+// Smallest cluster whose per-CTA strip fits shared memory.  Returns false when none does (caller falls back to the
+// per-direction kernels).
+static bool plan_vertical(const ssm_ctx* c, VerticalPlan& plan)
+{
+    const DevParams& p = c->dp;
+    const int NR = p.D <= 64 ? 1 : (p.D <= 128 ? 2 : (p.D <= 256 ? 4 : 8));
+    const size_t limit = 220 * 1024;
+    for (int cs : {1, 2, 4, 8, 16}) {
+        if (cs > c->max_cluster) break;
+        if (cs < c->min_cluster) continue;
+        const int T = (p.W1 + cs - 1) / cs;
+        const size_t need = vertical_smem(NR, T);
+        if (need <= limit) {
+            plan.cluster = cs; plan.T = T; plan.smem = need;
+            return true;
+        }
+    }
+    return false;
+}
+
+int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done)
+{
+    *done = false;
+    if (c->force_legacy_vertical) return SSM_OK;
+    VerticalPlan plan;
+    if (!plan_vertical(c, plan)) return SSM_OK;
+    const int D = c->dp.D;
+    if (D <= 64) return launch_vertical_t<1, 32>(c, B, plan, s, done);
+    if (D <= 128) return launch_vertical_t<2, 32>(c, B, plan, s, done);
+    if (D <= 256) return launch_vertical_t<4, 16>(c, B, plan, s, done);
+    return launch_vertical_t<8, 16>(c, B, plan, s, done);
+}
+
+}  // namespace ssm

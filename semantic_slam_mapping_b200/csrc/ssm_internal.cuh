@@ -92,6 +92,9 @@ struct ssm_ctx {
     ssm::DevParams dp;
     int device = 0;
     int sm_count = 148;
+    int max_cluster = 16, min_cluster = 1;   // thread-block cluster sizes the vertical kernel may use (SSM_MAX_CLUSTER / SSM_MIN_CLUSTER)
+    bool force_legacy_cost = false;       // SSM_LEGACY_COST=1: k_pix_hsum + k_vsum instead of the fused cost kernel
+    bool force_legacy_vertical = false;   // SSM_LEGACY_VERTICAL=1: per-direction kernels instead of the cluster kernel
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
     bool timing = false;
@@ -156,6 +159,7 @@ int cuda_fail(cudaError_t e, const char* what);
 int launch_prefilter(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, cudaStream_t s);
 int launch_cost_volume(ssm_ctx* c, int B, cudaStream_t s);
 int launch_aggregate(ssm_ctx* c, int B, cudaStream_t s);
+int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done);   // cluster kernel; *done = false -> caller falls back
 int launch_select(ssm_ctx* c, int B, cudaStream_t s);
 int launch_hsweep(ssm_ctx* c, int B, cudaStream_t s);
 int launch_wta_finalize(ssm_ctx* c, int B, cudaStream_t s);

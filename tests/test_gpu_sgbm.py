@@ -112,3 +112,67 @@ def test_error_behaviour():
             ctx.sgbm(np.zeros((60, 100), np.uint8), np.zeros((60, 100), np.uint8))  # taller than the context
         with pytest.raises(SsmError):
             ctx.sgbm(np.zeros((10, 30), np.uint8), np.zeros((10, 30), np.uint8))    # W <= D
+
+
+@pytest.mark.parametrize("min_cluster", [1, 2, 4, 8])
+@pytest.mark.parametrize("H,W,D,seed", [(40, 101, 32, 31), (33, 21, 16, 32), (50, 333, 128, 33), (24, 270, 256, 34), (30, 200, 80, 35)])
+def test_vertical_cluster_kernel_all_cluster_sizes(monkeypatch, min_cluster, H, W, D, seed):
+    """The three top-down paths in one cluster launch: strips of unequal / zero width, 1..8 CTAs per frame."""
+    monkeypatch.setenv("SSM_MIN_CLUSTER", str(min_cluster))
+    L, R, _ = synth.stereo_pair(H, W, D, seed)
+    p = _params(D, W, H)
+    want, vols = oracle.sgbm(L, R, _oparams(p), want_volumes=True)
+    with Context(p) as ctx:
+        got = ctx.sgbm(L, R)
+        Sf = ctx.debug_volume("S", W, H)
+    assert int((Sf != vols["Sf"]).sum()) == 0
+    assert int((got != want).sum()) == 0
+
+
+def test_legacy_per_direction_kernels_still_exact(monkeypatch):
+    monkeypatch.setenv("SSM_LEGACY_VERTICAL", "1")
+    L, R, _ = synth.stereo_pair(64, 240, 96, 41)
+    p = _params(96, 240, 64)
+    with Context(p) as ctx:
+        assert int((ctx.sgbm(L, R) != oracle.sgbm(L, R, _oparams(p))).sum()) == 0
+
+
+def test_vertical_cluster_kernel_batched_frames():
+    import torch
+    H, W, D, B = 60, 500, 128, 7
+    p = _params(D, W, H, max_batch=B)
+    Ls, Rs = zip(*[synth.stereo_pair(H, W, D, 300 + i)[:2] for i in range(B)])
+    dL = torch.from_numpy(np.stack(Ls)).cuda()
+    dR = torch.from_numpy(np.stack(Rs)).cuda()
+    dD = torch.empty((B, H, W), dtype=torch.int16, device="cuda")
+    with Context(p) as ctx:
+        ctx.sgbm_batch_device(dL, dR, dD, B, W, H, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    op = _oparams(p)
+    for i in (0, 3, 6):
+        assert int((oracle.sgbm(Ls[i], Rs[i], op) != dD[i].cpu().numpy()).sum()) == 0
+
+
+@pytest.mark.parametrize("H,W,D,bs,seed", [(45, 140, 16, 11, 51), (40, 120, 32, 11, 52), (52, 170, 64, 5, 53), (130, 333, 128, 11, 54),
+                                            (61, 300, 256, 11, 55), (36, 150, 80, 11, 56), (20, 90, 48, 3, 57), (25, 200, 128, 1, 58)])
+def test_fused_cost_kernel_matches_oracle_cost_volume(H, W, D, bs, seed):
+    """Fused pixel-cost + box-sum kernel (every tile width, run-time and compile-time window, band edges)."""
+    L, R, _ = synth.stereo_pair(H, W, D, seed)
+    p = _params(D, W, H, block_size=bs, p1=4 * bs * bs, p2=32 * bs * bs)
+    want, vols = oracle.sgbm(L, R, _oparams(p), want_volumes=True)
+    with Context(p) as ctx:
+        got = ctx.sgbm(L, R)
+        C = ctx.debug_volume("C", W, H)
+    assert int((C != vols["C"]).sum()) == 0
+    assert int((got != want).sum()) == 0
+
+
+def test_legacy_two_kernel_cost_path_still_exact(monkeypatch):
+    monkeypatch.setenv("SSM_LEGACY_COST", "1")
+    L, R, _ = synth.stereo_pair(64, 240, 64, 61)
+    p = _params(64, 240, 64)
+    want, vols = oracle.sgbm(L, R, _oparams(p), want_volumes=True)
+    with Context(p) as ctx:
+        got = ctx.sgbm(L, R)
+        C = ctx.debug_volume("C", W=240, h=64) if False else ctx.debug_volume("C", 240, 64)
+    assert int((C != vols["C"]).sum()) == 0 and int((got != want).sum()) == 0
