@@ -232,6 +232,12 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
     {
         const char* e = getenv("SSM_LEGACY_VERTICAL");
         c->force_legacy_vertical = e && e[0] == '1';
+        for (int t = 0; t < 4; ++t) {
+            const std::string name = "SSM_TUNE" + std::to_string(t);
+            const char* v = getenv(name.c_str());
+            static const int defaults[4] = {2 /* vertical: L2 prefetch distance in rows */, 0 /* hsweep: L2 prefetch off */, 0, 0};
+            c->tune[t] = v ? atoi(v) : defaults[t];
+        }
         const char* lc = getenv("SSM_LEGACY_COST");
         c->force_legacy_cost = lc && lc[0] == '1';
         const char* m = getenv("SSM_MAX_CLUSTER");

@@ -36,6 +36,15 @@ __device__ __forceinline__ void load_group(const uint16_t* __restrict__ Crow, co
     }
 }
 
+// L2 prefetch (TMA bulk) of pixels [x_lo, x_hi) of this row of C and S: one lane, two instructions
+constexpr int kAhead = 8;   // prefetch distance in groups of kPF pixels
+__device__ __forceinline__ void prefetch_span(const uint16_t* Cbase, const uint16_t* Sbase, int x_lo, int x_hi, int D)
+{
+    const uint32_t bytes = (uint32_t)(x_hi - x_lo) * D * 2;
+    l2_prefetch_bulk(Cbase + (size_t)x_lo * D, bytes);
+    l2_prefetch_bulk(Sbase + (size_t)x_lo * D, bytes);
+}
+
 template <int NR>
 __device__ __forceinline__ uint32_t pick(const uint32_t (&w)[NR], int idx)
 {   // 16-bit element idx (0 .. 2*NR-1) of this lane's packed words
@@ -48,7 +57,7 @@ __device__ __forceinline__ uint32_t pick(const uint32_t (&w)[NR], int idx)
 
 template <int NR>
 __global__ void __launch_bounds__(128) k_hsweep(const int16_t* __restrict__ C, uint16_t* S /* read and written: no restrict */, uint2* __restrict__ rec,
-                                                const uint32_t* __restrict__ uniq_thr, int W1, int D, int P1, int P2, int nrows, uint32_t one)
+                                                const uint32_t* __restrict__ uniq_thr, int W1, int D, int P1, int P2, int nrows, uint32_t one, int pf)
 {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -62,6 +71,8 @@ __global__ void __launch_bounds__(128) k_hsweep(const int16_t* __restrict__ C, u
     const uint16_t* Crow = reinterpret_cast<const uint16_t*>(C) + (size_t)row * W1 * D + d0;
     uint16_t* Srow = S + (size_t)row * W1 * D + d0;
     const int ngroups = (W1 + kPF - 1) / kPF;
+    const uint16_t* Cbase = Crow - d0;
+    const uint16_t* Sbase = Srow - d0;
 
     uint32_t L[NR], Ca[kPF][NR], Sa[kPF][NR], Cb[kPF][NR], Sb[kPF][NR];
 
@@ -71,7 +82,12 @@ __global__ void __launch_bounds__(128) k_hsweep(const int16_t* __restrict__ C, u
         for (int r = 0; r < NR; ++r) L[r] = 0u;
         uint32_t m = 0u;
         load_group<NR, false>(Crow, Srow, 0, W1, D, active, padC, Ca, Sa);
+        if (lane == 0 && pf) prefetch_span(Cbase, Sbase, 0, min(kAhead * kPF, W1), D);
         for (int g = 0; g < ngroups; g += 2) {
+            if (lane == 0 && pf) {   // the 8 pixels that will be loaded kAhead groups from now, into L2
+                const int x0 = (g + kAhead) * kPF;
+                if (x0 < W1) prefetch_span(Cbase, Sbase, x0, min(x0 + 2 * kPF, W1), D);
+            }
             load_group<NR, false>(Crow, Srow, g + 1, W1, D, active, padC, Cb, Sb);
 #pragma unroll
             for (int j = 0; j < kPF; ++j) {
@@ -149,7 +165,12 @@ __global__ void __launch_bounds__(128) k_hsweep(const int16_t* __restrict__ C, u
         for (int r = 0; r < NR; ++r) L[r] = 0u;
         uint32_t m = 0u;
         load_group<NR, true>(Crow, Srow, 0, W1, D, active, padC, Ca, Sa);
+        if (lane == 0 && pf) prefetch_span(Cbase, Sbase, max(W1 - kAhead * kPF, 0), W1, D);
         for (int g = 0; g < ngroups; g += 2) {
+            if (lane == 0 && pf) {
+                const int x1 = W1 - (g + kAhead) * kPF;        // pixels [x1 - 8, x1) are loaded kAhead groups from now
+                if (x1 > 0) prefetch_span(Cbase, Sbase, max(x1 - 2 * kPF, 0), x1, D);
+            }
             load_group<NR, true>(Crow, Srow, g + 1, W1, D, active, padC, Cb, Sb);
 #pragma unroll
             for (int j = 0; j < kPF; ++j) {
@@ -207,10 +228,10 @@ int launch_hsweep(ssm_ctx* c, int B, cudaStream_t s)
     const unsigned grid = (unsigned)((nrows + wpb - 1) / wpb);
     uint2* rec = reinterpret_cast<uint2*>(c->d_wta_rec);
     switch (nr) {
-        case 1: k_hsweep<1><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows, 1u); break;
-        case 2: k_hsweep<2><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows, 1u); break;
-        case 4: k_hsweep<4><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows, 1u); break;
-        default: k_hsweep<8><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows, 1u); break;
+        case 1: k_hsweep<1><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows, 1u, c->tune[1]); break;
+        case 2: k_hsweep<2><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows, 1u, c->tune[1]); break;
+        case 4: k_hsweep<4><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows, 1u, c->tune[1]); break;
+        default: k_hsweep<8><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_S, rec, c->d_uniq_thr, p.W1, p.D, p.P1, p.P2, nrows, 1u, c->tune[1]); break;
     }
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;

@@ -5,6 +5,13 @@
 
 namespace ssm {
 
+// TMA-issued L2 prefetch of a contiguous global range (16-byte aligned, size a multiple of 16): one instruction per
+// range, no registers held while the data travels.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 template <int NR> struct WordVec;
 template <> struct WordVec<1> { using T = uint32_t; };
 template <> struct WordVec<2> { using T = uint2; };

@@ -30,7 +30,7 @@ namespace ssm {
 
 template <int NR, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __restrict__ C, uint16_t* __restrict__ S, int W1, int H,
-                                                             int D, int P1, int P2, int T, uint32_t one)
+                                                             int D, int P1, int P2, int T, uint32_t one, int pf_rows)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -82,7 +82,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
     int h2 = Tc;                                 // ring-2 slot of my halo column Tc written during this row: (Tc + y) mod R
     int n1 = Tn;                                 // the same slot in the right neighbour's ring 1: (-1 - y) mod (Tn + 1)
     int l2 = T;                                  // and in the left neighbour's ring 2: (T + y) mod (T + 1)
+    // L2 prefetch (one TMA bulk instruction per row and CTA) pf_rows rows ahead of the register prefetch below:
+    // the per-row cluster barrier's release fence waits for every outstanding load, so their latency must be short
+    const uint32_t seg_bytes = (uint32_t)Tc * D * 2;            // my strip of one cost row is contiguous in memory
+    const char* const Cseg = Crow - d0 * 2;
+    if (threadIdx.x == 0 && Tc > 0 && pf_rows > 0)
+        for (int q = 1; q < pf_rows && q < H; ++q) l2_prefetch_bulk(Cseg + (size_t)q * rowbytes, seg_bytes);
     for (int y = 0; y < H; ++y) {
+        if (threadIdx.x == 0 && Tc > 0 && pf_rows > 0 && y + pf_rows < H) l2_prefetch_bulk(Cseg + (size_t)(y + pf_rows) * rowbytes, seg_bytes);
         uint32_t off = (uint32_t)warp * D * 2;
         int c = warp;
         int s1 = c + o1; s1 = (int)min((unsigned)s1, (unsigned)(s1 - R));
@@ -199,7 +206,7 @@ static int launch_vertical_t(ssm_ctx* c, int B, const VerticalPlan& plan, cudaSt
         cudaGetLastError();      // this cluster shape cannot be co-scheduled on this device: fall back
         return SSM_OK;
     }
-    SSM_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int16_t*)c->d_C, c->d_S, p.W1, p.H, p.D, p.P1, p.P2, plan.T, 1u));
+    SSM_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int16_t*)c->d_C, c->d_S, p.W1, p.H, p.D, p.P1, p.P2, plan.T, 1u, c->tune[0]));
     SSM_LAUNCH_CHECK(c);
     *done = true;
     return SSM_OK;

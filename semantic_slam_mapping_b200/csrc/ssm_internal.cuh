@@ -93,6 +93,7 @@ struct ssm_ctx {
     int device = 0;
     int sm_count = 148;
     int max_cluster = 16, min_cluster = 1;   // thread-block cluster sizes the vertical kernel may use (SSM_MAX_CLUSTER / SSM_MIN_CLUSTER)
+    int tune[4] = {0, 0, 0, 0};           // SSM_TUNE0..3: experiment knobs (see the kernels that read them)
     bool force_legacy_cost = false;       // SSM_LEGACY_COST=1: k_pix_hsum + k_vsum instead of the fused cost kernel
     bool force_legacy_vertical = false;   // SSM_LEGACY_VERTICAL=1: per-direction kernels instead of the cluster kernel
     cudaStream_t stream = nullptr;
