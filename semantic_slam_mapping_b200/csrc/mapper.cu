@@ -76,28 +76,35 @@ __global__ void __launch_bounds__(256) k_labels(const uint8_t* __restrict__ sem,
     label[idx] = (uint8_t)label_of(p, (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16));
 }
 
-// cv::dilate(img, img, ones(3,3), anchor centre, iterations) == (2*it+1)^2 max filter, out-of-image ignored
-__global__ void __launch_bounds__(256) k_moving_mask(const uint8_t* __restrict__ label, uint8_t* __restrict__ mask, size_t total, SSM_DP)
+// cv::dilate(img, img, ones(3,3), anchor centre, iterations) == (2*it+1)^2 max filter, out-of-image ignored.
+// One warp covers 32 - 2R consecutive pixels of a row plus R halo pixels per side: each of the 2R+1 rows in reach
+// costs one label load per lane; the "dynamic class" predicate becomes one ballot word per row, the horizontal
+// dilation is 2R shifts of that word, the vertical one an OR over the rows.
+__global__ void __launch_bounds__(256) k_moving_mask(const uint8_t* __restrict__ label, uint8_t* __restrict__ mask, int segs_per_row,
+                                                     size_t total_segs, SSM_DP)
 {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int x = (int)(idx % p.W);
-    const size_t r = idx / p.W;
-    const int y = (int)(r % p.H);
-    const uint8_t* img = label + (r / p.H) * (size_t)p.W * p.H;
+    const int lane = threadIdx.x & 31;
+    const size_t seg = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (seg >= total_segs) return;
     const int R = p.dilate_radius;
-    bool hit = false;
+    const int span = 32 - 2 * R;
+    const size_t row = seg / segs_per_row;
+    const int y = (int)(row % p.H);
+    const int x = (int)(seg % segs_per_row) * span - R + lane;      // lanes [R, 32 - R) own an output pixel
+    const uint8_t* img = label + (row / p.H) * (size_t)p.W * p.H;
+    uint32_t acc = 0u;
     for (int dy = -R; dy <= R; ++dy) {
         const int yy = y + dy;
-        if (yy < 0 || yy >= p.H) continue;
-        for (int dx = -R; dx <= R; ++dx) {
-            const int xx = x + dx;
-            if (xx < 0 || xx >= p.W) continue;
-            const int l = img[(size_t)yy * p.W + xx];
-            hit |= (l != SSM_LABEL_UNKNOWN) && ((p.dynamic_mask >> l) & 1u);
+        bool dyn = false;
+        if (yy >= 0 && yy < p.H && x >= 0 && x < p.W) {
+            const int l = img[(size_t)yy * p.W + x];
+            dyn = (l != SSM_LABEL_UNKNOWN) && ((p.dynamic_mask >> l) & 1u);
         }
+        acc |= __ballot_sync(0xffffffffu, dyn);
     }
-    mask[idx] = hit ? 255 : 0;
+    uint32_t dil = acc;
+    for (int k = 1; k <= R; ++k) dil |= (acc << k) | (acc >> k);
+    if (lane >= R && lane < 32 - R && x < p.W) mask[row * p.W + x] = ((dil >> lane) & 1u) ? 255 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -323,7 +330,10 @@ int launch_labels_mask(ssm_ctx* c, int B, const uint8_t* d_sem, cudaStream_t s)
     const unsigned grid = (unsigned)((total + 255) / 256);
     k_labels<<<grid, 256, 0, s>>>(d_sem, c->d_label, total, p);
     SSM_LAUNCH_CHECK(c);
-    k_moving_mask<<<grid, 256, 0, s>>>(c->d_label, c->d_mask, total, p);
+    const int span = 32 - 2 * p.dilate_radius;   // dilate_iterations <= 8 keeps this positive
+    const int segs_per_row = (p.W + span - 1) / span;
+    const size_t total_segs = (size_t)segs_per_row * p.H * B;
+    k_moving_mask<<<(unsigned)((total_segs + 7) / 8), 256, 0, s>>>(c->d_label, c->d_mask, segs_per_row, total_segs, p);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }

@@ -205,6 +205,58 @@ __global__ void __launch_bounds__(256) k_vsum(const uint16_t* __restrict__ hs, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// K0 (compact): prefilter + BT half-sample intervals as 8-byte records {gv, glo, ghi, rv, rlo, rhi, 0, 0} (all
+// values fit a byte: Sobel channel in [0, 126], raw channel in [0, 255]).  One thread makes 4 consecutive pixels
+// from one 8 x 3 pixel neighbourhood; both images in one launch.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prefilter8(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right,
+                                                    uint2* __restrict__ recL, uint2* __restrict__ recR, int W, int H, int ftzero,
+                                                    int quads_per_row, size_t total_quads)
+{
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total_quads) return;
+    const int which = blockIdx.y;                    // 0 = left, 1 = right
+    const uint8_t* img_all = which ? right : left;
+    uint2* rec = which ? recR : recL;
+    const int x0 = (int)(q % quads_per_row) * 4;
+    const size_t row = q / quads_per_row;            // frame * H + y
+    const int y = (int)(row % H);
+    const uint8_t* cur = img_all + row * (size_t)W;
+    const uint8_t* up = y > 0 ? cur - W : cur;
+    const uint8_t* dn = y < H - 1 ? cur + W : cur;
+    // columns x0 - 2 .. x0 + 5 of the three rows (clamped loads; out-of-range values are never used unclamped)
+    int a[8], b[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int x = min(max(x0 - 2 + i, 0), W - 1);
+        a[i] = up[x]; b[i] = cur[x]; c[i] = dn[x];
+    }
+    // g[i], r[i] for columns x0 - 1 .. x0 + 4
+    int g[6], r[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int x = x0 - 1 + i;
+        const bool border = x <= 0 || x >= W - 1;    // first / last column (and beyond) are ftzero in both channels (A-1)
+        int sx = (b[i + 2] - b[i]) * 2 + (a[i + 2] - a[i]) + (c[i + 2] - c[i]);
+        sx = max(-ftzero, min(ftzero, sx)) + ftzero;
+        g[i] = border ? ftzero : sx;
+        r[i] = border ? ftzero : b[i + 1];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = x0 + i;
+        if (x >= W) break;
+        const bool hl = x > 0, hr = x < W - 1;
+        const int ga = hl ? (g[i + 1] + g[i]) >> 1 : g[i + 1], gb = hr ? (g[i + 1] + g[i + 2]) >> 1 : g[i + 1];
+        const int ra = hl ? (r[i + 1] + r[i]) >> 1 : r[i + 1], rb = hr ? (r[i + 1] + r[i + 2]) >> 1 : r[i + 1];
+        const int glo = min(min(ga, gb), g[i + 1]), ghi = max(max(ga, gb), g[i + 1]);
+        const int rlo = min(min(ra, rb), r[i + 1]), rhi = max(max(ra, rb), r[i + 1]);
+        rec[row * (size_t)W + x] = make_uint2((uint32_t)g[i + 1] | ((uint32_t)glo << 8) | ((uint32_t)ghi << 16) | ((uint32_t)r[i + 1] << 24),
+                                              (uint32_t)rlo | ((uint32_t)rhi << 8));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1 fused: pixel cost + horizontal window sum + vertical window sum -> C, one launch, no intermediate volume.
 //
 // CTA = (tile of TX output columns, band of rows, frame); TX * D/2 = 2048 packed words, 256 threads.  The CTA
@@ -241,7 +293,7 @@ struct CostGeom {
 };
 
 template <int TX, int RAD /* block_size / 2, or -1: run-time radius (slow generic window sums) */>
-__global__ void __launch_bounds__(256, 2) k_cost_fused(const uint4* __restrict__ recL, const uint4* __restrict__ recR,
+__global__ void __launch_bounds__(256, 2) k_cost_fused(const uint2* __restrict__ recL, const uint2* __restrict__ recR,
                                                        int16_t* __restrict__ C, int W, int H, int radius, int band_rows,
                                                        uint32_t mone /* 0xffffffff, opaque: x * mone + K is one IMAD */)
 {
@@ -272,7 +324,7 @@ __global__ void __launch_bounds__(256, 2) k_cost_fused(const uint4* __restrict__
     for (int i = 0; i < 8; ++i) { crun[i] = 0u; hs[i] = 0u; }
 
     // records of the next fresh row, prefetched one row ahead
-    uint4 qr[G::RPT], ql[G::LPT];
+    uint2 qr[G::RPT], ql[G::LPT];
     auto fetch = [&](int r) {
         const size_t rowbase = ((size_t)b * H + r) * W;
 #pragma unroll
@@ -300,10 +352,10 @@ __global__ void __launch_bounds__(256, 2) k_cost_fused(const uint4* __restrict__
             for (int k = 0; k < G::RPT; ++k) {
                 const int i = threadIdx.x + k * 256;
                 if (i < n_r) {
-                    const uint4 q = qr[k];
-                    // record: x = v | (-v) << 16, y = lo | (-hi) << 16 (Sobel); z, w the same for the raw channel
-                    const uint16_t val[6] = {(uint16_t)(q.y & 0xffffu), (uint16_t)(0u - (q.y >> 16)), (uint16_t)(q.x & 0xffffu),
-                                             (uint16_t)(q.w & 0xffffu), (uint16_t)(0u - (q.w >> 16)), (uint16_t)(q.z & 0xffffu)};
+                    const uint2 q = qr[k];
+                    // record bytes: gv, glo, ghi, rv | rlo, rhi
+                    const uint16_t val[6] = {(uint16_t)((q.x >> 8) & 0xffu), (uint16_t)((q.x >> 16) & 0xffu), (uint16_t)(q.x & 0xffu),
+                                             (uint16_t)(q.y & 0xffu), (uint16_t)((q.y >> 8) & 0xffu), (uint16_t)(q.x >> 24)};
 #pragma unroll
                     for (int t = 0; t < 6; ++t) {
                         uint16_t* a0 = reinterpret_cast<uint16_t*>(Rt + (2 * t) * TW);
@@ -317,10 +369,11 @@ __global__ void __launch_bounds__(256, 2) k_cost_fused(const uint4* __restrict__
             for (int k = 0; k < G::LPT; ++k) {
                 const int i = threadIdx.x + k * 256;
                 if (i < n_e) {
-                    const uint4 q = ql[k];
+                    const uint2 q = ql[k];
                     // per channel: dup(-u), dup(u - K), dup(-hi), dup(lo - K)
-                    const uint32_t ug = q.x & 0xffffu, nug = q.x >> 16, log_ = q.y & 0xffffu, nhig = q.y >> 16;
-                    const uint32_t ur = q.z & 0xffffu, nur = q.z >> 16, lor = q.w & 0xffffu, nhir = q.w >> 16;
+                    const uint32_t ug = q.x & 0xffu, log_ = (q.x >> 8) & 0xffu, hig = (q.x >> 16) & 0xffu;
+                    const uint32_t ur = q.x >> 24, lor = q.y & 0xffu, hir = (q.y >> 8) & 0xffu;
+                    const uint32_t nug = (0u - ug) & 0xffffu, nhig = (0u - hig) & 0xffffu, nur = (0u - ur) & 0xffffu, nhir = (0u - hir) & 0xffffu;
                     uint4* dst = reinterpret_cast<uint4*>(Lt + i * 8);
                     dst[0] = make_uint4(nug * 0x10001u, ((ug - kKb) & 0xffffu) * 0x10001u, nhig * 0x10001u, ((log_ - kKb) & 0xffffu) * 0x10001u);
                     dst[1] = make_uint4(nur * 0x10001u, ((ur - kKb) & 0xffffu) * 0x10001u, nhir * 0x10001u, ((lor - kKb) & 0xffffu) * 0x10001u);
@@ -414,9 +467,24 @@ __global__ void __launch_bounds__(256, 2) k_cost_fused(const uint4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+static bool use_fused_cost(const ssm_ctx* c)
+{
+    const int D = c->dp.D;
+    return !c->force_legacy_cost && (D == 16 || D == 32 || D == 64 || D == 128 || D == 256 || D == 512);
+}
+
 int launch_prefilter(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, cudaStream_t s)
 {
     const DevParams& p = c->dp;
+    if (use_fused_cost(c)) {
+        const int quads_per_row = (p.W + 3) / 4;
+        const size_t total_quads = (size_t)B * p.H * quads_per_row;
+        dim3 grid((unsigned)((total_quads + 255) / 256), 2);
+        k_prefilter8<<<grid, 256, 0, s>>>(dL, dR, reinterpret_cast<uint2*>(c->d_recL), reinterpret_cast<uint2*>(c->d_recR), p.W, p.H,
+                                          p.ftzero, quads_per_row, total_quads);
+        SSM_LAUNCH_CHECK(c);
+        return SSM_OK;
+    }
     const size_t total = (size_t)B * p.H * p.W;
     dim3 grid((unsigned)((total + 255) / 256), 2);
     k_prefilter<<<grid, 256, 0, s>>>(dL, dR, c->d_recL, c->d_recR, p.W, p.H, p.ftzero, total);
@@ -437,7 +505,7 @@ static int launch_cost_fused_t(ssm_ctx* c, int B, cudaStream_t s)
     const int band_rows = (p.H + bands - 1) / bands;
     bands = (p.H + band_rows - 1) / band_rows;
     dim3 grid(tiles, bands, B);
-    k_cost_fused<TX, RAD><<<grid, 256, smem, s>>>(c->d_recL, c->d_recR, c->d_C, p.W, p.H, radius, band_rows, 0xffffffffu);
+    k_cost_fused<TX, RAD><<<grid, 256, smem, s>>>(reinterpret_cast<const uint2*>(c->d_recL), reinterpret_cast<const uint2*>(c->d_recR), c->d_C, p.W, p.H, radius, band_rows, 0xffffffffu);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }
@@ -445,7 +513,7 @@ static int launch_cost_fused_t(ssm_ctx* c, int B, cudaStream_t s)
 int launch_cost_volume(ssm_ctx* c, int B, cudaStream_t s)
 {
     const DevParams& p = c->dp;
-    if (!c->force_legacy_cost) {
+    if (use_fused_cost(c)) {
         // TX * D/2 = 2048 words per CTA row
         const bool r5 = p.bs == 11;   // the reference's block size gets the compile-time window; others the generic one
         switch (p.D) {
