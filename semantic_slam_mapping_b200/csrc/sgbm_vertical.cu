@@ -28,6 +28,52 @@ namespace cg = cooperative_groups;
 
 namespace ssm {
 
+// ---- mbarrier / st.async helpers (shared::cluster addresses are 32-bit) ----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// asynchronous store into a peer CTA's shared memory; the peer's mbarrier is credited with the bytes on arrival
+template <int NR>
+__device__ __forceinline__ void st_async_words(uint32_t remote_addr, const uint32_t (&w)[NR], uint32_t remote_bar)
+{
+    if constexpr (NR == 1) {
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(w[0]), "r"(remote_bar) : "memory");
+    } else if constexpr (NR == 2) {
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(remote_addr), "r"(w[0]), "r"(w[1]), "r"(remote_bar) : "memory");
+    } else {
+#pragma unroll
+        for (int q = 0; q < NR / 4; ++q)
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr + 16 * q),
+                         "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3]), "r"(remote_bar) : "memory");
+    }
+}
+__device__ __forceinline__ void st_async_word(uint32_t remote_addr, uint32_t v, uint32_t remote_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
+}
+
 template <int NR, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __restrict__ C, uint16_t* __restrict__ S, int W1, int H,
                                                              int D, int P1, int P2, int T, uint32_t one, int pf_rows)
@@ -40,23 +86,41 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int LW = 32 * NR;                  // words per (column, direction) line
     constexpr int LWB = LW * 4;                  // bytes per line
+    constexpr uint32_t kHandBytes = LWB + 4;     // one hand-over: a state line + its packed minimum
 
     const int x0 = rank * T;
     const int Tc = max(0, min(T, W1 - x0));      // columns of this CTA (the last strips may be shorter or empty)
-    const int R = Tc + 1;                        // ring length of the diagonal directions: one spare slot for the halo column
+    const int R = Tc + 2;                        // ring length of the diagonal directions: two spare slots, because the
+                                                 // neighbour that fills the halo slot may run one row ahead of this CTA
     const bool has_left = rank > 0 && Tc > 0;
     const bool has_right = Tc > 0 && (x0 + T < W1);
     const int Tn = has_right ? min(T, W1 - (x0 + T)) : 0;   // columns of the right neighbour (the left one always has T)
 
-    // shared memory: st0 [T] lines (down), st1 / st2 [T+1] lines (rings), then the three arrays of packed minima
-    const int n_state = (3 * T + 2) * LW;
-    const int n_all = n_state + 3 * (T + 1);
+    // shared memory: st0 [T] lines (down), st1 / st2 [T+2] lines (rings), the three arrays of packed minima, two mbarriers
+    const int n_state = (3 * T + 4) * LW;
+    const int n_min = (3 * (T + 2) + 1) & ~1;     // keeps the mbarriers 8-byte aligned
+    const int n_all = n_state + n_min + 4;
     for (int i = threadIdx.x; i < n_all; i += NWARPS * 32) smem[i] = 0u;
     char* const sm = reinterpret_cast<char*>(smem);
-    const int b0 = lane * NR * 4, b1 = b0 + T * LWB, b2 = b1 + (T + 1) * LWB;   // byte offsets incl. this lane's words
-    const int mb0 = n_state * 4, mb1 = mb0 + T * 4, mb2 = mb1 + (T + 1) * 4;
-    char* const right_sm = has_right ? reinterpret_cast<char*>(cluster.map_shared_rank(smem, rank + 1)) : nullptr;
-    char* const left_sm = has_left ? reinterpret_cast<char*>(cluster.map_shared_rank(smem, rank - 1)) : nullptr;
+    const int b0 = lane * NR * 4, b1 = b0 + T * LWB, b2 = b1 + (T + 2) * LWB;   // byte offsets incl. this lane's words
+    const int mb0 = n_state * 4, mb1 = mb0 + (T + 2) * 4, mb2 = mb1 + (T + 2) * 4;
+    const uint32_t sm_a = smem_u32(smem);
+    const uint32_t bar_l = sm_a + (uint32_t)(n_state + n_min) * 4;      // credited by the left neighbour (ring 1 halo)
+    const uint32_t bar_r = bar_l + 8;                                          // credited by the right neighbour (ring 2 halo)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_init(bar_l, 1);
+        mbar_init(bar_r, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // phase 0 collects what the neighbours produce during their row 0
+        if (has_left) mbar_arrive_expect_tx(bar_l, kHandBytes);
+        if (has_right) mbar_arrive_expect_tx(bar_r, kHandBytes);
+    }
+    // peers' windows onto this layout
+    const uint32_t right_a = has_right ? mapa_u32(sm_a, (uint32_t)(rank + 1)) : 0u;
+    const uint32_t left_a = has_left ? mapa_u32(sm_a, (uint32_t)(rank - 1)) : 0u;
+    const uint32_t right_bar_l = has_right ? mapa_u32(bar_l, (uint32_t)(rank + 1)) : 0u;   // my ring-1 data lands at the right peer's bar_l
+    const uint32_t left_bar_r = has_left ? mapa_u32(bar_r, (uint32_t)(rank - 1)) : 0u;
     cluster.sync();
 
     const int d0 = lane * 2 * NR;
@@ -78,18 +142,29 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
 
     // ring phases: my column c lives in slot (c + o1) mod R of ring 1 and (c + o2) mod R of ring 2
     int o1 = 0, o2 = 0;
-    int h1 = Tc;                                 // ring-1 slot of my halo column -1 written during this row: (-1 - y) mod R
-    int h2 = Tc;                                 // ring-2 slot of my halo column Tc written during this row: (Tc + y) mod R
-    int n1 = Tn;                                 // the same slot in the right neighbour's ring 1: (-1 - y) mod (Tn + 1)
-    int l2 = T;                                  // and in the left neighbour's ring 2: (T + y) mod (T + 1)
-    // L2 prefetch (one TMA bulk instruction per row and CTA) pf_rows rows ahead of the register prefetch below:
-    // the per-row cluster barrier's release fence waits for every outstanding load, so their latency must be short
+    int h1 = Tc + 1;                             // ring-1 slot of my halo column -1 for this row's hand-over: (-1 - y) mod R
+    int h2 = Tc;                                 // ring-2 slot of my halo column Tc: (Tc + y) mod R
+    int n1 = Tn + 1;                             // the same slot in the right neighbour's ring 1: (-1 - y) mod (Tn + 2)
+    int l2 = T;                                  // and in the left neighbour's ring 2: (T + y) mod (T + 2)
+    // L2 prefetch (one TMA bulk instruction per row and CTA) pf_rows rows ahead of the register prefetch below
     const uint32_t seg_bytes = (uint32_t)Tc * D * 2;            // my strip of one cost row is contiguous in memory
     const char* const Cseg = Crow - d0 * 2;
     if (threadIdx.x == 0 && Tc > 0 && pf_rows > 0)
         for (int q = 1; q < pf_rows && q < H; ++q) l2_prefetch_bulk(Cseg + (size_t)q * rowbytes, seg_bytes);
     for (int y = 0; y < H; ++y) {
         if (threadIdx.x == 0 && Tc > 0 && pf_rows > 0 && y + pf_rows < H) l2_prefetch_bulk(Cseg + (size_t)(y + pf_rows) * rowbytes, seg_bytes);
+        // the hand-overs of the neighbours' previous row must have landed before the border columns are touched
+        if (y > 0) {
+            const uint32_t parity = (uint32_t)(y - 1) & 1u;
+            if (warp == 0 && has_left) {
+                mbar_wait_cluster(bar_l, parity);
+                if (lane == 0) mbar_arrive_expect_tx(bar_l, kHandBytes);      // arm the next phase (this row's hand-over)
+            }
+            if (warp == wl && has_right) {
+                mbar_wait_cluster(bar_r, parity);
+                if (lane == 0) mbar_arrive_expect_tx(bar_r, kHandBytes);
+            }
+        }
         uint32_t off = (uint32_t)warp * D * 2;
         int c = warp;
         int s1 = c + o1; s1 = (int)min((unsigned)s1, (unsigned)(s1 - R));
@@ -131,15 +206,19 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
             s1 += NWARPS; s1 = (int)min((unsigned)s1, (unsigned)(s1 - R));
             s2 += NWARPS; s2 = (int)min((unsigned)s2, (unsigned)(s2 - R));
         }
-        // hand the strip's border columns to the neighbours (or feed zeros at the image border)
+        // hand the strip's border columns to the neighbours (asynchronous stores that credit the peer's mbarrier; no
+        // fence, no cluster barrier), or feed zeros at the image border.  Nothing is sent after the last row: the
+        // peer may already have left.
         if (warp == wl) {
             // my last column's down-right state is the right neighbour's halo column -1 for the next row
             int sl = Tc - 1 + o1; sl = (int)min((unsigned)sl, (unsigned)(sl - R));
             if (has_right) {
-                uint32_t Lx[NR];
-                load_words<NR>(sm + sl * LWB + b1, Lx);
-                store_words<NR>(right_sm + n1 * LWB + b1, Lx);
-                if (lane == 0) *(reinterpret_cast<uint32_t*>(right_sm + mb1) + n1) = *(reinterpret_cast<uint32_t*>(sm + mb1) + sl);
+                if (y + 1 < H) {
+                    uint32_t Lx[NR];
+                    load_words<NR>(sm + sl * LWB + b1, Lx);
+                    st_async_words<NR>(right_a + (uint32_t)(n1 * LWB + b1), Lx, right_bar_l);
+                    if (lane == 0) st_async_word(right_a + (uint32_t)(mb1 + n1 * 4), *(reinterpret_cast<uint32_t*>(sm + mb1) + sl), right_bar_l);
+                }
             } else if (Tc > 0) {
                 // image border on the right: the down-left predecessor of my last column is the zero state
                 uint32_t Z[NR];
@@ -151,10 +230,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
         }
         if (warp == 0 && Tc > 0) {
             if (has_left) {
-                uint32_t Lx[NR];
-                load_words<NR>(sm + o2 * LWB + b2, Lx);         // my column 0 lives in ring-2 slot (0 + o2)
-                store_words<NR>(left_sm + l2 * LWB + b2, Lx);
-                if (lane == 0) *(reinterpret_cast<uint32_t*>(left_sm + mb2) + l2) = *(reinterpret_cast<uint32_t*>(sm + mb2) + o2);
+                if (y + 1 < H) {
+                    uint32_t Lx[NR];
+                    load_words<NR>(sm + o2 * LWB + b2, Lx);         // my column 0 lives in ring-2 slot (0 + o2)
+                    st_async_words<NR>(left_a + (uint32_t)(l2 * LWB + b2), Lx, left_bar_r);
+                    if (lane == 0) st_async_word(left_a + (uint32_t)(mb2 + l2 * 4), *(reinterpret_cast<uint32_t*>(sm + mb2) + o2), left_bar_r);
+                }
             } else {
                 uint32_t Z[NR];
 #pragma unroll
@@ -170,10 +251,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
         o2 = o2 + 1 == R ? 0 : o2 + 1;
         h1 = h1 == 0 ? R - 1 : h1 - 1;
         h2 = h2 + 1 == R ? 0 : h2 + 1;
-        n1 = n1 == 0 ? Tn : n1 - 1;
-        l2 = l2 == T ? 0 : l2 + 1;
-        cluster.sync();
+        n1 = n1 == 0 ? Tn + 1 : n1 - 1;
+        l2 = l2 == T + 1 ? 0 : l2 + 1;
+        __syncthreads();                         // the strip's own columns: row y is complete before row y + 1 reads it
     }
+    cluster.sync();                              // nobody leaves while a peer could still address its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -215,7 +297,7 @@ static int launch_vertical_t(ssm_ctx* c, int B, const VerticalPlan& plan, cudaSt
 static size_t vertical_smem(int NR, int T)
 {
     const int LW = 32 * NR;
-    return sizeof(uint32_t) * ((size_t)(3 * T + 2) * LW + 3 * (T + 1));
+    return sizeof(uint32_t) * ((size_t)(3 * T + 4) * LW + ((3 * (T + 2) + 1) & ~1) + 4);
 }
 
 // Smallest cluster whose per-CTA strip fits shared memory.  Returns false when none does (caller falls back to the
@@ -224,7 +306,7 @@ static bool plan_vertical(const ssm_ctx* c, VerticalPlan& plan)
 {
     const DevParams& p = c->dp;
     const int NR = p.D <= 64 ? 1 : (p.D <= 128 ? 2 : (p.D <= 256 ? 4 : 8));
-    const size_t limit = 220 * 1024;
+    const size_t limit = 225 * 1024;
     for (int cs : {1, 2, 4, 8, 16}) {
         if (cs > c->max_cluster) break;
         if (cs < c->min_cluster) continue;
