@@ -175,9 +175,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     p = Params(num_disparities=D, max_width=W, max_height=H, max_batch=B, resolution=LEAF, map_capacity=args.map_capacity)
     ctx = Context(p, device=local_rank)
     if world > 1:
-        uid = torch.from_numpy(Context.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
-        dist.broadcast(uid, 0)
-        ctx.comm_init(uid.cpu().numpy(), rank, world)
+        from semantic_slam_mapping_b200 import distributed as ssm_dist
+        ssm_dist.init_comm(ctx, p2p=not args.no_p2p)   # NCCL communicator + (default) peer-memory inboxes over NVLink
 
     # synthetic sequence: this rank's frames (frame batches are sharded per GPU; poses continue across ranks)
     n_frames = nb * B
@@ -294,7 +293,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                "12-class masks, 0.05 m voxel map", "frames_per_step_per_gpu": B, "distinct_input_batches": nb,
                    "l2": "each step streams > 2 GB of cost volumes through HBM (>> 126 MB L2); input batches cycle",
                    "voxels_in_map_rank0": n_vox, "points_per_frame": pts,
-                   "parallelism": f"frames sharded over {world} GPU(s); voxel hash spatially owned, NCCL all-to-all" if world > 1 else "1 GPU"},
+                   "parallelism": (f"frames sharded over {world} GPU(s); voxel hash spatially owned; points routed to the owner by "
+                                   + ("NCCL send/recv all-to-all" if args.no_p2p else "peer-memory stores over NVLink fused into the point kernel + NCCL barrier"))
+                   if world > 1 else "1 GPU"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * (2 * W * H + 6 * W * H + 128), "d2h_bytes_per_step": 16},
         "gpu_launches": int(launches),
         "clocks": clk,
@@ -317,6 +318,7 @@ def main():
     ap.add_argument("--map-capacity", type=int, default=1 << 24)
     ap.add_argument("--ref-frames-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL send/recv all-to-all instead of peer-memory routing")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -156,6 +156,14 @@ int ssm_synchronize(ssm_ctx* ctx);
 #define SSM_UNIQUE_ID_BYTES 128
 int ssm_comm_get_unique_id(uint8_t id[SSM_UNIQUE_ID_BYTES]);               /* rank 0, then broadcast by the host */
 int ssm_comm_init(ssm_ctx* ctx, const uint8_t id[SSM_UNIQUE_ID_BYTES], int rank, int nranks);
+/* Peer-memory routing (preferred on one NVLink/NVSwitch box): after ssm_comm_init every rank exports its inbox as a
+ * CUDA IPC handle, the host all-gathers the handles ([nranks][SSM_IPC_HANDLE_BYTES]) and every rank connects.  From
+ * then on point generation and the dispatch all-to-all are ONE kernel (peer stores over NVLink), followed by a
+ * stream-ordered NCCL barrier and the fusion of the rank's inbox; no host synchronisation per batch.  Without this
+ * call the NCCL send/recv all-to-all is used. */
+#define SSM_IPC_HANDLE_BYTES 64
+int ssm_comm_ipc_export(ssm_ctx* ctx, uint8_t handle[SSM_IPC_HANDLE_BYTES]);
+int ssm_comm_ipc_connect(ssm_ctx* ctx, const uint8_t* handles, int nranks);
 int ssm_comm_destroy(ssm_ctx* ctx);
 /* owner rank of a voxel (pure function of ijk, brick shift and nranks; exposed for host-side tests) */
 int ssm_voxel_owner(int32_t i, int32_t j, int32_t k, int nranks);

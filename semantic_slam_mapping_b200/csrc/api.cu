@@ -127,7 +127,10 @@ static int run_map(ssm_ctx* c, int B, const int16_t* d_disp, const uint8_t* d_se
     int rc;
     if ((rc = launch_depth(c, B, d_disp, c->d_depth, s))) return rc;
     if ((rc = launch_labels_mask(c, B, d_sem, s))) return rc;
-    if (c->nranks > 1) {
+    if (c->nranks > 1 && c->p2p) {
+        mark(c, 5, s);   // points are made, fused or sent to their owner in one kernel; then barrier + inbox fusion
+        if ((rc = points_route_p2p(c, B, c->d_depth, d_sem, d_rgb, d_pose, s))) return rc;
+    } else if (c->nranks > 1) {
         if ((rc = launch_points(c, B, c->d_depth, d_sem, d_rgb, d_pose, false, s))) return rc;
         mark(c, 5, s);
         if ((rc = route_and_fuse(c, s))) return rc;
@@ -166,6 +169,11 @@ static int check_overflow(ssm_ctx* c, cudaStream_t s, uint64_t* n_voxels)
     uint32_t h[4];
     SSM_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
     SSM_CUDA(cudaStreamSynchronize(s));
+    if (c->p2p && c->ipc_base) {
+        uint32_t flag = 0;
+        SSM_CUDA(cudaMemcpy(&flag, static_cast<char*>(c->ipc_base) + 8, sizeof(flag), cudaMemcpyDeviceToHost));
+        if (flag) return fail(SSM_ERR_CAPACITY, "peer inbox overflow: more routed points than 2x a local batch (raise max_batch)");
+    }
     if (h[2] & 1u) return fail(SSM_ERR_CAPACITY, "voxel hash table is full (raise ssm_params.map_capacity)");
     if (h[2] & 2u) return fail(SSM_ERR_CAPACITY, "point outside the 21-bit voxel coordinate range");
     if (n_voxels) *n_voxels = h[1];
@@ -451,7 +459,9 @@ int ssm_map_integrate_frame(ssm_ctx* c, const uint16_t* depth, const uint8_t* se
     cudaStream_t s = c->stream;
     if ((rc = upload_frame(c, depth, sem, rgb, w, h, T, s))) return rc;
     if ((rc = launch_labels_mask(c, 1, c->d_sem, s))) return rc;
-    if (c->nranks > 1) {
+    if (c->nranks > 1 && c->p2p) {
+        if ((rc = points_route_p2p(c, 1, c->d_depth, c->d_sem, c->d_rgb, c->d_pose, s))) return rc;
+    } else if (c->nranks > 1) {
         if ((rc = launch_points(c, 1, c->d_depth, c->d_sem, c->d_rgb, c->d_pose, false, s))) return rc;
         if ((rc = route_and_fuse(c, s))) return rc;
     } else if ((rc = launch_points(c, 1, c->d_depth, c->d_sem, c->d_rgb, c->d_pose, true, s))) {

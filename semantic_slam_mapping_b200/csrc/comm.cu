@@ -27,6 +27,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -51,6 +52,7 @@ static int load_nccl()
     SSM_SYM(CommInitRank, "ncclCommInitRank")
     SSM_SYM(CommDestroy, "ncclCommDestroy")
     SSM_SYM(AllGather, "ncclAllGather")
+    SSM_SYM(AllReduce, "ncclAllReduce")
     SSM_SYM(Send, "ncclSend")
     SSM_SYM(Recv, "ncclRecv")
     SSM_SYM(GroupStart, "ncclGroupStart")
@@ -172,6 +174,29 @@ int route_and_fuse(ssm_ctx* c, cudaStream_t s)
     return launch_fuse_points(c, c->d_recv, nullptr, (uint32_t)total_recv, s);
 }
 
+// stream-ordered barrier over the ranks: a one-word all-reduce (no host synchronisation)
+int comm_barrier(ssm_ctx* c, cudaStream_t s)
+{
+    if (!c->comm) {
+        set_error("ssm_comm_init has not been called on this context");
+        return SSM_ERR_COMM;
+    }
+    uint32_t* word = c->d_send_counts;   // scratch
+    SSM_NCCL(g_nccl.AllReduce(word, word, 1, ncclUint32, 0 /* ncclSum */, (ncclComm_t)c->comm, s));
+    return SSM_OK;
+}
+
+int points_route_p2p(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t* d_sem, const uint8_t* d_rgb, const double* d_pose,
+                     cudaStream_t s)
+{
+    const int parity = (int)(c->p2p_step & 1u);
+    c->p2p_step++;
+    int rc = launch_points_p2p(c, B, d_depth, d_sem, d_rgb, d_pose, c->d_peer_base, parity, s);
+    if (rc) return rc;
+    if ((rc = comm_barrier(c, s))) return rc;   // every peer's stores for this step have landed
+    return launch_fuse_inbox(c, parity, s);
+}
+
 }  // namespace ssm
 
 using namespace ssm;
@@ -214,8 +239,57 @@ int ssm_comm_init(ssm_ctx* c, const uint8_t id[SSM_UNIQUE_ID_BYTES], int rank, i
     return SSM_OK;
 }
 
+int ssm_comm_ipc_export(ssm_ctx* c, uint8_t handle[SSM_IPC_HANDLE_BYTES])
+{
+    if (!c || !handle) { set_error("null argument"); return SSM_ERR_INVALID_ARGUMENT; }
+    if (!c->comm) { set_error("call ssm_comm_init first"); return SSM_ERR_COMM; }
+    static_assert(sizeof(cudaIpcMemHandle_t) <= SSM_IPC_HANDLE_BYTES, "handle size");
+    SSM_CUDA(cudaSetDevice(c->device));
+    if (!c->ipc_base) {
+        // worst case every peer's whole batch is owned by this rank; sized for twice a local batch per parity,
+        // overflow is reported (SSM_ERR_CAPACITY) rather than silently dropped
+        c->inbox_cap = 2 * (size_t)c->cap_w * c->cap_h * c->cap_b;
+        const size_t bytes = kInboxHeader + 2 * c->inbox_cap * sizeof(Point);
+        SSM_CUDA(cudaMalloc(&c->ipc_base, bytes));
+        SSM_CUDA(cudaMemset(c->ipc_base, 0, kInboxHeader));
+    }
+    cudaIpcMemHandle_t h;
+    SSM_CUDA(cudaIpcGetMemHandle(&h, c->ipc_base));
+    memset(handle, 0, SSM_IPC_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof(h));
+    return SSM_OK;
+}
+
+int ssm_comm_ipc_connect(ssm_ctx* c, const uint8_t* handles, int nranks)
+{
+    if (!c || !handles) { set_error("null argument"); return SSM_ERR_INVALID_ARGUMENT; }
+    if (!c->comm || !c->ipc_base || nranks != c->nranks || nranks > ssm_ctx::kMaxPeers) {
+        set_error("ssm_comm_ipc_connect needs ssm_comm_init + ssm_comm_ipc_export first, with the same rank count");
+        return SSM_ERR_COMM;
+    }
+    SSM_CUDA(cudaSetDevice(c->device));
+    for (int r = 0; r < nranks; ++r) {
+        if (r == c->rank) { c->peer_base[r] = c->ipc_base; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * SSM_IPC_HANDLE_BYTES, sizeof(h));
+        SSM_CUDA(cudaIpcOpenMemHandle(&c->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    SSM_CUDA(cudaMalloc(&c->d_peer_base, sizeof(void*) * nranks));
+    SSM_CUDA(cudaMemcpy(c->d_peer_base, c->peer_base, sizeof(void*) * nranks, cudaMemcpyHostToDevice));
+    c->p2p = true;
+    c->p2p_step = 0;
+    return SSM_OK;
+}
+
 int ssm_comm_destroy(ssm_ctx* c)
 {
+    if (c && c->p2p) {
+        for (int r = 0; r < c->nranks; ++r)
+            if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+        c->p2p = false;
+    }
+    if (c && c->d_peer_base) { cudaFree(c->d_peer_base); c->d_peer_base = nullptr; }
+    if (c && c->ipc_base) { cudaFree(c->ipc_base); c->ipc_base = nullptr; }
     if (!c || !c->comm) return SSM_OK;
     g_nccl.CommDestroy((ncclComm_t)c->comm);
     c->comm = nullptr;

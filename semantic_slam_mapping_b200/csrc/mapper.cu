@@ -200,6 +200,51 @@ __global__ void __launch_bounds__(256) k_points_fuse(const uint16_t* __restrict_
     }
 }
 
+// P2P mode (multi-GPU): straight from pixels; locally owned points go into this rank's hash, the others are appended
+// to their owner's inbox through the peer mapping (NVLink stores; slots are reserved with one system-scope atomic per
+// (warp, owner) group).  The compute step (back-projection, transform) and the dispatch all-to-all are one kernel.
+__global__ void __launch_bounds__(256) k_points_p2p(const uint16_t* __restrict__ depth, const uint8_t* __restrict__ label,
+                                                    const uint8_t* __restrict__ mask, const uint8_t* __restrict__ sem,
+                                                    const uint8_t* __restrict__ rgb, const double* __restrict__ pose,
+                                                    Voxel* __restrict__ table, uint64_t slot_mask, uint32_t* counters,
+                                                    void* const* __restrict__ peer_base, int rank, int nranks, int parity,
+                                                    uint32_t inbox_cap, size_t total, SSM_DP)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    Point pt;
+    int owner = -1;
+    if (idx < total && make_point(p, idx, depth, label, mask, sem, rgb, pose, pt) && isfinite(pt.x) && isfinite(pt.y) && isfinite(pt.z)) {
+        const int i = (int)floorf(__fmul_rn(pt.x, p.inv_leaf));
+        const int j = (int)floorf(__fmul_rn(pt.y, p.inv_leaf));
+        const int k = (int)floorf(__fmul_rn(pt.z, p.inv_leaf));
+        owner = voxel_owner(i, j, k, nranks);
+        atomicAdd(&counters[0], 1u);
+    }
+    if (owner == rank) fuse_point(p, table, slot_mask, pt, counters);
+    // remote points: group the warp's lanes by owner
+    uint32_t pending = __ballot_sync(0xffffffffu, owner >= 0 && owner != rank);
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const int o = __shfl_sync(0xffffffffu, owner, leader);
+        const uint32_t group = __ballot_sync(0xffffffffu, owner == o) & pending;
+        char* base = static_cast<char*>(peer_base[o]);
+        uint32_t slot0 = 0;
+        if (lane == leader) slot0 = atomicAdd_system(reinterpret_cast<uint32_t*>(base) + parity, (uint32_t)__popc(group));
+        slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+        if ((group >> lane) & 1u) {
+            const uint32_t slot = slot0 + __popc(group & ((1u << lane) - 1u));
+            if (slot < inbox_cap) {
+                Point* dst = reinterpret_cast<Point*>(base + kInboxHeader) + (size_t)parity * inbox_cap + slot;
+                *dst = pt;
+            } else {
+                atomicOr_system(reinterpret_cast<uint32_t*>(base) + 2, 1u);
+            }
+        }
+        pending &= ~group;
+    }
+}
+
 // COMPACT mode (ordered, row-major like the reference's push_back loop): count per block, scan, scatter
 constexpr int kCompactBlock = 1024;
 __global__ void __launch_bounds__(kCompactBlock) k_points_count(const uint16_t* __restrict__ depth, const uint8_t* __restrict__ label,
@@ -358,6 +403,30 @@ int launch_points(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t* d_s
     k_points_scatter<<<nblk, kCompactBlock, 0, s>>>(d_depth, c->d_label, c->d_mask, d_sem, d_rgb, d_pose, c->d_blk_count,
                                                     c->d_points, total, p);
     SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+int launch_points_p2p(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t* d_sem, const uint8_t* d_rgb, const double* d_pose,
+                      void* const* d_peer_base, int parity, cudaStream_t s)
+{
+    const DevParams& p = c->dp;
+    const size_t total = (size_t)p.W * p.H * B;
+    SSM_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t), s));
+    k_points_p2p<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_depth, c->d_label, c->d_mask, d_sem, d_rgb, d_pose, c->d_table,
+                                                                 c->table_slots - 1, c->d_counters, d_peer_base, c->rank, c->nranks, parity,
+                                                                 (uint32_t)c->inbox_cap, total, p);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+int launch_fuse_inbox(ssm_ctx* c, int parity, cudaStream_t s)
+{
+    char* base = static_cast<char*>(c->ipc_base);
+    const Point* pts = reinterpret_cast<const Point*>(base + kInboxHeader) + (size_t)parity * c->inbox_cap;
+    uint32_t* count = reinterpret_cast<uint32_t*>(base) + parity;
+    k_fuse_list<<<c->sm_count * 16, 256, 0, s>>>(pts, count, (uint32_t)c->inbox_cap, c->d_table, c->table_slots - 1, c->d_counters, c->dp);
+    SSM_LAUNCH_CHECK(c);
+    SSM_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));   // ready for the step after next
     return SSM_OK;
 }
 

@@ -76,6 +76,9 @@ struct DevParams {
     int dilate_radius, colour_source;
 };
 
+// inbox layout: [256-byte header: u32 count[2] (per parity), u32 overflow][parity 0 points][parity 1 points]
+constexpr size_t kInboxHeader = 256;
+
 struct Point {                              // routed between ranks, 20 bytes
     float x, y, z;
     uint32_t rgba;                          // 0x00RRGGBB
@@ -136,6 +139,15 @@ struct ssm_ctx {
     ssm::Point *d_send = nullptr, *d_recv = nullptr; // routing buffers
     uint32_t *d_send_counts = nullptr;               // [nranks] + offsets
     size_t route_cap = 0;
+    // peer-memory routing (ssm_comm_ipc_*): every rank owns an inbox = {header, two point buffers (step parity)} that
+    // its peers append to directly over NVLink
+    static constexpr int kMaxPeers = 64;
+    void* ipc_base = nullptr;                        // this rank's inbox allocation (exported through CUDA IPC)
+    void* peer_base[kMaxPeers] = {};                 // peers' inbox allocations as mapped into this process (own entry = ipc_base)
+    void** d_peer_base = nullptr;                    // the same table on the device
+    size_t inbox_cap = 0;                            // points per parity buffer
+    bool p2p = false;
+    uint64_t p2p_step = 0;                           // parity source
 };
 
 namespace ssm {
@@ -174,6 +186,14 @@ int launch_map_clear(ssm_ctx* c, cudaStream_t s);
 int launch_export(ssm_ctx* c, Voxel* d_out, uint32_t max_out, cudaStream_t s);
 int launch_route_bucket(ssm_ctx* c, uint32_t max_points, cudaStream_t s);   // d_points -> d_send grouped by owner rank
 int route_and_fuse(ssm_ctx* c, cudaStream_t s);   // multi-GPU: bucket by owner, NCCL all-to-all, fuse received
+// multi-GPU, peer-memory path: one kernel makes the points, fuses the locally owned ones and appends the others to
+// their owner's inbox over NVLink; then a stream-ordered NCCL barrier and the fusion of this rank's inbox
+int points_route_p2p(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t* d_sem, const uint8_t* d_rgb, const double* d_pose,
+                     cudaStream_t s);
+int launch_points_p2p(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t* d_sem, const uint8_t* d_rgb, const double* d_pose,
+                      void* const* d_peer_base, int parity, cudaStream_t s);
+int launch_fuse_inbox(ssm_ctx* c, int parity, cudaStream_t s);
+int comm_barrier(ssm_ctx* c, cudaStream_t s);
 
 // packed 16x2 helpers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t dup16(int v) { return (uint32_t)(v & 0xffff) * 0x10001u; }

@@ -21,7 +21,7 @@ SYMBOLS = [
     "ssm_disparity_to_depth", "ssm_semantic_motion_fuse", "ssm_generate_point_cloud", "ssm_map_integrate_frame",
     "ssm_map_integrate_points", "ssm_map_clear", "ssm_map_size", "ssm_map_export", "ssm_map_save_pcd",
     "ssm_pipeline_batch_device", "ssm_pipeline_batch_host", "ssm_synchronize", "ssm_comm_get_unique_id",
-    "ssm_comm_init", "ssm_comm_destroy", "ssm_voxel_owner",
+    "ssm_comm_init", "ssm_comm_ipc_export", "ssm_comm_ipc_connect", "ssm_comm_destroy", "ssm_voxel_owner",
 ]
 
 
@@ -76,6 +76,8 @@ def load() -> C.CDLL:
     L.ssm_synchronize.argtypes = [vp]
     L.ssm_comm_get_unique_id.argtypes = [vp]
     L.ssm_comm_init.argtypes = [vp, vp, i, i]
+    L.ssm_comm_ipc_export.argtypes = [vp, vp]
+    L.ssm_comm_ipc_connect.argtypes = [vp, vp, i]
     L.ssm_comm_destroy.argtypes = [vp]
     L.ssm_voxel_owner.argtypes = [C.c_int32, C.c_int32, C.c_int32, i]
     _lib = L
@@ -266,3 +268,12 @@ class Context:
     def comm_init(self, unique_id: np.ndarray, rank: int, nranks: int):
         uid = np.ascontiguousarray(unique_id, np.uint8)
         self._check(self._L.ssm_comm_init(self._h, _ptr(uid), rank, nranks))
+
+    def comm_ipc_export(self) -> np.ndarray:
+        h = np.zeros(64, np.uint8)
+        self._check(self._L.ssm_comm_ipc_export(self._h, _ptr(h)))
+        return h
+
+    def comm_ipc_connect(self, handles: np.ndarray):
+        handles = np.ascontiguousarray(handles, np.uint8)
+        self._check(self._L.ssm_comm_ipc_connect(self._h, _ptr(handles), handles.shape[0]))
