@@ -148,7 +148,7 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         vp = C.c_void_p
         L.oracle_sgbm.restype = C.c_int
-        L.oracle_sgbm.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, C.POINTER(_SgbmParams), vp, C.c_size_t, vp, vp, vp, vp, vp]
+        L.oracle_sgbm.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, C.POINTER(_SgbmParams), vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
         L.oracle_median3x3_s16.argtypes = [vp, vp, C.c_int, C.c_int]
         L.oracle_filter_speckles.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle_disparity_to_depth.argtypes = [vp, C.c_int, C.c_int, C.POINTER(_MapParams), vp]
@@ -181,16 +181,17 @@ def sgbm(left: np.ndarray, right: np.ndarray, params: SgbmParams, want_volumes: 
     D = params.num_disparities
     disp = np.empty((H, W), np.int16)
     vols = {}
-    Cv = Sv = raw = med = Sf = None
+    Cv = Sv = raw = med = Sf = Svert = None
     if want_volumes:
         Cv = np.empty((H, W - D, D), np.int16)
         Sv = np.empty((H, W - D, D), np.int16)
         Sf = np.empty((H, W - D, D), np.int16)
+        Svert = np.empty((H, W - D, D), np.int16)
         raw = np.empty((H, W), np.int16)
         med = np.empty((H, W), np.int16)
-        vols = {"C": Cv, "S": Sv, "Sf": Sf, "disp_raw": raw, "disp_median": med}
+        vols = {"C": Cv, "S": Sv, "Sf": Sf, "Sv": Svert, "disp_raw": raw, "disp_median": med}
     cp = params.c()
-    rc = lib().oracle_sgbm(_p(left), _p(right), W, H, W, C.byref(cp), _p(disp), W, _p(Cv), _p(Sv), _p(raw), _p(med), _p(Sf))
+    rc = lib().oracle_sgbm(_p(left), _p(right), W, H, W, C.byref(cp), _p(disp), W, _p(Cv), _p(Sv), _p(raw), _p(med), _p(Sf), _p(Svert))
     if rc != 0:
         raise ValueError(f"oracle_sgbm rejected the arguments (rc={rc})")
     return (disp, vols) if want_volumes else disp

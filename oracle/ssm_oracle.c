@@ -174,7 +174,7 @@ static inline int sat16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768
 
 /* A-4..A-6: 5-direction single-pass aggregation, WTA, uniqueness, sub-pixel, disp2, L-R check. */
 static void aggregate_and_select(const int16_t* C, int W, int H, int D, const osgbm_params* p, int16_t* disp,
-                                 size_t dstride, int16_t* S_out, int16_t* Sf_out)
+                                 size_t dstride, int16_t* S_out, int16_t* Sf_out, int16_t* Sv_out)
 {
     const int W1 = W - D, minX1 = D;
     const int P1 = p->p1 > 0 ? p->p1 : 2;
@@ -224,6 +224,9 @@ static void aggregate_and_select(const int16_t* C, int W, int H, int D, const os
                 s = sat16(s + Lcur[1][(size_t)xp * D + d]);
                 s = sat16(s + Lcur[2][(size_t)xp * D + d]);
                 Sp[d] = (int16_t)s;
+                if (Sv_out) /* the three top-down directions alone (a device-side intermediate, for stage parity) */
+                    Sv_out[row * y + (size_t)xp * D + d] = (int16_t)sat16(
+                        sat16(Lcur[0][(size_t)xp * D + d] + Lcur[1][(size_t)xp * D + d]) + Lcur[2][(size_t)xp * D + d]);
             }
         }
         if (Sf_out) memcpy(Sf_out + row * y, S, sizeof(int16_t) * row); /* S_f = sat(L0+L1+L2+L3) */
@@ -362,7 +365,7 @@ void oracle_filter_speckles(int16_t* img, int W, int H, int new_val, int max_spe
 
 int oracle_sgbm(const uint8_t* left, const uint8_t* right, int W, int H, size_t stride, const osgbm_params* p,
                 int16_t* disp, size_t dstride, int16_t* C_out, int16_t* S_out, int16_t* disp_raw_out,
-                int16_t* disp_median_out, int16_t* Sf_out)
+                int16_t* disp_median_out, int16_t* Sf_out, int16_t* Sv_out)
 {
     const int D = p->num_disparities;
     if (D <= 0 || D % 16 != 0 || W <= D || H <= 0 || p->block_size < 1 || p->block_size % 2 == 0) return -1;
@@ -372,7 +375,7 @@ int oracle_sgbm(const uint8_t* left, const uint8_t* right, int W, int H, size_t 
     cost_volume(left, right, W, H, stride, D, p->block_size, ftzero, C);
 
     int16_t* raw = (int16_t*)malloc(sizeof(int16_t) * (size_t)W * H);
-    aggregate_and_select(C, W, H, D, p, raw, (size_t)W, S_out, Sf_out);
+    aggregate_and_select(C, W, H, D, p, raw, (size_t)W, S_out, Sf_out, Sv_out);
     if (!C_out) free(C);
     if (disp_raw_out) memcpy(disp_raw_out, raw, sizeof(int16_t) * (size_t)W * H);
 

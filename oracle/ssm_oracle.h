@@ -59,7 +59,8 @@ typedef struct {
 int oracle_sgbm(const uint8_t* left, const uint8_t* right, int W, int H, size_t stride,
                 const osgbm_params* p, int16_t* disp, size_t disp_stride_elems,
                 int16_t* C_out, int16_t* S_out, int16_t* disp_raw_out, int16_t* disp_median_out,
-                int16_t* Sf_out /* sat(L0+L1+L2+L3), before the right-to-left path is added */);
+                int16_t* Sf_out /* sat(L0+L1+L2+L3), before the right-to-left path is added */,
+                int16_t* Sv_out /* sat(L1+L2+L3): the three top-down directions alone */);
 
 void oracle_median3x3_s16(const int16_t* src, int16_t* dst, int W, int H);
 void oracle_filter_speckles(int16_t* img, int W, int H, int new_val, int max_speckle_size, int max_diff);

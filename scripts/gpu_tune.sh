@@ -8,7 +8,7 @@ import json
 d=json.load(open('gpurun_out/tune.json'))
 print('cfg=$cfg', round(d['value'],1),'fps', {k:v['ms_per_step'] for k,v in d['roofline']['stages'].items()})
 PY
-  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_vertical3|k_hsweep|k_cost_fused" -s 6 -c 3 --csv --log-file gpurun_out/tune_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --batch ${B:-33} --input-batches 2 > /dev/null 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_vertical3|k_hsweep|k_cost_fused|k_hfwd|k_hrev" -s 8 -c 4 --csv --log-file gpurun_out/tune_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --batch ${B:-33} --input-batches 2 > /dev/null 2>&1
   python - <<'PY'
 import csv
 rows=[r for r in csv.reader(open('gpurun_out/tune_launches.csv')) if len(r)>10 and r[0].isdigit()]

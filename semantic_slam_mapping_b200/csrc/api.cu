@@ -86,7 +86,7 @@ static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<
 static void free_all(ssm_ctx* c)
 {
     void* ptrs[] = {c->d_left, c->d_right, c->d_recL, c->d_recR, c->d_C, c->d_S, c->d_disp_raw, c->d_disp_lr, c->d_disp_med,
-                    c->d_disp, c->d_disp2key, c->d_wta_rec, c->d_uniq_thr, c->d_cc_label, c->d_cc_size, c->d_depth, c->d_label, c->d_mask, c->d_sem,
+                    c->d_disp, c->d_disp2key, c->d_wta_rec, c->d_ck, c->d_uniq_thr, c->d_cc_label, c->d_cc_size, c->d_depth, c->d_label, c->d_mask, c->d_sem,
                     c->d_rgb, c->d_pose, c->d_min_disp, c->d_points, c->d_blk_count, c->d_counters, c->d_table, c->d_send,
                     c->d_recv, c->d_send_counts};
     for (void* q : ptrs)
@@ -94,6 +94,11 @@ static void free_all(ssm_ctx* c)
     for (auto& set : c->ev)
         for (auto& e : set)
             if (e) cudaEventDestroy(e);
+    for (auto& st : c->sub_stream)
+        if (st) cudaStreamDestroy(st);
+    for (auto& e : c->sub_join)
+        if (e) cudaEventDestroy(e);
+    if (c->sub_fork) cudaEventDestroy(c->sub_fork);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -144,6 +149,62 @@ static int run_map(ssm_ctx* c, int B, const int16_t* d_disp, const uint8_t* d_se
         c->ev_set = (c->ev_set + 1) % ssm_ctx::kEvSets;
     }
     return SSM_OK;
+}
+
+// Shift every per-frame work buffer of the context by `frames` frames (positive or negative): a sub-batch then runs
+// through the unchanged stage launchers on its own slice of the buffers.
+static void offset_buffers(ssm_ctx* c, ptrdiff_t frames)
+{
+    const ptrdiff_t npix = (ptrdiff_t)c->dp.W * c->dp.H * frames;
+    const ptrdiff_t cells = (ptrdiff_t)c->dp.W1 * c->dp.H * c->dp.D * frames;
+    c->d_recL += npix; c->d_recR += npix;
+    c->d_C += cells; c->d_S += cells; c->d_hs += cells;
+    c->d_disp_raw += npix; c->d_disp_lr += npix; c->d_disp_med += npix; c->d_disp += npix;
+    c->d_disp2key += npix; c->d_wta_rec += 2 * npix; c->d_cc_label += npix;
+    if (c->d_ck) c->d_ck += (ptrdiff_t)hsweep2_ck_words(c->dp.W1, c->dp.D, c->dp.H, 1) * frames; c->d_cc_size += npix;
+    c->d_depth += npix; c->d_label += npix; c->d_mask += npix;
+    c->d_min_disp += frames;
+}
+
+static int run_map(ssm_ctx* c, int B, const int16_t* d_disp, const uint8_t* d_sem, const uint8_t* d_rgb, const double* d_pose, cudaStream_t s);
+
+// The whole path on device buffers.  With SSM_TUNE3 = n > 1 (single GPU) the batch is cut into n sub-batches that run
+// on n streams and meet again on `s`.
+static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, const uint8_t* d_sem, const uint8_t* d_rgb,
+                        const double* d_pose, int16_t* d_disp, cudaStream_t s)
+{
+    int rc;
+    const int nsplit = std::min({c->tune[3], (int)ssm_ctx::kMaxSplit, B});
+    if (nsplit <= 1 || c->nranks > 1 || c->timing) {
+        if ((rc = run_sgbm(c, B, dL, dR, d_disp, s))) return rc;
+        return run_map(c, B, d_disp, d_sem, d_rgb, d_pose, s);
+    }
+    const size_t npix = (size_t)c->dp.W * c->dp.H;
+    if (!c->sub_fork) {
+        SSM_CUDA(cudaEventCreateWithFlags(&c->sub_fork, cudaEventDisableTiming));
+        for (int i = 0; i < ssm_ctx::kMaxSplit; ++i) {
+            SSM_CUDA(cudaStreamCreateWithFlags(&c->sub_stream[i], cudaStreamNonBlocking));
+            SSM_CUDA(cudaEventCreateWithFlags(&c->sub_join[i], cudaEventDisableTiming));
+        }
+    }
+    SSM_CUDA(cudaEventRecord(c->sub_fork, s));
+    int first = 0;
+    rc = SSM_OK;
+    for (int i = 0; i < nsplit && rc == SSM_OK; ++i) {
+        const int n = B / nsplit + (i < B % nsplit ? 1 : 0);
+        cudaStream_t ss = c->sub_stream[i];
+        SSM_CUDA(cudaStreamWaitEvent(ss, c->sub_fork, 0));
+        offset_buffers(c, first);
+        rc = run_sgbm(c, n, dL + first * npix, dR + first * npix, d_disp + first * npix, ss);
+        if (rc == SSM_OK) rc = run_map(c, n, d_disp + first * npix, d_sem + first * npix * 3, d_rgb + first * npix * 3, d_pose + (size_t)first * 16, ss);
+        offset_buffers(c, -first);
+        if (rc == SSM_OK) {
+            SSM_CUDA(cudaEventRecord(c->sub_join[i], ss));
+            SSM_CUDA(cudaStreamWaitEvent(s, c->sub_join[i], 0));
+        }
+        first += n;
+    }
+    return rc;
 }
 
 static int finish_timing(ssm_ctx* c)
@@ -246,6 +307,8 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
             static const int defaults[4] = {2 /* vertical: L2 prefetch distance in rows */, 0 /* hsweep: L2 prefetch off */, 0, 0};
             c->tune[t] = v ? atoi(v) : defaults[t];
         }
+        const char* lh = getenv("SSM_LEGACY_HSWEEP");
+        c->force_legacy_hsweep = lh && lh[0] == '1';
         const char* lc = getenv("SSM_LEGACY_COST");
         c->force_legacy_cost = lc && lc[0] == '1';
         const char* m = getenv("SSM_MAX_CLUSTER");
@@ -269,7 +332,9 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
     A(dalloc(&c->d_C, ncell)); A(dalloc(&c->d_S, ncell));
     c->d_hs = c->d_S;   // horizontal sums are dead once C exists; S is written afterwards
     A(dalloc(&c->d_disp_raw, npix)); A(dalloc(&c->d_disp_lr, npix)); A(dalloc(&c->d_disp_med, npix)); A(dalloc(&c->d_disp, npix));
-    A(dalloc(&c->d_disp2key, npix)); A(dalloc(&c->d_wta_rec, npix)); A(dalloc(&c->d_uniq_thr, (size_t)32768)); A(dalloc(&c->d_cc_label, npix)); A(dalloc(&c->d_cc_size, npix));
+    A(dalloc(&c->d_disp2key, npix)); A(dalloc(&c->d_wta_rec, npix * 2));
+    if (p->num_disparities <= 128)
+        A(dalloc(&c->d_ck, hsweep2_ck_words(c->cap_w - p->num_disparities, p->num_disparities, c->cap_h, c->cap_b))); A(dalloc(&c->d_uniq_thr, (size_t)32768)); A(dalloc(&c->d_cc_label, npix)); A(dalloc(&c->d_cc_size, npix));
     A(dalloc(&c->d_depth, npix)); A(dalloc(&c->d_label, npix)); A(dalloc(&c->d_mask, npix));
     A(dalloc(&c->d_sem, npix * 3)); A(dalloc(&c->d_rgb, npix * 3));
     A(dalloc(&c->d_pose, (size_t)16 * c->cap_b)); A(dalloc(&c->d_min_disp, (size_t)c->cap_b));
@@ -615,9 +680,7 @@ int ssm_pipeline_batch_device(ssm_ctx* c, int batch, const uint8_t* dL, const ui
     if (rc) return rc;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     int16_t* d_disp = d_disp_out ? d_disp_out : c->d_disp;
-    if ((rc = run_sgbm(c, batch, dL, dR, d_disp, s))) return rc;
-    if ((rc = run_map(c, batch, d_disp, d_sem, d_rgb, d_poses, s))) return rc;
-    return SSM_OK;
+    return run_pipeline(c, batch, dL, dR, d_sem, d_rgb, d_poses, d_disp, s);
 }
 
 int ssm_pipeline_batch_host(ssm_ctx* c, int batch, const uint8_t* left, const uint8_t* right, const uint8_t* sem,
@@ -633,8 +696,7 @@ int ssm_pipeline_batch_host(ssm_ctx* c, int batch, const uint8_t* left, const ui
     SSM_CUDA(cudaMemcpyAsync(c->d_sem, sem, npix * 3, cudaMemcpyHostToDevice, s));
     SSM_CUDA(cudaMemcpyAsync(c->d_rgb, rgb, npix * 3, cudaMemcpyHostToDevice, s));
     SSM_CUDA(cudaMemcpyAsync(c->d_pose, poses, sizeof(double) * 16 * batch, cudaMemcpyHostToDevice, s));
-    if ((rc = run_sgbm(c, batch, c->d_left, c->d_right, c->d_disp, s))) return rc;
-    if ((rc = run_map(c, batch, c->d_disp, c->d_sem, c->d_rgb, c->d_pose, s))) return rc;
+    if ((rc = run_pipeline(c, batch, c->d_left, c->d_right, c->d_sem, c->d_rgb, c->d_pose, c->d_disp, s))) return rc;
     if (disp_out) SSM_CUDA(cudaMemcpyAsync(disp_out, c->d_disp, npix * 2, cudaMemcpyDeviceToHost, s));
     return check_overflow(c, s, n_voxels_out);
 }

@@ -95,7 +95,7 @@ int launch_aggregate(ssm_ctx* c, int B, cudaStream_t s)
     bool done = false;
     int rc = launch_vertical(c, B, s, &done);
     if (rc) return rc;
-    if (done) return launch_hsweep(c, B, s);
+    if (done) return hsweep2_supported(c) ? launch_hsweep2(c, B, s) : launch_hsweep(c, B, s);
     // fallback: the three top-down directions walk one warp per path; the horizontal pair + WTA is k_hsweep
     const int order[3] = {2, 1, 3};
     for (int i = 0; i < 3; ++i) {
@@ -113,7 +113,7 @@ int launch_aggregate(ssm_ctx* c, int B, cudaStream_t s)
         }
         SSM_LAUNCH_CHECK(c);
     }
-    return launch_hsweep(c, B, s);
+    return hsweep2_supported(c) ? launch_hsweep2(c, B, s) : launch_hsweep(c, B, s);
 }
 
 }  // namespace ssm

@@ -1,0 +1,332 @@
+// sgbm_hsweep2.cu -- the two horizontal SGM paths + winner-take-all with checkpointed recomputation (SURVEY.md
+// App. A-4, A-5), sm_100a.  Used for D <= 128 (NR <= 2 words per lane); sgbm_hsweep.cu remains the generic path.
+//
+// The one-kernel sweep (sgbm_hsweep.cu) writes S_f = S_v + L(->) for the whole row and reads it back on the way
+// home: 10N bytes of HBM traffic for 4N algorithmic bytes, at 5.2 TB/s -- it is HBM-bound.  Here the left-to-right
+// path is computed twice instead of being stored:
+//   k_hfwd   one warp per row walks left to right through C only and drops a checkpoint (its D-wide state, 256 B)
+//            every kBlk columns: reads 2N, writes ~1 %.
+//   k_hrev   one warp per row walks the blocks right to left.  Per block: one elected lane pulls the block's C and
+//            S_v rows into shared memory with two TMA bulk copies (the rows are contiguous: kBlk * D * 2 bytes)
+//            tracked by an mbarrier; the warp re-runs the left-to-right recurrence over the block from its
+//            checkpoint, folding it into the staged rows in place (T = sat(S_v + L->)); then walks the block right
+//            to left with the right-to-left recurrence, S = sat(T + L<-) in registers, winner-take-all.
+//            Reads 4N (+ checkpoints), writes 16 B per pixel.
+// Winner-take-all on the ALU-pipe diet: first minimum by one REDUX on (S << 16 | d) keys; the uniqueness test
+// "exists d outside [best-1, best+1] with S[d] * (100 - u) < minS * 100" as a packed compare against the exact
+// integer threshold (computed with a multiply-high, no table load) -> one flag byte per disparity -> window bytes
+// masked by a 64-bit shift -> one vote.  The sub-pixel neighbours are NOT extracted in the serial loop: the lane that
+// holds the winner stores its packed costs and the two values across its lane borders (one 16-byte record), and the
+// per-pixel finalize kernel picks S[best-1], S[best+1] from it.
+#include "sgbm_path.cuh"
+
+namespace ssm {
+
+constexpr int kBlk = 16;    // columns per checkpoint block
+constexpr int kPF2 = 4;     // k_hfwd: columns per register prefetch group
+
+// ---- mbarrier / TMA helpers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init1(uint32_t bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar) : "memory");
+}
+
+// ---- pass A: left-to-right checkpoints -----------------------------------------------------------------
+// ck[row][j][LW + 32] words, j = 1 .. nb-1: the state entering block j (after column j*kBlk - 1), packed minimum at [LW]
+template <int NR>
+__global__ void __launch_bounds__(128) k_hfwd(const int16_t* __restrict__ C, uint32_t* __restrict__ ck, int W1, int D, int P1, int P2,
+                                              int nrows, int nb, uint32_t one)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    constexpr int LW = 32 * NR;
+    const int d0 = lane * 2 * NR;
+    const bool active = d0 < D;
+    const PathLane pl = make_path_lane(lane, one);
+    const uint32_t P1w = (uint32_t)P1 * 0x10001u, P2w = (uint32_t)P2 * 0x10001u;
+    const uint32_t padC = (kBig - (uint32_t)P2) * 0x10001u;
+    const uint16_t* Crow = reinterpret_cast<const uint16_t*>(C) + (size_t)row * W1 * D + d0;
+    uint32_t* ckrow = ck + (size_t)row * nb * (LW + 32);
+    const int xend = (nb - 1) * kBlk;            // the last block is only ever recomputed by k_hrev
+    const int ngroups = (xend + kPF2 - 1) / kPF2;
+
+    uint32_t L[NR], Ca[kPF2][NR], Cb[kPF2][NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) L[r] = 0u;
+    uint32_t m = 0u;
+    auto load_group = [&](int g, uint32_t (&buf)[kPF2][NR]) {
+#pragma unroll
+        for (int j = 0; j < kPF2; ++j) {
+            const int x = g * kPF2 + j;
+            if (active && x < xend) load_words<NR>(Crow + (size_t)x * D, buf[j]);
+            else {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) buf[j][r] = padC;
+            }
+        }
+    };
+    auto run_group = [&](int g, const uint32_t (&buf)[kPF2][NR]) {
+#pragma unroll
+        for (int j = 0; j < kPF2; ++j) {
+            const int x = g * kPF2 + j;
+            if (x < xend) {
+                m = path_step<NR>(L, buf[j], m, P1w, P2w, pl);
+                if (((x + 1) & (kBlk - 1)) == 0) {       // state entering block (x + 1) / kBlk
+                    uint32_t* dst = ckrow + (size_t)((x + 1) / kBlk) * (LW + 32);
+                    store_words<NR>(dst + lane * NR, L);
+                    if (lane == 0) dst[LW] = m;
+                }
+            }
+        }
+    };
+    load_group(0, Ca);
+    for (int g = 0; g < ngroups; g += 2) {
+        load_group(g + 1, Cb);
+        run_group(g, Ca);
+        load_group(g + 2, Ca);
+        run_group(g + 1, Cb);
+    }
+}
+
+// ---- pass B: blocks right to left, recompute + reverse path + winner-take-all -----------------------------------
+struct HrevArgs {
+    const int16_t* C;
+    const uint16_t* Sv;
+    const uint32_t* ck;
+    uint4* rec;
+    int W1, D, P1, P2, nrows, nb;
+    uint32_t one;
+    uint32_t uniq_den;       // 100 - uniquenessRatio (0 when the ratio is >= 100)
+    uint64_t uniq_magic;     // ceil(2^40 / uniq_den)
+};
+
+template <int NR>
+__global__ void __launch_bounds__(128) k_hrev(const HrevArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    constexpr int LOG_DPL = NR == 1 ? 1 : 2;     // log2(disparities per lane)
+    const int D = a.D, W1 = a.W1;
+    const uint32_t colbytes = (uint32_t)D * 2;   // one column of C / S_v
+    const uint32_t blkbytes = colbytes * kBlk;
+    // per warp: [C block][S block] + one mbarrier (at the end of the CTA's dynamic shared memory)
+    uint8_t* myC = smem_raw + (size_t)warp * 2 * blkbytes;
+    uint8_t* myS = myC + blkbytes;
+    const uint32_t bar = smem_addr(smem_raw + (size_t)(blockDim.x >> 5) * 2 * blkbytes) + warp * 8;
+    if (lane == 0) mbar_init1(bar);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    if (row >= a.nrows) return;
+
+    constexpr int LW = 32 * NR;
+    const int d0 = lane * 2 * NR;
+    const bool active = d0 < D;
+    const PathLane pl = make_path_lane(lane, a.one);
+    const uint32_t P1w = (uint32_t)a.P1 * 0x10001u, P2w = (uint32_t)a.P2 * 0x10001u;
+    const uint32_t padC = (kBig - (uint32_t)a.P2) * 0x10001u;
+    const uint32_t lanemask = active ? (NR == 2 ? 0x80808080u : 0x00008080u) : 0u;
+    const uint8_t* Cg = reinterpret_cast<const uint8_t*>(a.C) + (size_t)row * W1 * colbytes;
+    const uint8_t* Sg = reinterpret_cast<const uint8_t*>(a.Sv) + (size_t)row * W1 * colbytes;
+    const uint32_t* ckrow = a.ck + (size_t)row * a.nb * (LW + 32);
+    uint4* rrow = a.rec + (size_t)row * W1;
+    const uint32_t loff = (uint32_t)lane * NR * 4;   // this lane's words inside a column
+
+    uint32_t Lr[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) Lr[r] = 0u;
+    uint32_t mr = 0u;
+    uint32_t phase = 0u;
+
+    for (int j = a.nb - 1; j >= 0; --j) {
+        const int xs = j * kBlk, n = min(kBlk, W1 - xs);
+        // stage the block: two bulk copies, one mbarrier phase
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my earlier generic writes to this buffer precede the async writes
+            const uint32_t bytes = colbytes * (uint32_t)n;
+            mbar_expect(bar, 2 * bytes);
+            tma_load_1d(smem_addr(myC), Cg + (size_t)xs * colbytes, bytes, bar);
+            tma_load_1d(smem_addr(myS), Sg + (size_t)xs * colbytes, bytes, bar);
+        }
+        // the state entering the block, while the copies fly
+        uint32_t Lf[NR];
+        uint32_t mf = 0u;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) Lf[r] = 0u;
+        if (j > 0) {
+            const uint32_t* src = ckrow + (size_t)j * (LW + 32);
+            load_words<NR>(src + lane * NR, Lf);
+            mf = src[LW];
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        // left to right again: T = sat(S_v + L->) replaces S_v in place
+        for (int i = 0; i < n; ++i) {
+            uint32_t cw[NR], sw[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) { cw[r] = padC; sw[r] = 0u; }
+            if (active) {
+                load_words<NR>(myC + i * colbytes + loff, cw);
+                load_words<NR>(myS + i * colbytes + loff, sw);
+            }
+            mf = path_step<NR>(Lf, cw, mf, P1w, P2w, pl);
+            if (active) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) sw[r] = __viaddmin_u16x2(sw[r], Lf[r], kSatW);
+                store_words<NR>(myS + i * colbytes + loff, sw);
+            }
+        }
+        // right to left: the fifth path, the full sum, winner-take-all
+        for (int i = n - 1; i >= 0; --i) {
+            uint32_t cw[NR], tw[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) { cw[r] = padC; tw[r] = 0u; }
+            if (active) {
+                load_words<NR>(myC + i * colbytes + loff, cw);
+                load_words<NR>(myS + i * colbytes + loff, tw);
+            }
+            mr = path_step<NR>(Lr, cw, mr, P1w, P2w, pl);
+            uint32_t Sw[NR];
+            uint32_t kmin = 0xffffffffu;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                Sw[r] = active ? __viaddmin_u16x2(tw[r], Lr[r], kSatW) : 0xffffffffu;
+                const uint32_t klo = Sw[r] * pl.sh16 + (uint32_t)(d0 + 2 * r);
+                const uint32_t khi = (Sw[r] & 0xffff0000u) | (uint32_t)(d0 + 2 * r + 1);
+                kmin = __vimin3_u32(kmin, klo, khi);                       // smaller d wins ties: first minimum
+            }
+            kmin = __reduce_min_sync(0xffffffffu, kmin);
+            const uint32_t minS = kmin >> 16, best = kmin & 0xffffu;
+            // S[d] * (100 - u) < minS * 100  <=>  S[d] < thr, thr = ceil(minS * 100 / (100 - u)) (exact; capped at 32768)
+            uint32_t thr;
+            if (a.uniq_den) thr = min((uint32_t)(((uint64_t)(minS * 100u + a.uniq_den - 1u) * a.uniq_magic) >> 40), 32768u);
+            else thr = minS ? 32768u : 0u;
+            // flag byte per disparity: bit 7 set <=> S < thr.  (S + 0x8000 - thr never leaves its 16-bit half.)
+            const uint32_t kt = 0x80008000u - thr * 0x10001u;
+            uint32_t flags;
+            if constexpr (NR == 2) flags = __byte_perm(Sw[0] * pl.one + kt, Sw[1] * pl.one + kt, 0x7531);
+            else flags = __byte_perm(Sw[0] * pl.one + kt, 0u, 0x4431);
+            const uint32_t below = ~flags & lanemask;
+            // bytes of [best - 1, best + 1] inside this lane: 0x808080 shifted by whole bytes (64-bit shift clamps to zero)
+            const uint32_t k8 = (uint32_t)((int)d0 + 4 - (int)best) * 8u;  // 8 * (4 - rel), rel = best - d0; wraps huge when negative
+            unsigned long long win;
+            asm("shr.u64 %0, %1, %2;" : "=l"(win) : "l"(0x0000808080000000ull), "r"(k8));
+            const uint32_t outside = below & ~(uint32_t)win;
+            const uint32_t reject = __any_sync(0xffffffffu, outside != 0u) ? 1u : 0u;
+            // values across the lane borders, for the sub-pixel fit when the winner sits at a lane edge
+            const uint32_t upv = __shfl_up_sync(0xffffffffu, Sw[NR - 1] >> 16, 1);
+            const uint32_t dnv = __shfl_down_sync(0xffffffffu, Sw[0] & 0xffffu, 1);
+            if (lane == (int)(best >> LOG_DPL))
+                rrow[xs + i] = make_uint4(minS | (best << 16) | (reject << 31), Sw[0], NR == 2 ? Sw[NR - 1] : 0u, (upv & 0xffffu) | (dnv << 16));
+        }
+        __syncwarp();
+    }
+}
+
+// sub-pixel fit, disp2 candidates, raw disparity: one thread per pixel of the valid region (16-byte records)
+template <int NR>
+__global__ void __launch_bounds__(256) k_wta_finalize2(const uint4* __restrict__ rec, int16_t* __restrict__ disp_raw,
+                                                       uint32_t* __restrict__ disp2key, int W, int D, size_t total)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int W1 = W - D;
+    const int xp = (int)(idx % W1);
+    const size_t row = idx / W1;
+    const uint4 r = rec[idx];
+    const int minS = (int)(r.x & 0xffffu), best = (int)((r.x >> 16) & 0x7fffu);
+    const int x = xp + D;
+    int out = kInvalidDisp;
+    if (!(r.x >> 31)) {
+        atomicMin(&disp2key[row * W + (x - best)], ((uint32_t)minS << 16) | (uint32_t)(0xffff - x));
+        int d16 = best * kDispScale;
+        if (best > 0 && best < D - 1) {
+            // half-words {up, v0, .., v(2NR-1), down}; the winner is element q + 1
+            uint32_t w[3];
+            w[0] = (r.w & 0xffffu) | (r.y << 16);
+            if (NR == 2) { w[1] = (r.y >> 16) | (r.z << 16); w[2] = (r.z >> 16) | (r.w & 0xffff0000u); }
+            else { w[1] = (r.y >> 16) | (r.w & 0xffff0000u); w[2] = 0u; }
+            const int q = best & (2 * NR - 1);
+            auto elem = [&](int i) { const uint32_t v = i < 2 ? w[0] : (i < 4 ? w[1] : w[2]); return (int)((i & 1) ? (v >> 16) : (v & 0xffffu)); };
+            const int sm = elem(q), sp = elem(q + 2);
+            const int denom2 = max(sm + sp - 2 * minS, 1);
+            d16 += ((sm - sp) * kDispScale + denom2) / (denom2 * 2);
+        }
+        out = d16;
+    }
+    disp_raw[row * W + x] = (int16_t)out;
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t hsweep2_ck_words(int W1, int D, int H, int B)
+{
+    const int NR = D <= 64 ? 1 : 2;
+    const int nb = (W1 + kBlk - 1) / kBlk;
+    return (size_t)B * H * nb * (32 * NR + 32);
+}
+
+bool hsweep2_supported(const ssm_ctx* c) { return c->dp.D <= 128 && !c->force_legacy_hsweep && c->d_ck != nullptr; }
+
+template <int NR>
+static int launch_hsweep2_t(ssm_ctx* c, int B, cudaStream_t s)
+{
+    const DevParams& p = c->dp;
+    const int nrows = B * p.H;
+    const int nb = (p.W1 + kBlk - 1) / kBlk;
+    const int wpb = 4;
+    const unsigned grid = (unsigned)((nrows + wpb - 1) / wpb);
+    if (nb > 1) {
+        k_hfwd<NR><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_ck, p.W1, p.D, p.P1, p.P2, nrows, nb, 1u);
+        SSM_LAUNCH_CHECK(c);
+    }
+    HrevArgs a;
+    a.C = c->d_C; a.Sv = c->d_S; a.ck = c->d_ck; a.rec = reinterpret_cast<uint4*>(c->d_wta_rec);
+    a.W1 = p.W1; a.D = p.D; a.P1 = p.P1; a.P2 = p.P2; a.nrows = nrows; a.nb = nb; a.one = 1u;
+    a.uniq_den = p.uniq < 100 ? (uint32_t)(100 - p.uniq) : 0u;
+    a.uniq_magic = a.uniq_den ? (((1ull << 40) + a.uniq_den - 1) / a.uniq_den) : 0ull;
+    const size_t smem = (size_t)wpb * 2 * kBlk * p.D * 2 + wpb * 8;
+    SSM_CUDA(cudaFuncSetAttribute(k_hrev<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_hrev<NR><<<grid, wpb * 32, smem, s>>>(a);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+int launch_hsweep2(ssm_ctx* c, int B, cudaStream_t s)
+{
+    return c->dp.D <= 64 ? launch_hsweep2_t<1>(c, B, s) : launch_hsweep2_t<2>(c, B, s);
+}
+
+int launch_wta_finalize2(ssm_ctx* c, int B, cudaStream_t s)
+{
+    const DevParams& p = c->dp;
+    const size_t total = (size_t)B * p.H * p.W1;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    const uint4* rec = reinterpret_cast<const uint4*>(c->d_wta_rec);
+    if (p.D <= 64) k_wta_finalize2<1><<<grid, 256, 0, s>>>(rec, c->d_disp_raw, c->d_disp2key, p.W, p.D, total);
+    else k_wta_finalize2<2><<<grid, 256, 0, s>>>(rec, c->d_disp_raw, c->d_disp2key, p.W, p.D, total);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+}  // namespace ssm

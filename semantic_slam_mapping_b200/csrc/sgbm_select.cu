@@ -180,7 +180,7 @@ int launch_select(ssm_ctx* c, int B, cudaStream_t s)
     const DevParams& p = c->dp;
     const size_t npix = (size_t)B * p.H * p.W;
     SSM_CUDA(cudaMemsetAsync(c->d_disp2key, 0xff, npix * sizeof(uint32_t), s));
-    int rc = launch_wta_finalize(c, B, s);
+    int rc = hsweep2_supported(c) ? launch_wta_finalize2(c, B, s) : launch_wta_finalize(c, B, s);
     if (rc) return rc;
     k_lrcheck<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(c->d_disp_raw, c->d_disp2key, c->d_disp_lr, p.W, p.D, p.d12, npix);
     SSM_LAUNCH_CHECK(c);

@@ -97,9 +97,15 @@ struct ssm_ctx {
     int sm_count = 148;
     int max_cluster = 16, min_cluster = 1;   // thread-block cluster sizes the vertical kernel may use (SSM_MAX_CLUSTER / SSM_MIN_CLUSTER)
     int tune[4] = {0, 0, 0, 0};           // SSM_TUNE0..3: experiment knobs (see the kernels that read them)
+    bool force_legacy_hsweep = false;     // SSM_LEGACY_HSWEEP=1: one-kernel horizontal sweep (S_f through HBM) instead of checkpointed recomputation
     bool force_legacy_cost = false;       // SSM_LEGACY_COST=1: k_pix_hsum + k_vsum instead of the fused cost kernel
     bool force_legacy_vertical = false;   // SSM_LEGACY_VERTICAL=1: per-direction kernels instead of the cluster kernel
     cudaStream_t stream = nullptr;
+    // sub-batch streams of the split pipeline (SSM_TUNE3 = number of concurrent sub-batches): kernels bound by different
+    // units (shared-memory LSU, issue, HBM) overlap across sub-batches
+    static constexpr int kMaxSplit = 4;
+    cudaStream_t sub_stream[kMaxSplit] = {};
+    cudaEvent_t sub_fork = nullptr, sub_join[kMaxSplit] = {};
     uint64_t launches = 0;
     bool timing = false;
     // stage timing: a ring of event sets, one per timed pipeline call; read back (averaged) by ssm_stage_time_ms
@@ -118,7 +124,8 @@ struct ssm_ctx {
     uint16_t* d_S = nullptr;                         // [B][H][W1][D] aggregated cost
     int16_t *d_disp_raw = nullptr, *d_disp_lr = nullptr, *d_disp_med = nullptr, *d_disp = nullptr;  // [B][H][W]
     uint32_t* d_disp2key = nullptr;                  // [B][H][W]
-    uint64_t* d_wta_rec = nullptr;                   // [B][H][W1] winner-take-all records (minS, S[best-1], S[best+1], best, reject)
+    uint64_t* d_wta_rec = nullptr;                   // [B][H][W1] winner-take-all records, 8 bytes (sgbm_hsweep.cu) or 16 bytes (sgbm_hsweep2.cu) each
+    uint32_t* d_ck = nullptr;                        // [B][H][blocks][state] left-to-right path checkpoints (sgbm_hsweep2.cu)
     uint32_t* d_uniq_thr = nullptr;                  // [32768] uniqueness threshold per minS
     int32_t *d_cc_label = nullptr, *d_cc_size = nullptr;  // speckle filter
     // mapper
@@ -175,6 +182,10 @@ int launch_aggregate(ssm_ctx* c, int B, cudaStream_t s);
 int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done);   // cluster kernel; *done = false -> caller falls back
 int launch_select(ssm_ctx* c, int B, cudaStream_t s);
 int launch_hsweep(ssm_ctx* c, int B, cudaStream_t s);
+int launch_hsweep2(ssm_ctx* c, int B, cudaStream_t s);       // checkpointed recomputation (D <= 128)
+int launch_wta_finalize2(ssm_ctx* c, int B, cudaStream_t s);
+bool hsweep2_supported(const ssm_ctx* c);
+size_t hsweep2_ck_words(int W1, int D, int H, int B);
 int launch_wta_finalize(ssm_ctx* c, int B, cudaStream_t s);
 int launch_post(ssm_ctx* c, int B, int16_t* d_out, cudaStream_t s);
 int launch_depth(ssm_ctx* c, int B, const int16_t* d_disp, uint16_t* d_depth, cudaStream_t s);
