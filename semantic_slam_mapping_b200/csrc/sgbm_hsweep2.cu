@@ -53,7 +53,7 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
 
 // ---- pass A: left-to-right checkpoints -----------------------------------------------------------------
 // ck[row][j][LW + 32] words, j = 1 .. nb-1: the state entering block j (after column j*kBlk - 1), packed minimum at [LW]
-template <int NR>
+template <int NR, bool FULL /* D == 64 * NR: every lane owns disparities */>
 __global__ void __launch_bounds__(128) k_hfwd(const int16_t* __restrict__ C, uint32_t* __restrict__ ck, int W1, int D, int P1, int P2,
                                               int nrows, int nb, uint32_t one)
 {
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128) k_hfwd(const int16_t* __restrict__ C, uin
     if (row >= nrows) return;
     constexpr int LW = 32 * NR;
     const int d0 = lane * 2 * NR;
-    const bool active = d0 < D;
+    const bool active = FULL || d0 < D;
     const PathLane pl = make_path_lane(lane, one);
     const uint32_t P1w = (uint32_t)P1 * 0x10001u, P2w = (uint32_t)P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)P2) * 0x10001u;
@@ -117,11 +117,12 @@ struct HrevArgs {
     uint4* rec;
     int W1, D, P1, P2, nrows, nb;
     uint32_t one;
-    uint32_t uniq_den;       // 100 - uniquenessRatio (0 when the ratio is >= 100)
-    uint64_t uniq_magic;     // ceil(2^40 / uniq_den)
+    // uniqueness threshold thr = min(umulhi(minS * mul + add, magic), 32768): exact ceil(minS * 100 / (100 - ratio)) with
+    // magic = ceil(2^32 / den) (floor(n / den) == umulhi(n, magic) for n < 2^32 / den); see the launcher for ratio >= 100
+    uint32_t uniq_mul, uniq_add, uniq_magic;
 };
 
-template <int NR>
+template <int NR, bool FULL>
 __global__ void __launch_bounds__(128) k_hrev(const HrevArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(128) k_hrev(const HrevArgs a)
 
     constexpr int LW = 32 * NR;
     const int d0 = lane * 2 * NR;
-    const bool active = d0 < D;
+    const bool active = FULL || d0 < D;
     const PathLane pl = make_path_lane(lane, a.one);
     const uint32_t P1w = (uint32_t)a.P1 * 0x10001u, P2w = (uint32_t)a.P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)a.P2) * 0x10001u;
@@ -220,8 +221,7 @@ __global__ void __launch_bounds__(128) k_hrev(const HrevArgs a)
             const uint32_t minS = kmin >> 16, best = kmin & 0xffffu;
             // S[d] * (100 - u) < minS * 100  <=>  S[d] < thr, thr = ceil(minS * 100 / (100 - u)) (exact; capped at 32768)
             uint32_t thr;
-            if (a.uniq_den) thr = min((uint32_t)(((uint64_t)(minS * 100u + a.uniq_den - 1u) * a.uniq_magic) >> 40), 32768u);
-            else thr = minS ? 32768u : 0u;
+            thr = min(__umulhi(minS * a.uniq_mul + a.uniq_add, a.uniq_magic), 32768u);
             // flag byte per disparity: bit 7 set <=> S < thr.  (S + 0x8000 - thr never leaves its 16-bit half.)
             const uint32_t kt = 0x80008000u - thr * 0x10001u;
             uint32_t flags;
@@ -297,17 +297,29 @@ static int launch_hsweep2_t(ssm_ctx* c, int B, cudaStream_t s)
     const int wpb = 4;
     const unsigned grid = (unsigned)((nrows + wpb - 1) / wpb);
     if (nb > 1) {
-        k_hfwd<NR><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_ck, p.W1, p.D, p.P1, p.P2, nrows, nb, 1u);
+        if (p.D == 64 * NR) k_hfwd<NR, true><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_ck, p.W1, p.D, p.P1, p.P2, nrows, nb, 1u);
+        else k_hfwd<NR, false><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_ck, p.W1, p.D, p.P1, p.P2, nrows, nb, 1u);
         SSM_LAUNCH_CHECK(c);
     }
     HrevArgs a;
     a.C = c->d_C; a.Sv = c->d_S; a.ck = c->d_ck; a.rec = reinterpret_cast<uint4*>(c->d_wta_rec);
     a.W1 = p.W1; a.D = p.D; a.P1 = p.P1; a.P2 = p.P2; a.nrows = nrows; a.nb = nb; a.one = 1u;
-    a.uniq_den = p.uniq < 100 ? (uint32_t)(100 - p.uniq) : 0u;
-    a.uniq_magic = a.uniq_den ? (((1ull << 40) + a.uniq_den - 1) / a.uniq_den) : 0ull;
+    if (p.uniq < 100) {   // thr = ceil(minS * 100 / den) = floor((minS * 100 + den - 1) / den)
+        const uint32_t den = (uint32_t)(100 - p.uniq);
+        a.uniq_mul = 100u; a.uniq_add = den - 1u;
+        a.uniq_magic = (uint32_t)(((1ull << 32) + den - 1) / den);
+        if (den == 1) { a.uniq_mul = 200u; a.uniq_add = 0u; a.uniq_magic = 0x80000000u; }   // 2^32 / 1 does not fit: n / 1 = 2n / 2
+    } else {              // thr = minS ? 32768 : 0  ==  min(floor(minS * 32768 / 1), 32768) with the division by 1 as umulhi(n << ..)
+        a.uniq_mul = 65536u; a.uniq_add = 0u; a.uniq_magic = 0x80000000u;   // umulhi(minS << 16, 2^31) = minS << 15 >= 32768 for minS >= 1
+    }
     const size_t smem = (size_t)wpb * 2 * kBlk * p.D * 2 + wpb * 8;
-    SSM_CUDA(cudaFuncSetAttribute(k_hrev<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_hrev<NR><<<grid, wpb * 32, smem, s>>>(a);
+    if (p.D == 64 * NR) {
+        SSM_CUDA(cudaFuncSetAttribute(k_hrev<NR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hrev<NR, true><<<grid, wpb * 32, smem, s>>>(a);
+    } else {
+        SSM_CUDA(cudaFuncSetAttribute(k_hrev<NR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hrev<NR, false><<<grid, wpb * 32, smem, s>>>(a);
+    }
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }

@@ -74,7 +74,7 @@ __device__ __forceinline__ void st_async_word(uint32_t remote_addr, uint32_t v, 
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
 }
 
-template <int NR, int NWARPS>
+template <int NR, int NWARPS, bool FULL /* D == 64 * NR: every lane owns disparities */>
 __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __restrict__ C, uint16_t* __restrict__ S, int W1, int H,
                                                              int D, int P1, int P2, int T, uint32_t one, int pf_rows)
 {
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
     cluster.sync();
 
     const int d0 = lane * 2 * NR;
-    const bool active = d0 < D;
+    const bool active = FULL || d0 < D;
     const uint32_t P1w = (uint32_t)P1 * 0x10001u, P2w = (uint32_t)P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)P2) * 0x10001u;
     const PathLane pl = make_path_lane(lane, one);
@@ -264,11 +264,11 @@ struct VerticalPlan {
     size_t smem = 0;
 };
 
-template <int NR, int NWARPS>
+template <int NR, int NWARPS, bool FULL>
 static int launch_vertical_t(ssm_ctx* c, int B, const VerticalPlan& plan, cudaStream_t s, bool* done)
 {
     const DevParams& p = c->dp;
-    auto kern = k_vertical3<NR, NWARPS>;
+    auto kern = k_vertical3<NR, NWARPS, FULL>;
     SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     if (plan.cluster > 8) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
@@ -327,10 +327,11 @@ int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done)
     VerticalPlan plan;
     if (!plan_vertical(c, plan)) return SSM_OK;
     const int D = c->dp.D;
-    if (D <= 64) return launch_vertical_t<1, 32>(c, B, plan, s, done);
-    if (D <= 128) return launch_vertical_t<2, 32>(c, B, plan, s, done);
-    if (D <= 256) return launch_vertical_t<4, 16>(c, B, plan, s, done);
-    return launch_vertical_t<8, 16>(c, B, plan, s, done);
+    const bool full = D == 64 || D == 128 || D == 256 || D == 512;
+    if (D <= 64) return full ? launch_vertical_t<1, 32, true>(c, B, plan, s, done) : launch_vertical_t<1, 32, false>(c, B, plan, s, done);
+    if (D <= 128) return full ? launch_vertical_t<2, 32, true>(c, B, plan, s, done) : launch_vertical_t<2, 32, false>(c, B, plan, s, done);
+    if (D <= 256) return full ? launch_vertical_t<4, 16, true>(c, B, plan, s, done) : launch_vertical_t<4, 16, false>(c, B, plan, s, done);
+    return full ? launch_vertical_t<8, 16, true>(c, B, plan, s, done) : launch_vertical_t<8, 16, false>(c, B, plan, s, done);
 }
 
 }  // namespace ssm
