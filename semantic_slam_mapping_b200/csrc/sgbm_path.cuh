@@ -45,6 +45,39 @@ __device__ __forceinline__ void store_words(void* p, const uint32_t (&w)[NR])
     }
 }
 
+// shared-memory accesses through 32-bit shared-window addresses (no generic-to-shared conversion per access)
+template <int NR>
+__device__ __forceinline__ void lds_words(uint32_t addr, uint32_t (&w)[NR])
+{
+    if constexpr (NR == 1) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[0]) : "r"(addr));
+    else if constexpr (NR == 2) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(addr));
+    else {
+#pragma unroll
+        for (int q = 0; q < NR / 4; ++q)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * q]), "=r"(w[4 * q + 1]), "=r"(w[4 * q + 2]), "=r"(w[4 * q + 3]) : "r"(addr + 16 * q));
+    }
+}
+template <int NR>
+__device__ __forceinline__ void sts_words(uint32_t addr, const uint32_t (&w)[NR])
+{
+    if constexpr (NR == 1) asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(w[0]) : "memory");
+    else if constexpr (NR == 2) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(w[0]), "r"(w[1]) : "memory");
+    else {
+#pragma unroll
+        for (int q = 0; q < NR / 4; ++q)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 16 * q), "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3]) : "memory");
+    }
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+// make a loop-invariant value opaque so that it stays in its register instead of being re-derived every iteration
+__device__ __forceinline__ void keep(uint32_t& x) { asm volatile("" : "+r"(x)); }
+
 // Per-lane constants of path_step.  `one` is the integer 1 passed in as a kernel argument: the compiler cannot
 // fold a multiplication by it, so `a * one + b` is emitted as IMAD, which issues on the FMA pipe.  The aggregation
 // kernels are bound by the ALU pipe (IADD3 / LOP3 / SHF / SEL / VIMNMX / VIADDMNMX issue one warp instruction per
@@ -66,6 +99,7 @@ __device__ __forceinline__ PathLane make_path_lane(int lane, uint32_t one)
     p.add0 = lane == 0 ? kBig : 0u;
     p.mul31 = lane == 31 ? 0u : one << 16;
     p.add31 = lane == 31 ? kBig << 16 : 0u;
+    keep(p.sh16); keep(p.keep0); keep(p.add0); keep(p.mul31); keep(p.add31);
     return p;
 }
 

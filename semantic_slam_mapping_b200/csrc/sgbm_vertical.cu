@@ -105,6 +105,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
     const int b0 = lane * NR * 4, b1 = b0 + T * LWB, b2 = b1 + (T + 2) * LWB;   // byte offsets incl. this lane's words
     const int mb0 = n_state * 4, mb1 = mb0 + (T + 2) * 4, mb2 = mb1 + (T + 2) * 4;
     const uint32_t sm_a = smem_u32(smem);
+    uint32_t a0 = sm_a + b0, a1 = sm_a + b1, a2 = sm_a + b2;                   // shared-window addresses of this lane's words
+    uint32_t am0 = sm_a + mb0, am1 = sm_a + mb1, am2 = sm_a + mb2;
+    keep(a0); keep(a1); keep(a2); keep(am0); keep(am1); keep(am2);
     const uint32_t bar_l = sm_a + (uint32_t)(n_state + n_min) * 4;      // credited by the left neighbour (ring 1 halo)
     const uint32_t bar_r = bar_l + 8;                                          // credited by the right neighbour (ring 2 halo)
     __syncthreads();
@@ -175,24 +178,20 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
                 if (k + 1 < nk) load_words<NR>(Crow + off + cstep, Cn);
                 else if (y + 1 < H) load_words<NR>(Crow + rowbytes + (size_t)warp * D * 2, Cn);
             }
-            char* const p0 = sm + c * LWB + b0;
-            char* const p1 = sm + s1 * LWB + b1;
-            char* const p2 = sm + s2 * LWB + b2;
-            uint32_t* const q0 = reinterpret_cast<uint32_t*>(sm + mb0) + c;
-            uint32_t* const q1 = reinterpret_cast<uint32_t*>(sm + mb1) + s1;
-            uint32_t* const q2 = reinterpret_cast<uint32_t*>(sm + mb2) + s2;
+            const uint32_t p0 = a0 + c * LWB, p1 = a1 + s1 * LWB, p2 = a2 + s2 * LWB;
+            const uint32_t q0 = am0 + c * 4, q1 = am1 + s1 * 4, q2 = am2 + s2 * 4;
             uint32_t L0[NR], L1[NR], L2[NR];
-            load_words<NR>(p0, L0);
-            load_words<NR>(p1, L1);
-            load_words<NR>(p2, L2);
-            uint32_t m0 = *q0, m1 = *q1, m2 = *q2;
+            lds_words<NR>(p0, L0);
+            lds_words<NR>(p1, L1);
+            lds_words<NR>(p2, L2);
+            uint32_t m0 = lds_u32(q0), m1 = lds_u32(q1), m2 = lds_u32(q2);
             m0 = path_step<NR>(L0, Cw, m0, P1w, P2w, pl);
             m1 = path_step<NR>(L1, Cw, m1, P1w, P2w, pl);
             m2 = path_step<NR>(L2, Cw, m2, P1w, P2w, pl);
-            store_words<NR>(p0, L0);
-            store_words<NR>(p1, L1);
-            store_words<NR>(p2, L2);
-            if (lane == 0) { *q0 = m0; *q1 = m1; *q2 = m2; }
+            sts_words<NR>(p0, L0);
+            sts_words<NR>(p1, L1);
+            sts_words<NR>(p2, L2);
+            if (lane == 0) { sts_u32(q0, m0); sts_u32(q1, m1); sts_u32(q2, m2); }
             if (active) {
                 uint32_t o[NR];
 #pragma unroll
@@ -329,7 +328,10 @@ int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done)
     const int D = c->dp.D;
     const bool full = D == 64 || D == 128 || D == 256 || D == 512;
     if (D <= 64) return full ? launch_vertical_t<1, 32, true>(c, B, plan, s, done) : launch_vertical_t<1, 32, false>(c, B, plan, s, done);
-    if (D <= 128) return full ? launch_vertical_t<2, 32, true>(c, B, plan, s, done) : launch_vertical_t<2, 32, false>(c, B, plan, s, done);
+    if (D <= 128) {
+        if (full && c->tune[2] == 1) return launch_vertical_t<2, 24, true>(c, B, plan, s, done);
+        return full ? launch_vertical_t<2, 32, true>(c, B, plan, s, done) : launch_vertical_t<2, 32, false>(c, B, plan, s, done);
+    }
     if (D <= 256) return full ? launch_vertical_t<4, 16, true>(c, B, plan, s, done) : launch_vertical_t<4, 16, false>(c, B, plan, s, done);
     return full ? launch_vertical_t<8, 16, true>(c, B, plan, s, done) : launch_vertical_t<8, 16, false>(c, B, plan, s, done);
 }
