@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -72,9 +72,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
 
-    def stop(self) -> dict:
+    def stop(self, t_begin: float = 0.0, t_end: float = float("inf")) -> dict:
+        """Summary of the samples that arrived inside [t_begin, t_end] (host clock); all samples if none did."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -83,10 +84,12 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        inside = [r[1:] for r in self.rows if t_begin <= r[0] <= t_end + 0.06]
+        rows = inside if inside else [r[1:] for r in self.rows]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 9 for i in range(4) if r[5 + i].lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -223,14 +226,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     ctx.set_stage_timing(False)
 
     # ---- device-resident throughput ("value") --------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()                     # nvidia-smi needs a moment to start: launch it before the warm-up
     ctx.map_clear()
     for i in range(args.warmup):
         step_device(i)
     ctx.map_clear()
     barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    t_begin = time.perf_counter()
     launches0 = ctx.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(tstream)
@@ -241,22 +245,35 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.kernel_launches() - launches0
     n_vox = ctx.map_size()
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t_begin, time.perf_counter()) if rank == 0 else None
 
     # points per frame (for the algorithmic-byte model): one compact cloud on the first frame's disparity
     disp0 = ctx.sgbm(seq["left"][0], seq["right"][0])
     pts = len(ctx.generate_point_cloud(ctx.disparity_to_depth(disp0), seq["semantic"][0], seq["rgb"][0], seq["pose"][0])["xyz"])
 
     # ---- end to end through the host entry point ("e2e") ----------------------------------------------------
+    # Every step copies its inputs from pinned host memory (H2D inside the timed region) and copies the step's result
+    # (the map size after the batch) back to pinned host memory.  The streaming entry point stages inputs through two
+    # device buffer sets, so the copy of step k+1 overlaps the kernels of step k.
+    result = torch.zeros(args.steps + 8, dtype=torch.int32).pin_memory()
+
+    def step_host(i, slot):
+        j = (i % nb) * B
+        ctx.pipeline_batch_host_async(pin["left"][j:j + B].numpy(), pin["right"][j:j + B].numpy(), pin["semantic"][j:j + B].numpy(),
+                                      pin["rgb"][j:j + B].numpy(), pin["pose"][j:j + B].numpy(), result[slot:slot + 1])
+
     ctx.map_clear()
-    for i in range(min(args.warmup, 2)):
-        step_host(i)
+    for i in range(min(args.warmup, 3)):
+        step_host(i, args.steps + i)
+    ctx.synchronize()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        step_host(i)
+        step_host(i, i)
+    ctx.synchronize()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert int(result[args.steps - 1]) > 0 and ctx.map_size() > 0      # results arrived; no capacity error
 
     total_frames = args.steps * B * world
     value = total_frames / (dev_ms * 1e-3)
@@ -305,7 +322,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                    "parallelism": (f"frames sharded over {world} GPU(s); voxel hash spatially owned; points routed to the owner by "
                                    + ("NCCL send/recv all-to-all" if args.no_p2p else "peer-memory stores over NVLink fused into the point kernel + NCCL barrier"))
                    if world > 1 else "1 GPU"},
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * (2 * W * H + 6 * W * H + 128), "d2h_bytes_per_step": 16},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * (2 * W * H + 6 * W * H + 128), "d2h_bytes_per_step": 4,
+                "api": "ssm_pipeline_batch_host_async (pinned host buffers, double-buffered staging) + ssm_synchronize"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": f"stage '{dom}'", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -318,11 +336,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=20, help="frames per step per GPU")
-    ap.add_argument("--input-batches", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=33, help="frames per step per GPU (33 = one full wave of 4-CTA clusters on 132 SMs)")
+    ap.add_argument("--input-batches", type=int, default=3)
     ap.add_argument("--distinct", type=int, default=10, help="distinct synthetic images generated on the host")
     ap.add_argument("--map-capacity", type=int, default=1 << 24)
     ap.add_argument("--ref-frames-per-core", type=int, default=2)

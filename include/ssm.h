@@ -150,6 +150,15 @@ int ssm_pipeline_batch_device(ssm_ctx* ctx, int batch, const uint8_t* d_left, co
 int ssm_pipeline_batch_host(ssm_ctx* ctx, int batch, const uint8_t* left, const uint8_t* right,
                             const uint8_t* semantic, const uint8_t* rgb, const double* poses,
                             int w, int h, int16_t* disp_out /* may be NULL */, uint64_t* n_voxels_out);
+/* Asynchronous variant for streaming callers: returns as soon as the copies and kernels are enqueued.  Inputs are
+ * staged through two device buffer sets on a copy stream, so the H2D copy of call k+1 overlaps the kernels of call
+ * k.  The host buffers must stay valid (and should be pinned) until ssm_synchronize returns or two further calls have
+ * been made.  n_voxels_pinned (optional, pinned host memory) receives the map size after this batch, by an
+ * asynchronous D2H copy ordered after the batch's kernels.  Errors of the voxel hash (capacity) surface at the next
+ * ssm_map_size / ssm_map_export / blocking call. */
+int ssm_pipeline_batch_host_async(ssm_ctx* ctx, int batch, const uint8_t* left, const uint8_t* right,
+                                  const uint8_t* semantic, const uint8_t* rgb, const double* poses, int w, int h,
+                                  uint32_t* n_voxels_pinned);
 int ssm_synchronize(ssm_ctx* ctx);
 
 /* ---- multi-GPU: spatially owned voxel hash, NCCL all-to-all point routing ---------------------- */

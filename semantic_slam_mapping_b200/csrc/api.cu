@@ -99,6 +99,14 @@ static void free_all(ssm_ctx* c)
     for (auto& e : c->sub_join)
         if (e) cudaEventDestroy(e);
     if (c->sub_fork) cudaEventDestroy(c->sub_fork);
+    for (int k = 0; k < 2; ++k) {
+        void* st[] = {c->stage_left[k], c->stage_right[k], c->stage_sem[k], c->stage_rgb[k], c->stage_pose[k]};
+        for (void* q : st)
+            if (q) cudaFree(q);
+        if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
+        if (c->ev_consumed[k]) cudaEventDestroy(c->ev_consumed[k]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -681,6 +689,46 @@ int ssm_pipeline_batch_device(ssm_ctx* c, int batch, const uint8_t* dL, const ui
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     int16_t* d_disp = d_disp_out ? d_disp_out : c->d_disp;
     return run_pipeline(c, batch, dL, dR, d_sem, d_rgb, d_poses, d_disp, s);
+}
+
+int ssm_pipeline_batch_host_async(ssm_ctx* c, int batch, const uint8_t* left, const uint8_t* right, const uint8_t* sem,
+                                  const uint8_t* rgb, const double* poses, int w, int h, uint32_t* n_voxels_pinned)
+{
+    if (!c || !left || !right || !sem || !rgb || !poses) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = set_shape(c, w, h, batch);
+    if (rc) return rc;
+    SSM_CUDA(cudaSetDevice(c->device));
+    const size_t cap = (size_t)c->cap_w * c->cap_h * c->cap_b;
+    if (!c->copy_stream) {
+        SSM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            SSM_CUDA(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
+            SSM_CUDA(cudaEventCreateWithFlags(&c->ev_consumed[k], cudaEventDisableTiming));
+            SSM_CUDA(cudaMalloc(&c->stage_left[k], cap));
+            SSM_CUDA(cudaMalloc(&c->stage_right[k], cap));
+            SSM_CUDA(cudaMalloc(&c->stage_sem[k], cap * 3));
+            SSM_CUDA(cudaMalloc(&c->stage_rgb[k], cap * 3));
+            SSM_CUDA(cudaMalloc(&c->stage_pose[k], sizeof(double) * 16 * c->cap_b));
+        }
+    }
+    const int k = (int)(c->async_calls & 1u);
+    const bool reused = c->async_calls >= 2;
+    c->async_calls++;
+    cudaStream_t cs = c->copy_stream, s = c->stream;
+    const size_t npix = (size_t)w * h * batch;
+    if (reused) SSM_CUDA(cudaStreamWaitEvent(cs, c->ev_consumed[k], 0));   // the kernels that read this staging set are done
+    SSM_CUDA(cudaMemcpyAsync(c->stage_left[k], left, npix, cudaMemcpyHostToDevice, cs));
+    SSM_CUDA(cudaMemcpyAsync(c->stage_right[k], right, npix, cudaMemcpyHostToDevice, cs));
+    SSM_CUDA(cudaMemcpyAsync(c->stage_sem[k], sem, npix * 3, cudaMemcpyHostToDevice, cs));
+    SSM_CUDA(cudaMemcpyAsync(c->stage_rgb[k], rgb, npix * 3, cudaMemcpyHostToDevice, cs));
+    SSM_CUDA(cudaMemcpyAsync(c->stage_pose[k], poses, sizeof(double) * 16 * batch, cudaMemcpyHostToDevice, cs));
+    SSM_CUDA(cudaEventRecord(c->ev_copied[k], cs));
+    SSM_CUDA(cudaStreamWaitEvent(s, c->ev_copied[k], 0));
+    if ((rc = run_pipeline(c, batch, c->stage_left[k], c->stage_right[k], c->stage_sem[k], c->stage_rgb[k], c->stage_pose[k], c->d_disp, s)))
+        return rc;
+    SSM_CUDA(cudaEventRecord(c->ev_consumed[k], s));
+    if (n_voxels_pinned) SSM_CUDA(cudaMemcpyAsync(n_voxels_pinned, c->d_counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    return SSM_OK;
 }
 
 int ssm_pipeline_batch_host(ssm_ctx* c, int batch, const uint8_t* left, const uint8_t* right, const uint8_t* sem,

@@ -153,6 +153,8 @@ __global__ void __launch_bounds__(128) k_hrev(const HrevArgs a)
     const uint32_t* ckrow = a.ck + (size_t)row * a.nb * (LW + 32);
     uint4* rrow = a.rec + (size_t)row * W1;
     const uint32_t loff = (uint32_t)lane * NR * 4;   // this lane's words inside a column
+    uint32_t cA = smem_addr(myC) + loff, sA = smem_addr(myS) + loff;   // shared-window addresses of this lane's words
+    keep(cA); keep(sA);
 
     uint32_t Lr[NR];
 #pragma unroll
@@ -188,14 +190,14 @@ __global__ void __launch_bounds__(128) k_hrev(const HrevArgs a)
 #pragma unroll
             for (int r = 0; r < NR; ++r) { cw[r] = padC; sw[r] = 0u; }
             if (active) {
-                load_words<NR>(myC + i * colbytes + loff, cw);
-                load_words<NR>(myS + i * colbytes + loff, sw);
+                lds_words<NR>(cA + i * colbytes, cw);
+                lds_words<NR>(sA + i * colbytes, sw);
             }
             mf = path_step<NR>(Lf, cw, mf, P1w, P2w, pl);
             if (active) {
 #pragma unroll
                 for (int r = 0; r < NR; ++r) sw[r] = __viaddmin_u16x2(sw[r], Lf[r], kSatW);
-                store_words<NR>(myS + i * colbytes + loff, sw);
+                sts_words<NR>(sA + i * colbytes, sw);
             }
         }
         // right to left: the fifth path, the full sum, winner-take-all
@@ -204,8 +206,8 @@ __global__ void __launch_bounds__(128) k_hrev(const HrevArgs a)
 #pragma unroll
             for (int r = 0; r < NR; ++r) { cw[r] = padC; tw[r] = 0u; }
             if (active) {
-                load_words<NR>(myC + i * colbytes + loff, cw);
-                load_words<NR>(myS + i * colbytes + loff, tw);
+                lds_words<NR>(cA + i * colbytes, cw);
+                lds_words<NR>(sA + i * colbytes, tw);
             }
             mr = path_step<NR>(Lr, cw, mr, P1w, P2w, pl);
             uint32_t Sw[NR];

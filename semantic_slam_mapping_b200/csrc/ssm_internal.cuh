@@ -115,6 +115,14 @@ struct ssm_ctx {
     int ev_used = 0;         // sets recorded since the last ssm_set_stage_timing(1)
     float stage_ms[SSM_STAGE_COUNT] = {};
 
+    // asynchronous host pipeline (ssm_pipeline_batch_host_async): a copy stream and two input staging sets, so that the
+    // H2D copy of batch k+1 overlaps the kernels of batch k
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
+    uint8_t *stage_left[2] = {}, *stage_right[2] = {}, *stage_sem[2] = {}, *stage_rgb[2] = {};
+    double* stage_pose[2] = {};
+    uint64_t async_calls = 0;
+
     int cap_w = 0, cap_h = 0, cap_b = 0;
     // stereo
     uint8_t *d_left = nullptr, *d_right = nullptr;   // [B][H][W] staging for host calls

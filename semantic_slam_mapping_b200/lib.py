@@ -20,7 +20,7 @@ SYMBOLS = [
     "ssm_set_stage_timing", "ssm_stage_time_ms", "ssm_sgbm", "ssm_sgbm_batch_device", "ssm_debug_copy_volume",
     "ssm_disparity_to_depth", "ssm_semantic_motion_fuse", "ssm_generate_point_cloud", "ssm_map_integrate_frame",
     "ssm_map_integrate_points", "ssm_map_clear", "ssm_map_size", "ssm_map_export", "ssm_map_save_pcd",
-    "ssm_pipeline_batch_device", "ssm_pipeline_batch_host", "ssm_synchronize", "ssm_comm_get_unique_id",
+    "ssm_pipeline_batch_device", "ssm_pipeline_batch_host", "ssm_pipeline_batch_host_async", "ssm_synchronize", "ssm_comm_get_unique_id",
     "ssm_comm_init", "ssm_comm_ipc_export", "ssm_comm_ipc_connect", "ssm_comm_destroy", "ssm_voxel_owner",
 ]
 
@@ -73,6 +73,7 @@ def load() -> C.CDLL:
     L.ssm_map_save_pcd.argtypes = [vp, C.c_char_p]
     L.ssm_pipeline_batch_device.argtypes = [vp, i, vp, vp, vp, vp, vp, i, i, vp, vp]
     L.ssm_pipeline_batch_host.argtypes = [vp, i, vp, vp, vp, vp, vp, i, i, vp, C.POINTER(u64)]
+    L.ssm_pipeline_batch_host_async.argtypes = [vp, i, vp, vp, vp, vp, vp, i, i, vp]
     L.ssm_synchronize.argtypes = [vp]
     L.ssm_comm_get_unique_id.argtypes = [vp]
     L.ssm_comm_init.argtypes = [vp, vp, i, i]
@@ -232,6 +233,13 @@ class Context:
         self._check(self._L.ssm_pipeline_batch_host(self._h, b, _ptr(left), _ptr(right), _ptr(semantic), _ptr(rgb), _ptr(poses),
                                                     w, h, _ptr(disp), C.byref(nvox)))
         return int(nvox.value), disp
+
+    def pipeline_batch_host_async(self, left, right, semantic, rgb, poses, n_voxels_pinned=None):
+        """Enqueue one batch (pinned host arrays; keep them alive until synchronize()).  n_voxels_pinned: a pinned
+        uint32 torch tensor / numpy array of one element that receives the map size after this batch."""
+        b, h, w = left.shape
+        self._check(self._L.ssm_pipeline_batch_host_async(self._h, b, _ptr(left), _ptr(right), _ptr(semantic), _ptr(rgb), _ptr(poses),
+                                                          w, h, _ptr(n_voxels_pinned)))
 
     def pipeline_batch_device(self, d_left, d_right, d_sem, d_rgb, d_poses, batch: int, w: int, h: int, d_disp=None, stream=None):
         self._check(self._L.ssm_pipeline_batch_device(self._h, batch, _ptr(d_left), _ptr(d_right), _ptr(d_sem), _ptr(d_rgb),

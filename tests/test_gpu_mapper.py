@@ -135,3 +135,52 @@ def test_table_full_is_reported():
         with pytest.raises(SsmError) as e:
             ctx.map_integrate_points(xyz, np.zeros(20000, np.uint32), np.zeros(20000, np.uint8))
         assert e.value.code == -4
+
+
+def test_async_host_pipeline_matches_oracle():
+    """Streaming entry point: three batches through the double-buffered staging; same map as the oracle."""
+    import torch
+    H, W, D, B, nb = 96, 320, 64, 2, 3
+    p = Params(num_disparities=D, max_width=W, max_height=H, max_batch=B, resolution=0.05, map_capacity=1 << 18)
+    mp = _mp(p)
+    seq = synth.sequence(B * nb, H, W, D, 12, seed=23)
+    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in seq.items() if k != "label"}
+    res = torch.zeros(nb, dtype=torch.int32).pin_memory()
+    vm = oracle.VoxelMap(p.resolution, p.num_labels)
+    sizes = []
+    for i in range(B * nb):
+        d = oracle.sgbm(seq["left"][i], seq["right"][i], _op(p))
+        pc = oracle.generate_point_cloud(oracle.disparity_to_depth(d, mp), seq["semantic"][i], seq["rgb"][i], mp, seq["pose"][i])
+        vm.insert(pc["xyz"], pc["rgba"], pc["label"])
+        if i % B == B - 1:
+            sizes.append(len(vm))
+    with Context(p) as ctx:
+        for k in range(nb):
+            sl = slice(k * B, (k + 1) * B)
+            ctx.pipeline_batch_host_async(pin["left"][sl].numpy(), pin["right"][sl].numpy(), pin["semantic"][sl].numpy(),
+                                          pin["rgb"][sl].numpy(), pin["pose"][sl].numpy(), res[k:k + 1])
+        ctx.synchronize()
+        got = ctx.map_export()
+    assert res.tolist() == sizes
+    _compare_maps(got, vm.export())
+
+
+def test_split_batch_streams_match_oracle(monkeypatch):
+    """SSM_TUNE3 = 2: the batch runs as two sub-batches on two streams."""
+    monkeypatch.setenv("SSM_TUNE3", "2")
+    H, W, D, B = 96, 320, 64, 5
+    p = Params(num_disparities=D, max_width=W, max_height=H, max_batch=B, resolution=0.05, map_capacity=1 << 18)
+    mp = _mp(p)
+    seq = synth.sequence(B, H, W, D, 12, seed=29)
+    vm = oracle.VoxelMap(p.resolution, p.num_labels)
+    disps = []
+    for i in range(B):
+        d = oracle.sgbm(seq["left"][i], seq["right"][i], _op(p))
+        disps.append(d)
+        pc = oracle.generate_point_cloud(oracle.disparity_to_depth(d, mp), seq["semantic"][i], seq["rgb"][i], mp, seq["pose"][i])
+        vm.insert(pc["xyz"], pc["rgba"], pc["label"])
+    with Context(p) as ctx:
+        nvox, disp = ctx.pipeline_batch_host(seq["left"], seq["right"], seq["semantic"], seq["rgb"], seq["pose"], want_disp=True)
+        got = ctx.map_export()
+    assert int((disp != np.stack(disps)).sum()) == 0 and nvox == len(vm)
+    _compare_maps(got, vm.export())
