@@ -41,8 +41,9 @@ def algorithmic_bytes(points_per_frame: float) -> dict:
     px = W * H
     return {
         "cost": 2 * px + 2 * N,                 # K1: read L,R; write C
-        "aggregate": 2 * N + 2 * N + 2 * N + 2 * N,   # K2: read C write S_v; K3: read C, S_v
-        "select": 2 * px,                       # K3/K4: write disp1
+        "vertical": 2 * N + 2 * N,              # K2: read C, write S_v
+        "horizontal": 2 * N + 2 * N + 2 * px,   # K3: read C, S_v; write disp1 records
+        "select": 2 * px,                       # K4: L-R check
         "post": 6 * 2 * px,                     # K5 + K6
         "points": 2 * px + 3 * px + 3 * px + 20 * points_per_frame,   # K7
         "fuse": 20 * points_per_frame + 64 * points_per_frame,       # K8 upper bound: one record RMW per point
@@ -288,6 +289,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     ab = algorithmic_bytes(pts)
+    kernels = {"cost": "k_prefilter8 + k_cost_fused", "vertical": "k_vertical3 (cluster kernel)", "horizontal": "k_hfwd + k_hrev",
+               "select": "k_wta_finalize2 + k_lrcheck", "post": "k_median3 + k_cc_*", "points": "k_depth + k_labels + k_moving_mask",
+               "fuse": "k_points_fuse" if world == 1 else "k_points_p2p + barrier + k_fuse_list"}
     dom = max(stage, key=stage.get)
     achieved = ab[dom] * B / (stage[dom] * 1e-3) / 1e9
     stage_roof = {k: {"ms_per_step": round(v, 4), "alg_GBps": round(ab[k] * B / (v * 1e-3) / 1e9, 1) if v > 0 else None}
@@ -326,8 +330,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "api": "ssm_pipeline_batch_host_async (pinned host buffers, double-buffered staging) + ssm_synchronize"},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": f"stage '{dom}'", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "stages": stage_roof},
+        "roofline": {"bound": "hbm", "kernel": f"stage '{dom}': {kernels[dom]}", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "note": "achieved = SURVEY 8d algorithmic bytes of the stage x frames per launch / CUDA-event time of the stage; "
+                             "traffic = ncu dram bytes per launch of the stage's kernels (profiles/dominant_kernel_traffic.json)",
+                     "whole_path": {"alg_bytes_per_frame": ab["total"], "achieved": ab["total"] * total_frames / world / (dev_ms * 1e-3) / 1e9,
+                                    "frac": ab["total"] * total_frames / world / (dev_ms * 1e-3) / 1e9 / peak},
+                     "stages": stage_roof},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -95,8 +95,8 @@ const char* ssm_version(void);
 /* number of kernels this library launched on the ctx since creation (for bench.py gpu_launches) */
 uint64_t ssm_kernel_launches(const ssm_ctx* ctx);
 /* per-stage device time of the most recent *_host / pipeline call, ms (stage ids below) */
-enum { SSM_STAGE_COST = 0, SSM_STAGE_AGGREGATE = 1, SSM_STAGE_SELECT = 2, SSM_STAGE_POST = 3,
-       SSM_STAGE_POINTS = 4, SSM_STAGE_FUSE = 5, SSM_STAGE_COUNT = 6 };
+enum { SSM_STAGE_COST = 0, SSM_STAGE_VERTICAL = 1, SSM_STAGE_HORIZONTAL = 2, SSM_STAGE_SELECT = 3, SSM_STAGE_POST = 4,
+       SSM_STAGE_POINTS = 5, SSM_STAGE_FUSE = 6, SSM_STAGE_COUNT = 7 };
 int ssm_set_stage_timing(ssm_ctx* ctx, int enabled);
 int ssm_stage_time_ms(ssm_ctx* ctx, int stage, float* ms);
 

@@ -124,12 +124,14 @@ static int run_sgbm(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, int
     if ((rc = launch_prefilter(c, B, dL, dR, s))) return rc;
     if ((rc = launch_cost_volume(c, B, s))) return rc;
     mark(c, 1, s);
-    if ((rc = launch_aggregate(c, B, s))) return rc;
+    if ((rc = launch_aggregate_vertical(c, B, s))) return rc;
     mark(c, 2, s);
-    if ((rc = launch_select(c, B, s))) return rc;
+    if ((rc = launch_aggregate_horizontal(c, B, s))) return rc;
     mark(c, 3, s);
-    if ((rc = launch_post(c, B, d_out, s))) return rc;
+    if ((rc = launch_select(c, B, s))) return rc;
     mark(c, 4, s);
+    if ((rc = launch_post(c, B, d_out, s))) return rc;
+    mark(c, 5, s);
     return SSM_OK;
 }
 
@@ -141,17 +143,17 @@ static int run_map(ssm_ctx* c, int B, const int16_t* d_disp, const uint8_t* d_se
     if ((rc = launch_depth(c, B, d_disp, c->d_depth, s))) return rc;
     if ((rc = launch_labels_mask(c, B, d_sem, s))) return rc;
     if (c->nranks > 1 && c->p2p) {
-        mark(c, 5, s);   // points are made, fused or sent to their owner in one kernel; then barrier + inbox fusion
+        mark(c, 6, s);   // points are made, fused or sent to their owner in one kernel; then barrier + inbox fusion
         if ((rc = points_route_p2p(c, B, c->d_depth, d_sem, d_rgb, d_pose, s))) return rc;
     } else if (c->nranks > 1) {
         if ((rc = launch_points(c, B, c->d_depth, d_sem, d_rgb, d_pose, false, s))) return rc;
-        mark(c, 5, s);
+        mark(c, 6, s);
         if ((rc = route_and_fuse(c, s))) return rc;
     } else {
-        mark(c, 5, s);   // single GPU: points are fused as they are generated, one kernel
+        mark(c, 6, s);   // single GPU: points are fused as they are generated, one kernel
         if ((rc = launch_points(c, B, c->d_depth, d_sem, d_rgb, d_pose, true, s))) return rc;
     }
-    mark(c, 6, s);
+    mark(c, 7, s);
     if (c->timing) {
         c->ev_used = std::min(c->ev_used + 1, (int)ssm_ctx::kEvSets);
         c->ev_set = (c->ev_set + 1) % ssm_ctx::kEvSets;

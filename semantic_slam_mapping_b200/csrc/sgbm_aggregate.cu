@@ -85,7 +85,12 @@ __global__ void __launch_bounds__(256) k_aggr_path(AggrArgs a)
     }
 }
 
-int launch_aggregate(ssm_ctx* c, int B, cudaStream_t s)
+int launch_aggregate_horizontal(ssm_ctx* c, int B, cudaStream_t s)
+{
+    return hsweep2_supported(c) ? launch_hsweep2(c, B, s) : launch_hsweep(c, B, s);
+}
+
+int launch_aggregate_vertical(ssm_ctx* c, int B, cudaStream_t s)
 {
     const DevParams& p = c->dp;
     AggrArgs a;
@@ -95,7 +100,7 @@ int launch_aggregate(ssm_ctx* c, int B, cudaStream_t s)
     bool done = false;
     int rc = launch_vertical(c, B, s, &done);
     if (rc) return rc;
-    if (done) return hsweep2_supported(c) ? launch_hsweep2(c, B, s) : launch_hsweep(c, B, s);
+    if (done) return SSM_OK;
     // fallback: the three top-down directions walk one warp per path; the horizontal pair + WTA is k_hsweep
     const int order[3] = {2, 1, 3};
     for (int i = 0; i < 3; ++i) {
@@ -113,7 +118,7 @@ int launch_aggregate(ssm_ctx* c, int B, cudaStream_t s)
         }
         SSM_LAUNCH_CHECK(c);
     }
-    return hsweep2_supported(c) ? launch_hsweep2(c, B, s) : launch_hsweep(c, B, s);
+    return SSM_OK;
 }
 
 }  // namespace ssm

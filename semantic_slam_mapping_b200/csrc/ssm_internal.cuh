@@ -186,7 +186,8 @@ int cuda_fail(cudaError_t e, const char* what);
 // stage launchers (each returns an ssm_status); all buffers densely packed
 int launch_prefilter(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, cudaStream_t s);
 int launch_cost_volume(ssm_ctx* c, int B, cudaStream_t s);
-int launch_aggregate(ssm_ctx* c, int B, cudaStream_t s);
+int launch_aggregate_vertical(ssm_ctx* c, int B, cudaStream_t s);     // down, down-right, down-left -> S_v
+int launch_aggregate_horizontal(ssm_ctx* c, int B, cudaStream_t s);   // right, left, winner-take-all records
 int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done);   // cluster kernel; *done = false -> caller falls back
 int launch_select(ssm_ctx* c, int B, cudaStream_t s);
 int launch_hsweep(ssm_ctx* c, int B, cudaStream_t s);

@@ -12,7 +12,7 @@ from .params import CParams, Params
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssm.so")
 
-STAGES = ("cost", "aggregate", "select", "post", "points", "fuse")
+STAGES = ("cost", "vertical", "horizontal", "select", "post", "points", "fuse")
 
 # every symbol include/ssm.h declares (tests/test_boundary.py checks the .so exports all of them)
 SYMBOLS = [
