@@ -199,3 +199,13 @@ def test_legacy_one_kernel_horizontal_sweep_still_exact(monkeypatch):
         got = ctx.sgbm(L, R)
         Sf = ctx.debug_volume("S", 300, 64)
     assert int((Sf != vols["Sf"]).sum()) == 0 and int((got != want).sum()) == 0
+
+
+def test_cityscapes_width_256_disparities_band():
+    """BASELINE configs[3] shape class: 2048 px wide, 256 disparities (NR = 4 path: generic kernels / 16-CTA clusters)."""
+    H, W, D = 24, 2048, 256
+    L, R, _ = synth.stereo_pair(H, W, D, 91)
+    p = _params(D, W, H)
+    with Context(p) as ctx:
+        got = ctx.sgbm(L, R)
+    assert int((got != oracle.sgbm(L, R, _oparams(p))).sum()) == 0
