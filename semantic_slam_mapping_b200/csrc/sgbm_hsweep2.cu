@@ -18,12 +18,13 @@
 // masked by a 64-bit shift -> one vote.  The sub-pixel neighbours are NOT extracted in the serial loop: the lane that
 // holds the winner stores its packed costs and the two values across its lane borders (one 16-byte record), and the
 // per-pixel finalize kernel picks S[best-1], S[best+1] from it.
+#include <type_traits>
+
 #include "sgbm_path.cuh"
 
 namespace ssm {
 
 constexpr int kBlk = 16;    // columns per checkpoint block
-constexpr int kPF2 = 4;     // k_hfwd: columns per register prefetch group
 
 // ---- mbarrier / TMA helpers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -52,13 +53,24 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
 }
 
 // ---- pass A: left-to-right checkpoints -----------------------------------------------------------------
-// ck[row][j][LW + 32] words, j = 1 .. nb-1: the state entering block j (after column j*kBlk - 1), packed minimum at [LW]
+// ck[row][j][LW + 32] words, j = 1 .. nb-1: the state entering block j (after column j*kBlk - 1), packed minimum at [LW].
+// One warp per row.  The row's cost blocks (kBlk columns = kBlk * D * 2 contiguous bytes) stream through a two-stage
+// shared-memory ring filled by TMA bulk copies (one elected lane, one mbarrier per stage); the kBlk steps of a block
+// are fully unrolled, so every shared-memory load has an immediate offset and the loop carries no address arithmetic.
+// Only full blocks are walked: the last block of a row is never needed as a checkpoint source.
 template <int NR, bool FULL /* D == 64 * NR: every lane owns disparities */>
 __global__ void __launch_bounds__(128) k_hfwd(const int16_t* __restrict__ C, uint32_t* __restrict__ ck, int W1, int D, int P1, int P2,
                                               int nrows, int nb, uint32_t one)
 {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    const uint32_t colbytes = (uint32_t)D * 2, blkbytes = colbytes * kBlk;
+    uint8_t* mine = smem_raw + (size_t)warp * 2 * blkbytes;            // two stages
+    const uint32_t bar0 = smem_addr(smem_raw + (size_t)(blockDim.x >> 5) * 2 * blkbytes) + warp * 16;
+    if (lane == 0) { mbar_init1(bar0); mbar_init1(bar0 + 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
     if (row >= nrows) return;
     constexpr int LW = 32 * NR;
     const int d0 = lane * 2 * NR;
@@ -66,46 +78,44 @@ __global__ void __launch_bounds__(128) k_hfwd(const int16_t* __restrict__ C, uin
     const PathLane pl = make_path_lane(lane, one);
     const uint32_t P1w = (uint32_t)P1 * 0x10001u, P2w = (uint32_t)P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)P2) * 0x10001u;
-    const uint16_t* Crow = reinterpret_cast<const uint16_t*>(C) + (size_t)row * W1 * D + d0;
+    const uint8_t* Cg = reinterpret_cast<const uint8_t*>(C) + (size_t)row * W1 * colbytes;
     uint32_t* ckrow = ck + (size_t)row * nb * (LW + 32);
-    const int xend = (nb - 1) * kBlk;            // the last block is only ever recomputed by k_hrev
-    const int ngroups = (xend + kPF2 - 1) / kPF2;
+    const int nwalk = nb - 1;                    // blocks 0 .. nb-2, all full
+    uint32_t sA = smem_addr(mine) + (uint32_t)lane * NR * 4;
+    keep(sA);
 
-    uint32_t L[NR], Ca[kPF2][NR], Cb[kPF2][NR];
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < 2; ++st)
+            if (st < nwalk) {
+                mbar_expect(bar0 + 8 * st, blkbytes);
+                tma_load_1d(smem_addr(mine) + st * blkbytes, Cg + (size_t)st * blkbytes, blkbytes, bar0 + 8 * st);
+            }
+    }
+    uint32_t L[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) L[r] = 0u;
     uint32_t m = 0u;
-    auto load_group = [&](int g, uint32_t (&buf)[kPF2][NR]) {
+    for (int j = 0; j < nwalk; ++j) {
+        const int st = j & 1;
+        mbar_wait(bar0 + 8 * st, (uint32_t)(j >> 1) & 1u);
+        const uint32_t base = sA + st * blkbytes;
 #pragma unroll
-        for (int j = 0; j < kPF2; ++j) {
-            const int x = g * kPF2 + j;
-            if (active && x < xend) load_words<NR>(Crow + (size_t)x * D, buf[j]);
-            else {
+        for (int i = 0; i < kBlk; ++i) {
+            uint32_t cw[NR];
 #pragma unroll
-                for (int r = 0; r < NR; ++r) buf[j][r] = padC;
-            }
+            for (int r = 0; r < NR; ++r) cw[r] = padC;
+            if (active) lds_words<NR>(base + i * colbytes, cw);
+            m = path_step<NR>(L, cw, m, P1w, P2w, pl);
         }
-    };
-    auto run_group = [&](int g, const uint32_t (&buf)[kPF2][NR]) {
-#pragma unroll
-        for (int j = 0; j < kPF2; ++j) {
-            const int x = g * kPF2 + j;
-            if (x < xend) {
-                m = path_step<NR>(L, buf[j], m, P1w, P2w, pl);
-                if (((x + 1) & (kBlk - 1)) == 0) {       // state entering block (x + 1) / kBlk
-                    uint32_t* dst = ckrow + (size_t)((x + 1) / kBlk) * (LW + 32);
-                    store_words<NR>(dst + lane * NR, L);
-                    if (lane == 0) dst[LW] = m;
-                }
-            }
+        uint32_t* dst = ckrow + (size_t)(j + 1) * (LW + 32);           // state entering block j + 1
+        store_words<NR>(dst + lane * NR, L);
+        if (lane == 0) dst[LW] = m;
+        __syncwarp();                                                   // everyone has read this stage
+        if (lane == 0 && j + 2 < nwalk) {
+            mbar_expect(bar0 + 8 * st, blkbytes);
+            tma_load_1d(smem_addr(mine) + st * blkbytes, Cg + (size_t)(j + 2) * blkbytes, blkbytes, bar0 + 8 * st);
         }
-    };
-    load_group(0, Ca);
-    for (int g = 0; g < ngroups; g += 2) {
-        load_group(g + 1, Cb);
-        run_group(g, Ca);
-        load_group(g + 2, Ca);
-        run_group(g + 1, Cb);
     }
 }
 
@@ -185,7 +195,10 @@ __global__ void __launch_bounds__(128) k_hrev(const HrevArgs a)
         mbar_wait(bar, phase);
         phase ^= 1u;
         // left to right again: T = sat(S_v + L->) replaces S_v in place
-        for (int i = 0; i < n; ++i) {
+        auto walk = [&](auto nn) {
+        const int n_ = decltype(nn)::value > 0 ? decltype(nn)::value : n;   // compile-time kBlk for full blocks
+#pragma unroll
+        for (int i = 0; i < n_; ++i) {
             uint32_t cw[NR], sw[NR];
 #pragma unroll
             for (int r = 0; r < NR; ++r) { cw[r] = padC; sw[r] = 0u; }
@@ -201,7 +214,8 @@ __global__ void __launch_bounds__(128) k_hrev(const HrevArgs a)
             }
         }
         // right to left: the fifth path, the full sum, winner-take-all
-        for (int i = n - 1; i >= 0; --i) {
+#pragma unroll
+        for (int i = n_ - 1; i >= 0; --i) {
             uint32_t cw[NR], tw[NR];
 #pragma unroll
             for (int r = 0; r < NR; ++r) { cw[r] = padC; tw[r] = 0u; }
@@ -242,6 +256,9 @@ __global__ void __launch_bounds__(128) k_hrev(const HrevArgs a)
             if (lane == (int)(best >> LOG_DPL))
                 rrow[xs + i] = make_uint4(minS | (best << 16) | (reject << 31), Sw[0], NR == 2 ? Sw[NR - 1] : 0u, (upv & 0xffffu) | (dnv << 16));
         }
+        };
+        if (n == kBlk) walk(std::integral_constant<int, kBlk>{});
+        else walk(std::integral_constant<int, 0>{});
         __syncwarp();
     }
 }
@@ -299,8 +316,14 @@ static int launch_hsweep2_t(ssm_ctx* c, int B, cudaStream_t s)
     const int wpb = 4;
     const unsigned grid = (unsigned)((nrows + wpb - 1) / wpb);
     if (nb > 1) {
-        if (p.D == 64 * NR) k_hfwd<NR, true><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_ck, p.W1, p.D, p.P1, p.P2, nrows, nb, 1u);
-        else k_hfwd<NR, false><<<grid, wpb * 32, 0, s>>>(c->d_C, c->d_ck, p.W1, p.D, p.P1, p.P2, nrows, nb, 1u);
+        const size_t smem_f = (size_t)wpb * 2 * kBlk * p.D * 2 + wpb * 16;
+        if (p.D == 64 * NR) {
+            SSM_CUDA(cudaFuncSetAttribute(k_hfwd<NR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+            k_hfwd<NR, true><<<grid, wpb * 32, smem_f, s>>>(c->d_C, c->d_ck, p.W1, p.D, p.P1, p.P2, nrows, nb, 1u);
+        } else {
+            SSM_CUDA(cudaFuncSetAttribute(k_hfwd<NR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+            k_hfwd<NR, false><<<grid, wpb * 32, smem_f, s>>>(c->d_C, c->d_ck, p.W1, p.D, p.P1, p.P2, nrows, nb, 1u);
+        }
         SSM_LAUNCH_CHECK(c);
     }
     HrevArgs a;
