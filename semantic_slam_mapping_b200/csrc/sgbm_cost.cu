@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(256) k_prefilter8(const uint8_t* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 constexpr int kKb = 0x4000;                 // bias that keeps K - x positive in both halves
 constexpr uint32_t kKw = 0x40004000u;
+constexpr uint32_t kUnbias = 0u - 0x50005000u;   // -(K + K/4) in both halves
 
 // compile-time geometry of one tile width (TX * D / 2 = 2048 packed words per CTA row)
 template <int TX>
@@ -289,6 +290,8 @@ struct CostGeom {
     static constexpr int WPL = WPP / LPP;                    // words per lane
     static constexpr int RPT = (NR_MAX + 255) / 256;         // right records per thread
     static constexpr int LPT = (NE + 255) / 256;             // left records per thread
+    static constexpr int SL = ((NE + 1) / 2 + 6) / 7;        // diagonal sweep: pixels per segment (7 segments per pixel parity)
+    static constexpr bool DIAG = WPP >= 64 && SL <= 3;       // phase-1 diagonal sweep (D >= 128)
     static constexpr size_t smem_words(int bs) { return (size_t)12 * TW + NE * 8 + (size_t)NE * PS + (size_t)bs * TX * WPP; }
 };
 
@@ -307,6 +310,8 @@ __global__ void __launch_bounds__(256, 2) k_cost_fused(const uint2* __restrict__
     const int n_e = e_hi - e_lo + 1;
     const int n_r = n_e + D - 1;                     // right-image pixels [e_lo + 1, e_hi + D], stored reversed
     const int bs = 2 * radius + 1;
+    uint32_t one = 0u - mone;                        // 1, opaque to the compiler: x * one + y stays an IMAD
+    asm volatile("" : "+r"(one));
 
     uint32_t* Rt = smem;                             // [6 quantities][2 copies][TW]
     uint32_t* Lt = Rt + 12 * TW;                     // [NE][8]
@@ -370,13 +375,12 @@ __global__ void __launch_bounds__(256, 2) k_cost_fused(const uint2* __restrict__
                 const int i = threadIdx.x + k * 256;
                 if (i < n_e) {
                     const uint2 q = ql[k];
-                    // per channel: dup(-u), dup(u - K), dup(-hi), dup(lo - K)
+                    // per channel: dup(u + K), dup(K - u), dup(K - hi), dup(lo + K)  (K keeps every packed difference positive)
                     const uint32_t ug = q.x & 0xffu, log_ = (q.x >> 8) & 0xffu, hig = (q.x >> 16) & 0xffu;
                     const uint32_t ur = q.x >> 24, lor = q.y & 0xffu, hir = (q.y >> 8) & 0xffu;
-                    const uint32_t nug = (0u - ug) & 0xffffu, nhig = (0u - hig) & 0xffffu, nur = (0u - ur) & 0xffffu, nhir = (0u - hir) & 0xffffu;
                     uint4* dst = reinterpret_cast<uint4*>(Lt + i * 8);
-                    dst[0] = make_uint4(nug * 0x10001u, ((ug - kKb) & 0xffffu) * 0x10001u, nhig * 0x10001u, ((log_ - kKb) & 0xffffu) * 0x10001u);
-                    dst[1] = make_uint4(nur * 0x10001u, ((ur - kKb) & 0xffffu) * 0x10001u, nhir * 0x10001u, ((lor - kKb) & 0xffffu) * 0x10001u);
+                    dst[0] = make_uint4((ug + kKb) * 0x10001u, (kKb - ug) * 0x10001u, (kKb - hig) * 0x10001u, (log_ + kKb) * 0x10001u);
+                    dst[1] = make_uint4((ur + kKb) * 0x10001u, (kKb - ur) * 0x10001u, (kKb - hir) * 0x10001u, (lor + kKb) * 0x10001u);
                 }
             }
             // the records of the next distinct row travel while this row is processed
@@ -385,28 +389,85 @@ __global__ void __launch_bounds__(256, 2) k_cost_fused(const uint2* __restrict__
                 if (rn != r && j + 1 < j_end) fetch(rn);
             }
             __syncthreads();
-            // ---- phase 1: pixel costs of (pixel, lane-in-pixel) items; lane jl takes words jl, jl + LPP, ...
-            const int items = n_e * LPP;
-            for (int it = threadIdx.x; it < items; it += 256) {
-                const int el = it / LPP, jl = it % LPP;
-                const uint4 la = reinterpret_cast<const uint4*>(Lt + el * 8)[0];
-                const uint4 lb = reinterpret_cast<const uint4*>(Lt + el * 8)[1];
-                const int i0 = n_e - 1 - el;             // reversed index of d = 0 at pixel e_lo + el
-                const uint32_t* q = Rt + (i0 & 1) * TW + (i0 >> 1) + jl;
-                uint32_t* out = pix + el * PS + jl;
+            // ---- phase 1: pixel costs.  bt_word() is the Birchfield-Tomasi cost of one packed word, biased operands:
+            //   c0 = max(u - hiR, loR - u, 0), c1 = max(v - hiL, loL - v, 0), cost = min(c0, c1), all + K per half.
+            // The four differences are IMADs (FMA pipe); one VIMNMX3 per max, one VIMNMX per min (ALU pipe).
+            auto bt_word = [&](const uint4& la, const uint4& lb, uint32_t loG, uint32_t hiG, uint32_t vG, uint32_t loR, uint32_t hiR,
+                               uint32_t vR) -> uint32_t {
+                const uint32_t g0 = __vimax3_s16x2(hiG * mone + la.x, loG * one + la.y, kKw);
+                const uint32_t g1 = __vimax3_s16x2(vG * one + la.z, vG * mone + la.w, kKw);
+                const uint32_t r0 = __vimax3_s16x2(hiR * mone + lb.x, loR * one + lb.y, kKw);
+                const uint32_t r1 = __vimax3_s16x2(vR * one + lb.z, vR * mone + lb.w, kKw);
+                const uint32_t cgv = __vmins2(g0, g1), crv = __vmins2(r0, r1);
+                // (crv >> 2) per half = (cost_raw >> 2) + K/4; the sum carries K + K/4 per half
+                return cgv + ((crv >> 2) & 0x3fff3fffu) + kUnbias;
+            };
+            if constexpr (G::DIAG) {
+                // Diagonal sweep: word w of pixel e and word w + 1 of pixel e + 2 read the SAME right-image pair, so a
+                // thread that walks pixels e, e + 2, e + 4, ... while its words move up by one keeps its right-image
+                // operands in registers: 6 * WPL table loads per SL pixels instead of per pixel.  16 lanes x WPL words
+                // cover a pixel; the words that enter at the bottom of the disparity range on the way (word < step) are
+                // left to the spare warp below.
+                constexpr int SL = G::SL;
+                const int sg = threadIdx.x >> 4, jl = threadIdx.x & 15;
+                const int el0 = (sg >> 1) * 2 * SL + (sg & 1);
+                if (threadIdx.x < 224) {
+                    if (el0 < n_e) {
+                        const int i0 = n_e - 1 - el0;
+                        const uint32_t* q = Rt + (i0 & 1) * TW + (i0 >> 1) + jl;
+                        uint32_t loG[WPL], hiG[WPL], vG[WPL], loR[WPL], hiR[WPL], vR[WPL];
 #pragma unroll
-                for (int k = 0; k < WPL; ++k) {
-                    const uint32_t loG = q[k * LPP], hiG = q[k * LPP + 2 * TW], vG = q[k * LPP + 4 * TW];
-                    const uint32_t loR = q[k * LPP + 6 * TW], hiR = q[k * LPP + 8 * TW], vR = q[k * LPP + 10 * TW];
-                    const uint32_t nhiG = hiG * mone + kKw, nvG = vG * mone + kKw;   // K - x per half
-                    const uint32_t nhiR = hiR * mone + kKw, nvR = vR * mone + kKw;
-                    // c0 = max(0, u - hiR, loR - u), c1 = max(0, v - hiL, loL - v), cost = min(c0, c1)
-                    const uint32_t g0 = __viaddmax_s16x2(nhiG, la.y, __viaddmax_s16x2(loG, la.x, 0u));
-                    const uint32_t g1 = __viaddmax_s16x2(nvG, la.w, __viaddmax_s16x2(vG, la.z, 0u));
-                    const uint32_t r0 = __viaddmax_s16x2(nhiR, lb.y, __viaddmax_s16x2(loR, lb.x, 0u));
-                    const uint32_t r1 = __viaddmax_s16x2(nvR, lb.w, __viaddmax_s16x2(vR, lb.z, 0u));
-                    const uint32_t cgv = __vmins2(g0, g1), crv = __vmins2(r0, r1);
-                    out[k * LPP] = cgv + ((crv >> 2) & 0x3fff3fffu);
+                        for (int k = 0; k < WPL; ++k) {
+                            loG[k] = q[k * LPP]; hiG[k] = q[k * LPP + 2 * TW]; vG[k] = q[k * LPP + 4 * TW];
+                            loR[k] = q[k * LPP + 6 * TW]; hiR[k] = q[k * LPP + 8 * TW]; vR[k] = q[k * LPP + 10 * TW];
+                        }
+#pragma unroll
+                        for (int t = 0; t < SL; ++t) {
+                            const int el = el0 + 2 * t;
+                            if (el < n_e) {
+                                const uint4 la = reinterpret_cast<const uint4*>(Lt + el * 8)[0];
+                                const uint4 lb = reinterpret_cast<const uint4*>(Lt + el * 8)[1];
+                                uint32_t* out = pix + el * PS + jl + t;
+#pragma unroll
+                                for (int k = 0; k < WPL; ++k) {
+                                    const uint32_t v = bt_word(la, lb, loG[k], hiG[k], vG[k], loR[k], hiR[k], vR[k]);
+                                    if (k < WPL - 1 || jl + t < LPP) out[k * LPP] = v;
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    // spare warp: per group of 2 * SL pixels the words (step t, word w < t) of both pixel parities
+                    constexpr int IPG = SL * (SL - 1);                 // items per group
+                    const int n_items = ((n_e + 2 * SL - 1) / (2 * SL)) * IPG;
+                    for (int c = threadIdx.x - 224; c < n_items; c += 32) {
+                        const int g = c / IPG, r = c - g * IPG;
+                        const int qd = r >> 1;                         // (t, w): (1, 0), (2, 0), (2, 1)
+                        const int t = qd == 0 ? 1 : 2, w = qd == 2 ? 1 : 0;
+                        const int el = g * 2 * SL + 2 * t + (r & 1);
+                        if (el < n_e) {
+                            const uint4 la = reinterpret_cast<const uint4*>(Lt + el * 8)[0];
+                            const uint4 lb = reinterpret_cast<const uint4*>(Lt + el * 8)[1];
+                            const int i0 = n_e - 1 - el;
+                            const uint32_t* q = Rt + (i0 & 1) * TW + (i0 >> 1) + w;
+                            pix[el * PS + w] = bt_word(la, lb, q[0], q[2 * TW], q[4 * TW], q[6 * TW], q[8 * TW], q[10 * TW]);
+                        }
+                    }
+                }
+            } else {
+                // (pixel, lane-in-pixel) items; lane jl takes words jl, jl + LPP, ...
+                const int items = n_e * LPP;
+                for (int it = threadIdx.x; it < items; it += 256) {
+                    const int el = it / LPP, jl = it % LPP;
+                    const uint4 la = reinterpret_cast<const uint4*>(Lt + el * 8)[0];
+                    const uint4 lb = reinterpret_cast<const uint4*>(Lt + el * 8)[1];
+                    const int i0 = n_e - 1 - el;             // reversed index of d = 0 at pixel e_lo + el
+                    const uint32_t* q = Rt + (i0 & 1) * TW + (i0 >> 1) + jl;
+                    uint32_t* out = pix + el * PS + jl;
+#pragma unroll
+                    for (int k = 0; k < WPL; ++k)
+                        out[k * LPP] = bt_word(la, lb, q[k * LPP], q[k * LPP + 2 * TW], q[k * LPP + 4 * TW], q[k * LPP + 6 * TW],
+                                               q[k * LPP + 8 * TW], q[k * LPP + 10 * TW]);
                 }
             }
             __syncthreads();
