@@ -140,6 +140,46 @@ int ssm_map_export(ssm_ctx* ctx, const ssm_voxel_export* out, uint64_t max_voxel
 /* Write the fused map as a binary PCD with fields x y z rgba (pcl::PCDWriter, mapper.cpp:165-170). */
 int ssm_map_save_pcd(ssm_ctx* ctx, const char* path);
 
+/* ---- dense motion cues: the other dense consumer of the disparity map (tracker thread, src/track.cpp:67-79) ---- */
+/* The record image `xyz` is [h][w][10] fp32 = X, Y, Z, u, v, disparity, intensity, I_u, I_v, motion mark (CV_32FC(10)).
+ * Host entry points take host pointers and block; they mirror the reference functions one to one. */
+/* triangulate10D(img, disp, xyz, f, cx, cy, b, roi): src/stereo.cpp:41-118 (include/stereo.h:25) */
+int ssm_triangulate10d(ssm_ctx* ctx, const uint8_t* img, size_t img_stride, const int16_t* disp, size_t disp_stride,
+                       int w, int h, double f, double cx, double cy, double b, double roi_x, double roi_y, double roi_z,
+                       float* xyz);
+/* correct3DPoints(xyz, roi, pitch1, pitch2): src/stereo.cpp:127-181 (include/stereo.h:36); in place */
+int ssm_correct_3d_points(ssm_ctx* ctx, float* xyz, int w, int h, double roi_x, double roi_y, double roi_z,
+                          double pitch1, double pitch2);
+/* setImageROI(xyz, roi_mask): src/stereo.cpp:183-192 (include/stereo.h:43) */
+int ssm_set_image_roi(ssm_ctx* ctx, const float* xyz, int w, int h, uint8_t* roi_mask, size_t mask_stride);
+/* UVDisparity::calVDisparity(img_dis, xyz): src/uvdisparity.cpp:277-366 (include/uvdisparity.hpp:91).  *v_cols =
+ * cvCeil(max(disp)/16); v_dis_int [h][v_cols] int32 and v_dis [h][v_cols] u8 are dense (any may be NULL; both need
+ * v_cols <= cap_cols); channel 8 of xyz (may be NULL) is filled. */
+int ssm_v_disparity(ssm_ctx* ctx, const int16_t* disp, size_t disp_stride, int w, int h, float* xyz,
+                    int32_t* v_dis_int, uint8_t* v_dis, int cap_cols, int* v_cols);
+/* UVDisparity::calUDisparity(img_dis, xyz, roi_mask, ground_mask): src/uvdisparity.cpp:195-274
+ * (include/uvdisparity.hpp:88).  *u_rows = cvCeil(max(disp)/16) + 1; u_dis_int / u_dis [u_rows][w]; channel 7 of xyz. */
+int ssm_u_disparity(ssm_ctx* ctx, const int16_t* disp, size_t disp_stride, int w, int h, float* xyz,
+                    const uint8_t* roi_mask, const uint8_t* ground_mask, int32_t* u_dis_int, uint8_t* u_dis,
+                    int cap_rows, int* u_rows);
+/* The same chain on device-resident batches, in the order of UVDisparity::Process (src/uvdisparity.cpp:842-903), two
+ * asynchronous calls around the host's pitch estimation:
+ *   stage 1 = triangulate10D + calVDisparity: xyz [batch][h][w][10] complete up to channel 8; optional per-frame V maps
+ *             at d_v_dis_int / d_v_dis + frame * hist_stride, frame-local layout [h][v_cols] (v_cols <= cap_cols,
+ *             hist_stride >= h * cap_cols + 4 elements);
+ *   stage 2 = correct3DPoints + setImageROI + calUDisparity: xyz updated in place (channels 1, 2, 6, 7), roi mask
+ *             [batch][h][w], optional U maps [u_rows][w] per frame (u_rows <= cap_rows, hist_stride >= cap_rows * w).
+ *             d_ground_mask NULL = all ground.
+ * ssm_motion_cues_overflow reports (after synchronisation) bit 0: a V map exceeded cap_cols, bit 1: a U map cap_rows. */
+int ssm_motion_cues_stage1_device(ssm_ctx* ctx, int batch, const uint8_t* d_img, const int16_t* d_disp, int w, int h,
+                                  double f, double cx, double cy, double b, float* d_xyz, int32_t* d_v_dis_int,
+                                  uint8_t* d_v_dis, size_t hist_stride, int cap_cols, void* stream);
+int ssm_motion_cues_stage2_device(ssm_ctx* ctx, int batch, const int16_t* d_disp, int w, int h, float* d_xyz,
+                                  double roi_x, double roi_y, double roi_z, double pitch1, const uint8_t* d_ground_mask,
+                                  uint8_t* d_roi_mask, int32_t* d_u_dis_int, uint8_t* d_u_dis, size_t hist_stride,
+                                  int cap_rows, void* stream);
+int ssm_motion_cues_overflow(ssm_ctx* ctx, int* flags);
+
 /* ---- the whole path, batched (north_star: stereo pair + labels + pose -> map) ----------------- */
 /* Device-resident inputs: [batch][h][w] u8 left/right, [batch][h][w][3] u8 semantic/rgb BGR,
  * [batch][16] double poses.  d_disp_out (optional, may be NULL) receives [batch][h][w] int16. */

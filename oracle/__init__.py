@@ -284,3 +284,162 @@ class VoxelMap:
         lib().oracle_map_export(self._h, _p(out["ijk"]), _p(out["centroid"]), _p(out["centroid_d"]), _p(out["rgba"]),
                                 _p(out["count"]), _p(out["votes"]), _p(out["label"]))
         return out
+
+
+# ---- dense motion cues ---------------------------------------------------------------------------
+def _cue_sigs(L):
+    vp = C.c_void_p
+    d = C.c_double
+    L.oracle_triangulate10d.argtypes = [vp, vp, C.c_int, C.c_int, d, d, d, d, vp]
+    L.oracle_correct_3d_points.argtypes = [vp, C.c_int, C.c_int, d, d, d, d, d]
+    L.oracle_set_image_roi.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.oracle_v_disparity.restype = C.c_int
+    L.oracle_v_disparity.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int]
+    L.oracle_u_disparity.restype = C.c_int
+    L.oracle_u_disparity.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int]
+    return L
+
+
+def triangulate10d(img, disp, f, cx, cy, b) -> np.ndarray:
+    """triangulate10D (src/stereo.cpp:41-118): [H][W][10] fp32."""
+    img = np.ascontiguousarray(img, np.uint8)
+    disp = np.ascontiguousarray(disp, np.int16)
+    H, W = disp.shape
+    xyz = np.empty((H, W, 10), np.float32)
+    _cue_sigs(lib()).oracle_triangulate10d(_p(img), _p(disp), W, H, f, cx, cy, b, _p(xyz))
+    return xyz
+
+
+def correct_3d_points(xyz, roi, pitch1, pitch2=0.0) -> np.ndarray:
+    """correct3DPoints (src/stereo.cpp:127-181); returns a corrected copy."""
+    out = np.ascontiguousarray(xyz, np.float32).copy()
+    H, W = out.shape[:2]
+    _cue_sigs(lib()).oracle_correct_3d_points(_p(out), W, H, roi[0], roi[1], roi[2], pitch1, pitch2)
+    return out
+
+
+def set_image_roi(xyz) -> np.ndarray:
+    """setImageROI (src/stereo.cpp:183-192)."""
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    H, W = xyz.shape[:2]
+    m = np.empty((H, W), np.uint8)
+    _cue_sigs(lib()).oracle_set_image_roi(_p(xyz), W, H, _p(m))
+    return m
+
+
+def v_disparity(disp, xyz, cap_cols=1024):
+    """UVDisparity::calVDisparity (src/uvdisparity.cpp:277-366).  Returns (xyz with channel 8 filled, v_dis_int, v_dis)."""
+    disp = np.ascontiguousarray(disp, np.int16)
+    out = np.ascontiguousarray(xyz, np.float32).copy()
+    H, W = disp.shape
+    vi = np.zeros(H * cap_cols, np.int32)
+    v8 = np.zeros(H * cap_cols, np.uint8)
+    vc = _cue_sigs(lib()).oracle_v_disparity(_p(disp), W, H, _p(out), _p(vi), _p(v8), cap_cols)
+    if vc < 0:
+        raise ValueError("v-disparity wider than cap_cols")
+    return out, vi[: H * vc].reshape(H, vc).copy(), v8[: H * vc].reshape(H, vc).copy()
+
+
+def u_disparity(disp, xyz, roi_mask, ground_mask, cap_rows=1025):
+    """UVDisparity::calUDisparity (src/uvdisparity.cpp:195-274).  Returns (xyz with channel 7 filled, u_dis_int, u_dis)."""
+    disp = np.ascontiguousarray(disp, np.int16)
+    out = np.ascontiguousarray(xyz, np.float32).copy()
+    roi_mask = np.ascontiguousarray(roi_mask, np.uint8)
+    ground_mask = np.ascontiguousarray(ground_mask, np.uint8)
+    H, W = disp.shape
+    ui = np.zeros(cap_rows * W, np.int32)
+    u8 = np.zeros(cap_rows * W, np.uint8)
+    ur = _cue_sigs(lib()).oracle_u_disparity(_p(disp), W, H, _p(out), _p(roi_mask), _p(ground_mask), _p(ui), _p(u8), cap_rows)
+    if ur < 0:
+        raise ValueError("u-disparity taller than cap_rows")
+    return out, ui[: ur * W].reshape(ur, W).copy(), u8[: ur * W].reshape(ur, W).copy()
+
+
+# ---- the reference's own src/stereo.cpp, compiled against oracle/cvstub (oracle/_ref/libref_stereo.so) ---------------
+_REF_PATH = os.path.join(_HERE, "_ref", "libref_stereo.so")
+_REFERENCE_ROOT = os.environ.get("SSM_REFERENCE_ROOT", "/root/reference")
+_ref = None
+
+
+def build_ref() -> str | None:
+    """Compile the reference's src/stereo.cpp where it lies (only possible where /root/reference exists; the GPU box uses
+    the prebuilt file that travels with the snapshot).  Returns the path, or None when neither source nor binary exists."""
+    src = os.path.join(_REFERENCE_ROOT, "src", "stereo.cpp")
+    if os.path.exists(src):
+        deps = [src, os.path.join(_HERE, "ref_stereo_wrap.cpp"), os.path.join(_HERE, "cvstub", "cvstub.hpp")]
+        if (not os.path.exists(_REF_PATH)) or any(os.path.getmtime(f) > os.path.getmtime(_REF_PATH) for f in deps):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "_ref/libref_stereo.so", f"REF={_REFERENCE_ROOT}"], stdout=subprocess.DEVNULL)
+    return _REF_PATH if os.path.exists(_REF_PATH) else None
+
+
+_SGBM_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                       C.c_int, C.c_int, C.c_void_p)
+_ref_seen_params = {}
+
+
+@_SGBM_CB
+def _sgbm_cb(l, r, w, h, nd, bs, p1, p2, d12, cap, uniq, spw, spr, out):
+    # cv::StereoSGBM is un-vendored third-party code: the reference's calDisparity_SGBM runs over the oracle's restatement
+    _ref_seen_params.update(num_disparities=nd, block_size=bs, p1=p1, p2=p2, disp12_max_diff=d12, pre_filter_cap=cap,
+                            uniqueness_ratio=uniq, speckle_window_size=spw, speckle_range=spr)
+    left = np.ctypeslib.as_array(C.cast(l, C.POINTER(C.c_uint8)), (h, w))
+    right = np.ctypeslib.as_array(C.cast(r, C.POINTER(C.c_uint8)), (h, w))
+    d = sgbm(left, right, SgbmParams(**_ref_seen_params))
+    C.memmove(out, d.ctypes.data, d.nbytes)
+
+
+def ref():
+    """ctypes handle on oracle/_ref/libref_stereo.so, or None when it is not available."""
+    global _ref
+    if _ref is None:
+        path = build_ref()
+        if path is None:
+            return None
+        R = C.CDLL(path)
+        vp, d = C.c_void_p, C.c_double
+        R.ref_set_sgbm.argtypes = [_SGBM_CB]
+        R.ref_calDisparity_SGBM.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+        R.ref_triangulate10D.argtypes = [vp, vp, C.c_int, C.c_int, d, d, d, d, d, d, d, vp]
+        R.ref_correct3DPoints.argtypes = [vp, C.c_int, C.c_int, d, d, d, d, d]
+        R.ref_setImageROI.argtypes = [vp, C.c_int, C.c_int, vp]
+        R.ref_set_sgbm(_sgbm_cb)
+        _ref = R
+    return _ref
+
+
+def ref_sgbm_params() -> dict:
+    """The cv::StereoSGBM fields the reference's calDisparity_SGBM set on its last call (src/stereo.cpp:16-28)."""
+    return dict(_ref_seen_params)
+
+
+def ref_cal_disparity_sgbm(left, right) -> np.ndarray:
+    left = np.ascontiguousarray(left, np.uint8)
+    right = np.ascontiguousarray(right, np.uint8)
+    H, W = left.shape
+    out = np.empty((H, W), np.int16)
+    ref().ref_calDisparity_SGBM(_p(left), _p(right), W, H, _p(out))
+    return out
+
+
+def ref_triangulate10d(img, disp, f, cx, cy, b, roi=(30000.0, -1000.0, 30000.0)) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    disp = np.ascontiguousarray(disp, np.int16)
+    H, W = disp.shape
+    xyz = np.empty((H, W, 10), np.float32)
+    ref().ref_triangulate10D(_p(img), _p(disp), W, H, f, cx, cy, b, roi[0], roi[1], roi[2], _p(xyz))
+    return xyz
+
+
+def ref_correct_3d_points(xyz, roi, pitch1, pitch2=0.0) -> np.ndarray:
+    out = np.ascontiguousarray(xyz, np.float32).copy()
+    H, W = out.shape[:2]
+    ref().ref_correct3DPoints(_p(out), W, H, roi[0], roi[1], roi[2], pitch1, pitch2)
+    return out
+
+
+def ref_set_image_roi(xyz) -> np.ndarray:
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    H, W = xyz.shape[:2]
+    m = np.empty((H, W), np.uint8)
+    ref().ref_setImageROI(_p(xyz), W, H, _p(m))
+    return m

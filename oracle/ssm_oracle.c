@@ -10,6 +10,7 @@
  */
 #include "ssm_oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -671,4 +672,152 @@ int64_t oracle_map_export(const ovoxel_map* m, int32_t* ijk, float* centroid, do
     }
     free(s);
     return m->size;
+}
+
+/* ================================================================================================
+ * Dense motion cues: the other dense consumer of the disparity map, on the tracker thread
+ * (src/track.cpp:67-79 -> UVDisparity::Process, src/uvdisparity.cpp:842-903).
+ * ================================================================================================ */
+
+/* cvRound: round half to even (lrint under the default rounding mode) */
+static inline int ocv_round(double v) { return (int)nearbyint(v); }
+
+/* src/stereo.cpp:41-118.  xyz: [H][W][10] fp32 = X, Y, Z, u, v, disparity, intensity, I_u, I_v, motion mark.
+ * Both branches of the ROI test (:88-113) store the same values, so roi does not influence the result. */
+void oracle_triangulate10d(const uint8_t* img, const int16_t* disp, int W, int H, double f, double cx, double cy, double b,
+                           float* xyz)
+{
+    double min_disp = DBL_MAX; /* :58-59 cv::minMaxIdx */
+    for (size_t i = 0; i < (size_t)W * H; ++i)
+        if ((double)disp[i] < min_disp) min_disp = (double)disp[i];
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const short d = disp[(size_t)i * W + j];
+            const double pw = b / (1.0 * (double)d);               /* :78  (d == 0 -> +-inf) */
+            double px = (((double)j - cx) * pw) * 16.0;            /* :79  16.0f promotes to double */
+            double py = (((double)i - cy) * pw) * 16.0;            /* :80 */
+            double pz = (f * pw) * 16.0;                           /* :81 */
+            if (fabs((double)d - min_disp) <= (double)FLT_EPSILON) /* :83-88 missing values -> +inf */
+                px = py = pz = (double)INFINITY;
+            float* o = xyz + ((size_t)i * W + j) * 10;
+            o[0] = (float)px; o[1] = (float)py; o[2] = (float)pz;
+            o[3] = (float)j; o[4] = (float)i;
+            o[5] = (float)d / 16.0f;                               /* :95 */
+            o[6] = (float)(int)img[(size_t)i * W + j];             /* :96 */
+            o[7] = 0.f; o[8] = 0.f; o[9] = 0.f;
+        }
+}
+
+/* src/stereo.cpp:127-181: rotate Y/Z by the first pitch angle for 0 < round(disparity) < 100, clear the intensity
+ * channel outside the ROI (and for every other disparity).  pitch2 is accepted and unused, as in the reference. */
+void oracle_correct_3d_points(float* xyz, int W, int H, double roi_x, double roi_y, double roi_z, double pitch1, double pitch2)
+{
+    (void)pitch2;
+    const double cos_p1 = cos(pitch1), sin_p1 = sin(pitch1);
+    for (size_t k = 0; k < (size_t)W * H; ++k) {
+        float* o = xyz + k * 10;
+        const float yp = o[1], zp = o[2];
+        const int d = ocv_round((double)o[5]);                     /* :146 cvRound(float) */
+        if (d > 0 && d < 100) {                                    /* :148 and :161 are the same body */
+            o[1] = (float)(cos_p1 * (double)yp + sin_p1 * (double)zp);
+            o[2] = (float)(cos_p1 * (double)zp - sin_p1 * (double)yp);
+            if ((double)o[0] > roi_x || (double)o[1] > roi_y || (double)o[2] > roi_z) o[6] = 0.f;
+        } else {
+            o[6] = 0.f;                                            /* :174 */
+        }
+    }
+}
+
+/* src/stereo.cpp:183-192: roi_mask = convertScaleAbs(channel 6) = saturate_cast<uchar>(round(|intensity|)) */
+void oracle_set_image_roi(const float* xyz, int W, int H, uint8_t* roi_mask)
+{
+    for (size_t k = 0; k < (size_t)W * H; ++k) {
+        const int r = ocv_round((double)fabsf(xyz[k * 10 + 6]));
+        roi_mask[k] = (uint8_t)(r > 255 ? 255 : r);
+    }
+}
+
+static int disp_max_ceil(const int16_t* disp, int W, int H, double* max_dis_out)
+{
+    int mx = -32768;
+    for (size_t i = 0; i < (size_t)W * H; ++i)
+        if (disp[i] > mx) mx = disp[i];
+    const double max_dis = (double)mx / 16;                        /* uvdisparity.cpp:197-199 / 279-282 */
+    if (max_dis_out) *max_dis_out = max_dis;
+    const int c = (int)ceil(max_dis);
+    return c < 0 ? 0 : c;                                          /* canonical: a negative size is an empty map */
+}
+
+/* UVDisparity::calVDisparity, src/uvdisparity.cpp:277-366.  Outputs: v_dis_int [H][v_cols] int32, v_dis [H][v_cols] u8
+ * (both sized by the caller for v_cols <= cap_cols), xyz channel 8.  Returns v_cols = cvCeil(max(disp)/16).
+ * Canonical choices for the reference's out-of-bounds accesses (both buffers are continuous cv::Mat allocations):
+ *   - bin id = min(v_cols, round(d/16)) can equal v_cols (:309-311): the increment lands on the flat element
+ *     i * v_cols + v_cols, i.e. bin 0 of the next row; past the end of the matrix it is dropped;
+ *   - v_dis_.at<int>(v, d) on the 8-bit map (:352) reads the 4 bytes at flat byte offset v * v_cols + 4 * d as a
+ *     little-endian int; bytes past the end of the map read as 0;
+ *   - uchar = int * float (:331) is truncation toward zero, then modulo 256 (x86 cvttss2si + byte store). */
+int oracle_v_disparity(const int16_t* disp, int W, int H, float* xyz, int32_t* v_dis_int, uint8_t* v_dis, int cap_cols)
+{
+    const int v_cols = disp_max_ceil(disp, W, H, NULL);
+    if (v_cols > cap_cols) return -1;
+    const size_t n = (size_t)H * v_cols;
+    memset(v_dis_int, 0, n * sizeof(int32_t));
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const short d = disp[(size_t)i * W + j];
+            if (d > 0) {                                           /* :304 (Inf / NaN tests on a short are vacuous) */
+                const int dis = ocv_round((double)((float)d / 16.0f)); /* :306 */
+                const int id = imax(0, imin(v_cols, dis));         /* :307 */
+                const size_t flat = (size_t)i * v_cols + id;
+                if (flat < n) v_dis_int[flat]++;
+            }
+        }
+    const float scale = 255 * 1.0f / (float)W;                     /* :319 xyz.cols */
+    for (size_t k = 0; k < n; ++k) v_dis[k] = (uint8_t)(int)((float)v_dis_int[k] * scale);
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            float* o = xyz + ((size_t)i * W + j) * 10;
+            const int v = ocv_round((double)o[4]), d = ocv_round((double)o[5]);   /* :347-348 */
+            float out = 0.f;
+            if (d > 0) {
+                uint32_t word = 0;
+                for (int q = 0; q < 4; ++q) {
+                    const size_t off = (size_t)v * v_cols + 4 * (size_t)d + q;
+                    if (off < n) word |= (uint32_t)v_dis[off] << (8 * q);
+                }
+                out = (float)(int32_t)word;                        /* :352-353 */
+            }
+            o[8] = out;
+        }
+    return v_cols;
+}
+
+/* UVDisparity::calUDisparity, src/uvdisparity.cpp:195-274.  Outputs: u_dis_int [u_rows][W] int32, u_dis [u_rows][W] u8
+ * (u_rows <= cap_rows), xyz channel 7.  Returns u_rows = cvCeil(max(disp)/16) + 1.
+ * Canonical choice: u_dis_.at<uchar>(d, u) with d < 0 (invalid pixels carry disparity -1, :267-269) reads 0. */
+int oracle_u_disparity(const int16_t* disp, int W, int H, float* xyz, const uint8_t* roi_mask, const uint8_t* ground_mask,
+                       int32_t* u_dis_int, uint8_t* u_dis, int cap_rows)
+{
+    const int u_rows = disp_max_ceil(disp, W, H, NULL) + 1;
+    if (u_rows > cap_rows) return -1;
+    const size_t n = (size_t)u_rows * W;
+    memset(u_dis_int, 0, n * sizeof(int32_t));
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const short d = disp[(size_t)i * W + j];
+            if (d > 0) {
+                const int dis = d / 16;                            /* :219 cvRound(d/16): integer division first */
+                if (roi_mask[(size_t)i * W + j] > 0 && ground_mask[(size_t)i * W + j] > 0 && dis > 0)
+                    u_dis_int[(size_t)dis * W + j]++;
+            }
+        }
+    const float scale = 255 * 1.0f / (float)H;                     /* :235 xyz.rows */
+    for (size_t k = 0; k < n; ++k) u_dis[k] = (uint8_t)(int)((float)u_dis_int[k] * scale);
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            float* o = xyz + ((size_t)i * W + j) * 10;
+            const int u = ocv_round((double)o[3]), d = ocv_round((double)o[5]);   /* :265-266 */
+            o[7] = (d >= 0 && d < u_rows && u >= 0 && u < W) ? (float)u_dis[(size_t)d * W + u] : 0.f;
+        }
+    return u_rows;
 }

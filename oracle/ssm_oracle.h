@@ -96,6 +96,21 @@ int64_t oracle_map_size(const ovoxel_map* m);
 int64_t oracle_map_export(const ovoxel_map* m, int32_t* ijk, float* centroid, double* centroid_d,
                           uint32_t* rgba, uint32_t* count, uint32_t* votes, uint8_t* label);
 
+
+/* ---- dense motion cues --------------------------------------------------------- */
+/* src/stereo.cpp:41-118; xyz [H][W][10] fp32 */
+void oracle_triangulate10d(const uint8_t* img, const int16_t* disp, int W, int H, double f, double cx, double cy, double b,
+                           float* xyz);
+/* src/stereo.cpp:127-181 (in place) */
+void oracle_correct_3d_points(float* xyz, int W, int H, double roi_x, double roi_y, double roi_z, double pitch1, double pitch2);
+/* src/stereo.cpp:183-192 */
+void oracle_set_image_roi(const float* xyz, int W, int H, uint8_t* roi_mask);
+/* src/uvdisparity.cpp:277-366; returns v_cols (or -1 when it exceeds cap_cols); writes xyz channel 8 */
+int oracle_v_disparity(const int16_t* disp, int W, int H, float* xyz, int32_t* v_dis_int, uint8_t* v_dis, int cap_cols);
+/* src/uvdisparity.cpp:195-274; returns u_rows (or -1 when it exceeds cap_rows); writes xyz channel 7 */
+int oracle_u_disparity(const int16_t* disp, int W, int H, float* xyz, const uint8_t* roi_mask, const uint8_t* ground_mask,
+                       int32_t* u_dis_int, uint8_t* u_dis, int cap_rows);
+
 #ifdef __cplusplus
 }
 #endif

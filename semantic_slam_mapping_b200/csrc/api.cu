@@ -386,6 +386,7 @@ void ssm_destroy(ssm_ctx* c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     ssm_comm_destroy(c);
+    cues_free(c);
     free_all(c);
     delete c;
 }

@@ -163,11 +163,13 @@ struct ssm_ctx {
     size_t inbox_cap = 0;                            // points per parity buffer
     bool p2p = false;
     uint64_t p2p_step = 0;                           // parity source
+    void* cues_ws = nullptr;                         // dense motion cues workspace (cues.cu), allocated on first use
 };
 
 namespace ssm {
 
 void set_error(const std::string& s);
+void cues_free(ssm_ctx* c);   // cues.cu
 int cuda_fail(cudaError_t e, const char* what);
 
 #define SSM_CUDA(expr)                                                      \

@@ -22,6 +22,8 @@ SYMBOLS = [
     "ssm_map_integrate_points", "ssm_map_clear", "ssm_map_size", "ssm_map_export", "ssm_map_save_pcd",
     "ssm_pipeline_batch_device", "ssm_pipeline_batch_host", "ssm_pipeline_batch_host_async", "ssm_synchronize", "ssm_comm_get_unique_id",
     "ssm_comm_init", "ssm_comm_ipc_export", "ssm_comm_ipc_connect", "ssm_comm_destroy", "ssm_voxel_owner",
+    "ssm_triangulate10d", "ssm_correct_3d_points", "ssm_set_image_roi", "ssm_v_disparity", "ssm_u_disparity",
+    "ssm_motion_cues_stage1_device", "ssm_motion_cues_stage2_device", "ssm_motion_cues_overflow",
 ]
 
 
@@ -81,6 +83,15 @@ def load() -> C.CDLL:
     L.ssm_comm_ipc_connect.argtypes = [vp, vp, i]
     L.ssm_comm_destroy.argtypes = [vp]
     L.ssm_voxel_owner.argtypes = [C.c_int32, C.c_int32, C.c_int32, i]
+    d = C.c_double
+    L.ssm_triangulate10d.argtypes = [vp, vp, sz, vp, sz, i, i, d, d, d, d, d, d, d, vp]
+    L.ssm_correct_3d_points.argtypes = [vp, vp, i, i, d, d, d, d, d]
+    L.ssm_set_image_roi.argtypes = [vp, vp, i, i, vp, sz]
+    L.ssm_v_disparity.argtypes = [vp, vp, sz, i, i, vp, vp, vp, i, C.POINTER(i)]
+    L.ssm_u_disparity.argtypes = [vp, vp, sz, i, i, vp, vp, vp, vp, vp, i, C.POINTER(i)]
+    L.ssm_motion_cues_stage1_device.argtypes = [vp, i, vp, vp, i, i, d, d, d, d, vp, vp, vp, sz, i, vp]
+    L.ssm_motion_cues_stage2_device.argtypes = [vp, i, vp, i, i, vp, d, d, d, d, vp, vp, vp, vp, sz, i, vp]
+    L.ssm_motion_cues_overflow.argtypes = [vp, C.POINTER(i)]
     _lib = L
     return L
 
@@ -223,6 +234,71 @@ class Context:
 
     def map_save_pcd(self, path: str):
         self._check(self._L.ssm_map_save_pcd(self._h, path.encode()))
+
+    # -- dense motion cues (stereo.h triangulate10D / correct3DPoints / setImageROI, UVDisparity::cal[UV]Disparity) --------
+    def triangulate10d(self, img, disp, f, cx, cy, b, roi=(30000.0, -1000.0, 30000.0)) -> np.ndarray:
+        img = np.ascontiguousarray(img, np.uint8)
+        disp = np.ascontiguousarray(disp, np.int16)
+        h, w = disp.shape
+        xyz = np.empty((h, w, 10), np.float32)
+        self._check(self._L.ssm_triangulate10d(self._h, _ptr(img), w, _ptr(disp), w * 2, w, h, f, cx, cy, b, roi[0], roi[1], roi[2], _ptr(xyz)))
+        return xyz
+
+    def correct_3d_points(self, xyz, roi, pitch1, pitch2=0.0) -> np.ndarray:
+        out = np.ascontiguousarray(xyz, np.float32).copy()
+        h, w = out.shape[:2]
+        self._check(self._L.ssm_correct_3d_points(self._h, _ptr(out), w, h, roi[0], roi[1], roi[2], pitch1, pitch2))
+        return out
+
+    def set_image_roi(self, xyz) -> np.ndarray:
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        h, w = xyz.shape[:2]
+        m = np.empty((h, w), np.uint8)
+        self._check(self._L.ssm_set_image_roi(self._h, _ptr(xyz), w, h, _ptr(m), w))
+        return m
+
+    def v_disparity(self, disp, xyz=None):
+        """Returns (xyz with channel 8 filled or None, v_dis_int [H][v_cols], v_dis [H][v_cols])."""
+        disp = np.ascontiguousarray(disp, np.int16)
+        h, w = disp.shape
+        out = None if xyz is None else np.ascontiguousarray(xyz, np.float32).copy()
+        vc = C.c_int(0)
+        self._check(self._L.ssm_v_disparity(self._h, _ptr(disp), w * 2, w, h, None, None, None, 0, C.byref(vc)))   # size query
+        n = vc.value
+        vi = np.zeros((h, n), np.int32)
+        v8 = np.zeros((h, n), np.uint8)
+        self._check(self._L.ssm_v_disparity(self._h, _ptr(disp), w * 2, w, h, _ptr(out), _ptr(vi), _ptr(v8), n, C.byref(vc)))
+        return out, vi, v8
+
+    def u_disparity(self, disp, xyz, roi_mask, ground_mask):
+        """Returns (xyz with channel 7 filled or None, u_dis_int [u_rows][W], u_dis [u_rows][W])."""
+        disp = np.ascontiguousarray(disp, np.int16)
+        roi_mask = np.ascontiguousarray(roi_mask, np.uint8)
+        ground_mask = np.ascontiguousarray(ground_mask, np.uint8)
+        h, w = disp.shape
+        out = None if xyz is None else np.ascontiguousarray(xyz, np.float32).copy()
+        ur = C.c_int(0)
+        self._check(self._L.ssm_u_disparity(self._h, _ptr(disp), w * 2, w, h, None, _ptr(roi_mask), _ptr(ground_mask), None, None, 0, C.byref(ur)))
+        n = ur.value
+        ui = np.zeros((n, w), np.int32)
+        u8 = np.zeros((n, w), np.uint8)
+        self._check(self._L.ssm_u_disparity(self._h, _ptr(disp), w * 2, w, h, _ptr(out), _ptr(roi_mask), _ptr(ground_mask), _ptr(ui), _ptr(u8), n, C.byref(ur)))
+        return out, ui, u8
+
+    def motion_cues_stage1_device(self, d_img, d_disp, d_xyz, batch, w, h, f, cx, cy, b, d_v_int=None, d_v8=None, hist_stride=0, cap_cols=0, stream=None):
+        self._check(self._L.ssm_motion_cues_stage1_device(self._h, batch, _ptr(d_img), _ptr(d_disp), w, h, f, cx, cy, b, _ptr(d_xyz), _ptr(d_v_int),
+                                                          _ptr(d_v8), hist_stride, cap_cols, C.c_void_p(stream) if stream else None))
+
+    def motion_cues_stage2_device(self, d_disp, d_xyz, d_roi_mask, batch, w, h, roi, pitch1, d_ground=None, d_u_int=None, d_u8=None, hist_stride=0,
+                                  cap_rows=0, stream=None):
+        self._check(self._L.ssm_motion_cues_stage2_device(self._h, batch, _ptr(d_disp), w, h, _ptr(d_xyz), roi[0], roi[1], roi[2], pitch1, _ptr(d_ground),
+                                                          _ptr(d_roi_mask), _ptr(d_u_int), _ptr(d_u8), hist_stride, cap_rows,
+                                                          C.c_void_p(stream) if stream else None))
+
+    def motion_cues_overflow(self) -> int:
+        f = C.c_int(0)
+        self._check(self._L.ssm_motion_cues_overflow(self._h, C.byref(f)))
+        return int(f.value)
 
     # -- whole path ---------------------------------------------------------------------------------------
     def pipeline_batch_host(self, left, right, semantic, rgb, poses, want_disp: bool = False):
