@@ -16,8 +16,8 @@
 //   stage 2  k_correct_roi_uhist: rotate, ROI, roi mask, U histogram in one read-modify-write -> 8-bit U map ->
 //            k_assign_u writes channel 7
 // fp64 expressions are evaluated left to right without contraction (the library is built with --fmad=false), so the
-// fp32 results are bit-identical to the reference's.  The reference's out-of-bounds accesses are canonicalised as in
-// oracle/ssm_oracle.c (see the comments there and DESIGN.md).
+// fp32 results are bit-identical to the reference's.  The reference's out-of-bounds accesses are given the canonical
+// meaning stated in DESIGN.md (section 2) and at the kernels below.
 #include <algorithm>
 #include <cmath>
 #include <string>
