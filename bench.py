@@ -348,7 +348,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=33, help="frames per step per GPU (33 = one full wave of 4-CTA clusters on 132 SMs)")
+    ap.add_argument("--batch", type=int, default=66, help="frames per step per GPU (66 = two sub-batches of 33, each one full wave of 4-CTA clusters on 132 SMs)")
     ap.add_argument("--input-batches", type=int, default=3)
     ap.add_argument("--distinct", type=int, default=10, help="distinct synthetic images generated on the host")
     ap.add_argument("--map-capacity", type=int, default=1 << 24)

@@ -178,13 +178,16 @@ static void offset_buffers(ssm_ctx* c, ptrdiff_t frames)
 
 static int run_map(ssm_ctx* c, int B, const int16_t* d_disp, const uint8_t* d_sem, const uint8_t* d_rgb, const double* d_pose, cudaStream_t s);
 
-// The whole path on device buffers.  With SSM_TUNE3 = n > 1 (single GPU) the batch is cut into n sub-batches that run
-// on n streams and meet again on `s`.
+// The whole path on device buffers.  On a single GPU a batch of 64 frames or more (or SSM_TUNE3 = n > 1) is cut into
+// sub-batches that run on their own streams and meet again on `s`.
 static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, const uint8_t* d_sem, const uint8_t* d_rgb,
                         const double* d_pose, int16_t* d_disp, cudaStream_t s)
 {
     int rc;
-    const int nsplit = std::min({c->tune[3], (int)ssm_ctx::kMaxSplit, B});
+    // sub-batches of at least ~one full wave of the vertical cluster kernel each (33 KITTI frames on a B200): kernels of
+    // different sub-batches are bound by different units (shared memory, issue slots, HBM) and fill each other's tails
+    const int want = c->tune[3] >= 0 ? c->tune[3] : (B >= 96 ? 3 : (B >= 64 ? 2 : 1));
+    const int nsplit = std::min({want, (int)ssm_ctx::kMaxSplit, B});
     if (nsplit <= 1 || c->nranks > 1 || c->timing) {
         if ((rc = run_sgbm(c, B, dL, dR, d_disp, s))) return rc;
         return run_map(c, B, d_disp, d_sem, d_rgb, d_pose, s);
@@ -314,7 +317,8 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
         for (int t = 0; t < 4; ++t) {
             const std::string name = "SSM_TUNE" + std::to_string(t);
             const char* v = getenv(name.c_str());
-            static const int defaults[4] = {2 /* vertical: L2 prefetch distance in rows */, 0 /* hsweep: L2 prefetch off */, 0, 0};
+            static const int defaults[4] = {2 /* vertical: L2 prefetch distance in rows */, 0 /* hsweep: L2 prefetch off */, 0,
+                                             -1 /* sub-batch streams: automatic */};
             c->tune[t] = v ? atoi(v) : defaults[t];
         }
         const char* lh = getenv("SSM_LEGACY_HSWEEP");
