@@ -132,6 +132,19 @@ int ssm_map_integrate_frame(ssm_ctx* ctx, const uint16_t* depth, const uint8_t* 
                             const uint8_t* rgb_bgr, int w, int h, const double* T_f_w);
 /* fuse an explicit cloud (e.g. one returned by ssm_generate_point_cloud) */
 int ssm_map_integrate_points(ssm_ctx* ctx, const float* xyz, const uint32_t* rgba, const uint8_t* label, int n);
+/* Keyframe cache + redraw.  Mapper::generatePointCloud caches each keyframe's cloud in camera coordinates
+ * (frame->pointcloud, mapper.cpp:17-20) and re-transforms it by the frame's CURRENT pose on every update (:90-91),
+ * because the pose graph rewrites keyframe poses (pose_graph.cpp:253-260).  ssm_keyframe_add builds and keeps that
+ * cloud on the device and returns its id; ssm_keyframe_set_pose records a new T_f_w; ssm_map_redraw is the periodic
+ * full redraw (mapper.cpp:121-131: globalMap->clear(), then += the listed keyframes -- the reference passes every
+ * second one) and ssm_map_integrate_keyframes the incremental branch (:132-149).  ids == NULL: every live keyframe. */
+int ssm_keyframe_add(ssm_ctx* ctx, const uint16_t* depth, const uint8_t* semantic_bgr, const uint8_t* rgb_bgr,
+                     int w, int h, const double* T_f_w, int* id_out);
+int ssm_keyframe_set_pose(ssm_ctx* ctx, int id, const double* T_f_w);
+int ssm_keyframe_release(ssm_ctx* ctx, int id);
+int ssm_keyframe_count(ssm_ctx* ctx, int* n_live, uint64_t* n_points);
+int ssm_map_redraw(ssm_ctx* ctx, const int* ids, int n);
+int ssm_map_integrate_keyframes(ssm_ctx* ctx, const int* ids, int n);
 int ssm_map_clear(ssm_ctx* ctx);                      /* globalMap->clear(), mapper.cpp:125 */
 int ssm_map_size(ssm_ctx* ctx, uint64_t* n_voxels);   /* "points in global map", mapper.cpp:161 */
 /* Export up to max_voxels voxels of THIS rank's table; sorted != 0 orders them by (k,j,i)
@@ -179,6 +192,18 @@ int ssm_motion_cues_stage2_device(ssm_ctx* ctx, int batch, const int16_t* d_disp
                                   uint8_t* d_roi_mask, int32_t* d_u_dis_int, uint8_t* d_u_dis, size_t hist_stride,
                                   int cap_rows, void* stream);
 int ssm_motion_cues_overflow(ssm_ctx* ctx, int* flags);
+
+/* ---- label production in front of the path (experiment/segnet.cpp:121-135, src/rgbdframe.cpp:118-136) -------- */
+/* SegNet's argmax index image (8UC1, sw x sh; 480 x 360 in the reference) -> cv::resize to the frame size (default
+ * INTER_LINEAR) -> cv::LUT through the 256-entry BGR colour table -> the semantic image the Mapper reads.  `raw`
+ * (optional) receives the resized index image (= frame->raw_semantic).  Bit-exact with cv2.resize / cv2.LUT. */
+int ssm_labels_from_indices(ssm_ctx* ctx, const uint8_t* index, size_t index_stride, int sw, int sh, int dw, int dh,
+                            const uint8_t* lut_bgr /* [256][3] */, uint8_t* semantic_bgr, size_t sem_stride,
+                            uint8_t* raw, size_t raw_stride);
+/* Device, async: d_index [batch][sh][sw] -> d_semantic_bgr [batch][dh][dw][3] (+ d_raw [batch][dh][dw], may be NULL);
+ * the output feeds ssm_pipeline_batch_device directly.  lut_bgr is a host pointer. */
+int ssm_labels_from_indices_batch_device(ssm_ctx* ctx, int batch, const uint8_t* d_index, int sw, int sh, int dw, int dh,
+                                         const uint8_t* lut_bgr, uint8_t* d_semantic_bgr, uint8_t* d_raw, void* stream);
 
 /* ---- the whole path, batched (north_star: stereo pair + labels + pose -> map) ----------------- */
 /* Device-resident inputs: [batch][h][w] u8 left/right, [batch][h][w][3] u8 semantic/rgb BGR,

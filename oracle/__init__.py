@@ -443,3 +443,45 @@ def ref_set_image_roi(xyz) -> np.ndarray:
     m = np.empty((H, W), np.uint8)
     ref().ref_setImageROI(_p(xyz), W, H, _p(m))
     return m
+
+
+# ---- label production before the path: experiment/segnet.cpp:131-146, src/rgbdframe.cpp:118-136 --------
+def resize_linear_tables(dst: int, src: int, clamp: bool):
+    """Source index and the two 11-bit fixed-point weights of cv::resize(INTER_LINEAR) for every destination coordinate
+    (OpenCV imgproc resize, un-vendored third-party; pinned bit-exactly against cv2 4.13 by tests/test_oracle_labels.py).
+    x tables clamp at the borders (weight 0 on the outside sample); y tables do not -- the row INDEX is clamped later."""
+    scale = 1.0 / (dst / src)                                  # double, as 1. / inv_scale
+    d = np.arange(dst, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int32)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    if clamp:
+        lo, hi = s < 0, s >= src - 1
+        f = np.where(lo | hi, np.float32(0), f).astype(np.float32)
+        s = np.where(lo, 0, np.where(hi, src - 1, s)).astype(np.int32)
+    w0 = np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int32)    # saturate_cast<short>: round half to even
+    w1 = np.rint(f * np.float32(2048)).astype(np.int32)
+    return s, w0, w1
+
+
+def resize_linear_u8(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv::resize(img, dsize=(dw, dh)) with the default INTER_LINEAR on a single-channel 8-bit image (the 3-channel index
+    image of experiment/segnet.cpp:121-134 carries the same value in every channel)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    sh, sw = img.shape
+    xi, xa0, xa1 = resize_linear_tables(dw, sw, True)
+    yi, yb0, yb1 = resize_linear_tables(dh, sh, False)
+    I = img.astype(np.int32)
+    rows = I[:, xi] * xa0 + I[:, np.minimum(xi + 1, sw - 1)] * xa1              # horizontal pass, 11 fractional bits
+    r0, r1 = rows[np.clip(yi, 0, sh - 1)], rows[np.clip(yi + 1, 0, sh - 1)]
+    out = (((yb0[:, None] * (r0 >> 4)) >> 16) + ((yb1[:, None] * (r1 >> 4)) >> 16) + 2) >> 2
+    return out.astype(np.uint8)
+
+
+def labels_from_indices(index_img: np.ndarray, dw: int, dh: int, lut_bgr: np.ndarray):
+    """experiment/segnet.cpp:131-135 (= the commented online path src/rgbdframe.cpp:130-135): argmax index image ->
+    cv::resize to the frame size -> cv::LUT through the 256-entry BGR colour table.  Returns (semantic BGR [dh][dw][3],
+    raw index image [dh][dw] = cvtColor(BGR2GRAY) of the resized index image, whose channels are equal)."""
+    raw = resize_linear_u8(index_img, dw, dh)
+    lut = np.ascontiguousarray(lut_bgr, np.uint8).reshape(256, 3)
+    return lut[raw], raw

@@ -260,6 +260,7 @@ using namespace ssm;
 
 // =================================================================================================
 extern "C" {
+static void keyframes_free(ssm_ctx* c);
 
 void ssm_default_params(ssm_params* p)
 {
@@ -391,6 +392,8 @@ void ssm_destroy(ssm_ctx* c)
     cudaDeviceSynchronize();
     ssm_comm_destroy(c);
     cues_free(c);
+    labels_free(c);
+    keyframes_free(c);
     free_all(c);
     delete c;
 }
@@ -549,6 +552,125 @@ int ssm_map_integrate_frame(ssm_ctx* c, const uint16_t* depth, const uint8_t* se
     }
     return check_overflow(c, s, nullptr);
 }
+
+// ---- keyframe cache + redraw (mapper.cpp:17-20, :121-149; poses are rewritten by the pose graph, pose_graph.cpp:253-260) ----
+namespace {
+struct Keyframe {
+    Point* d_pts = nullptr;    // camera-frame cloud, row-major order
+    uint32_t n = 0;
+    double T[16];
+    bool live = false;
+};
+struct KeyframeStore { std::vector<Keyframe> kf; };
+KeyframeStore* kf_store(ssm_ctx* c)
+{
+    if (!c->keyframes) c->keyframes = new KeyframeStore();
+    return static_cast<KeyframeStore*>(c->keyframes);
+}
+}  // namespace
+
+static void keyframes_free(ssm_ctx* c)
+{
+    KeyframeStore* st = static_cast<KeyframeStore*>(c->keyframes);
+    if (!st) return;
+    for (auto& k : st->kf)
+        if (k.d_pts) cudaFree(k.d_pts);
+    delete st;
+    c->keyframes = nullptr;
+}
+
+int ssm_keyframe_add(ssm_ctx* c, const uint16_t* depth, const uint8_t* sem, const uint8_t* rgb, int w, int h, const double* T, int* id_out)
+{
+    if (!c || !depth || !sem || !rgb || !T || !id_out) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (c->nranks > 1) return fail(SSM_ERR_UNSUPPORTED, "the keyframe cache is per context; with a communicator use ssm_map_integrate_frame");
+    int rc = set_shape(c, w, h, 1);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    static const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    if ((rc = upload_frame(c, depth, sem, rgb, w, h, I, s))) return rc;   // identity pose: the compact cloud stays in camera coordinates
+    if ((rc = launch_labels_mask(c, 1, c->d_sem, s))) return rc;
+    if ((rc = launch_points(c, 1, c->d_depth, c->d_sem, c->d_rgb, c->d_pose, false, s))) return rc;
+    uint32_t n = 0;
+    SSM_CUDA(cudaMemcpyAsync(&n, c->d_counters, sizeof(n), cudaMemcpyDeviceToHost, s));
+    SSM_CUDA(cudaStreamSynchronize(s));
+    Keyframe k;
+    k.n = n;
+    k.live = true;
+    std::memcpy(k.T, T, sizeof(k.T));
+    if (n) {
+        SSM_CUDA(cudaMalloc(reinterpret_cast<void**>(&k.d_pts), sizeof(Point) * n));
+        SSM_CUDA(cudaMemcpyAsync(k.d_pts, c->d_points, sizeof(Point) * n, cudaMemcpyDeviceToDevice, s));
+        SSM_CUDA(cudaStreamSynchronize(s));
+    }
+    KeyframeStore* st = kf_store(c);
+    st->kf.push_back(k);
+    *id_out = (int)st->kf.size() - 1;
+    return SSM_OK;
+}
+
+static Keyframe* kf_get(ssm_ctx* c, int id)
+{
+    KeyframeStore* st = static_cast<KeyframeStore*>(c->keyframes);
+    if (!st || id < 0 || id >= (int)st->kf.size() || !st->kf[id].live) return nullptr;
+    return &st->kf[id];
+}
+
+int ssm_keyframe_set_pose(ssm_ctx* c, int id, const double* T)
+{
+    if (!c || !T) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    Keyframe* k = kf_get(c, id);
+    if (!k) return fail(SSM_ERR_INVALID_ARGUMENT, "unknown keyframe id");
+    std::memcpy(k->T, T, sizeof(k->T));
+    return SSM_OK;
+}
+
+int ssm_keyframe_release(ssm_ctx* c, int id)
+{
+    if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
+    Keyframe* k = kf_get(c, id);
+    if (!k) return fail(SSM_ERR_INVALID_ARGUMENT, "unknown keyframe id");
+    SSM_CUDA(cudaStreamSynchronize(c->stream));
+    if (k->d_pts) cudaFree(k->d_pts);
+    k->d_pts = nullptr; k->n = 0; k->live = false;
+    return SSM_OK;
+}
+
+int ssm_keyframe_count(ssm_ctx* c, int* n_live, uint64_t* n_points)
+{
+    if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
+    KeyframeStore* st = static_cast<KeyframeStore*>(c->keyframes);
+    int live = 0;
+    uint64_t pts = 0;
+    if (st)
+        for (auto& k : st->kf)
+            if (k.live) { ++live; pts += k.n; }
+    if (n_live) *n_live = live;
+    if (n_points) *n_points = pts;
+    return SSM_OK;
+}
+
+// fuse the cached clouds of the given keyframes (ids == NULL: every live keyframe) under their current poses
+static int integrate_keyframes(ssm_ctx* c, const int* ids, int n, bool clear_first)
+{
+    if (!c || n < 0) return fail(SSM_ERR_INVALID_ARGUMENT, "bad argument");
+    KeyframeStore* st = static_cast<KeyframeStore*>(c->keyframes);
+    cudaStream_t s = c->stream;
+    int rc;
+    if (ids)
+        for (int i = 0; i < n; ++i)
+            if (!kf_get(c, ids[i])) return fail(SSM_ERR_INVALID_ARGUMENT, "unknown keyframe id");
+    if (clear_first && (rc = launch_map_clear(c, s))) return rc;
+    const int count = ids ? n : (st ? (int)st->kf.size() : 0);
+    for (int i = 0; i < count; ++i) {
+        const Keyframe* k = ids ? kf_get(c, ids[i]) : (st->kf[i].live ? &st->kf[i] : nullptr);
+        if (!k) continue;
+        if ((rc = launch_transform_fuse(c, k->d_pts, k->n, k->T, s))) return rc;
+    }
+    return check_overflow(c, s, nullptr);
+}
+
+int ssm_map_redraw(ssm_ctx* c, const int* ids, int n) { return integrate_keyframes(c, ids, n, true); }
+int ssm_map_integrate_keyframes(ssm_ctx* c, const int* ids, int n) { return integrate_keyframes(c, ids, n, false); }
 
 int ssm_map_integrate_points(ssm_ctx* c, const float* xyz, const uint32_t* rgba, const uint8_t* label, int n)
 {

@@ -335,6 +335,28 @@ __global__ void __launch_bounds__(256) k_fuse_list(const Point* __restrict__ pts
         fuse_point(p, table, slot_mask, pts[i], counters);
 }
 
+// Cached keyframe clouds (mapper.cpp:17-20 keeps frame->pointcloud in camera coordinates; :90-91 re-transforms it by
+// the frame's current pose on every redraw): pcl::transformPointCloud in double, rounded to float, then the hash insert.
+struct Pose12 { double m[12]; };
+__global__ void __launch_bounds__(256) k_transform_fuse(const Point* __restrict__ pts, uint32_t n, Pose12 T, Voxel* __restrict__ table,
+                                                        uint64_t slot_mask, uint32_t* counters, SSM_DP)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Point pt = pts[i];
+        float w[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double acc = __dmul_rn(T.m[4 * k], (double)pt.x);
+            acc = __dadd_rn(acc, __dmul_rn(T.m[4 * k + 1], (double)pt.y));
+            acc = __dadd_rn(acc, __dmul_rn(T.m[4 * k + 2], (double)pt.z));
+            acc = __dadd_rn(acc, T.m[4 * k + 3]);
+            w[k] = (float)acc;
+        }
+        pt.x = w[0]; pt.y = w[1]; pt.z = w[2];
+        fuse_point(p, table, slot_mask, pt, counters);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_table_clear(Voxel* __restrict__ table, size_t words16)
 {
     uint4* t = reinterpret_cast<uint4*>(table);
@@ -435,6 +457,17 @@ int launch_fuse_points(ssm_ctx* c, const Point* d_pts, const uint32_t* d_count, 
     if (max_count == 0) return SSM_OK;
     const unsigned grid = (unsigned)std::min<size_t>(((size_t)max_count + 255) / 256, (size_t)c->sm_count * 16);
     k_fuse_list<<<grid, 256, 0, s>>>(d_pts, d_count, max_count, c->d_table, c->table_slots - 1, c->d_counters, c->dp);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+int launch_transform_fuse(ssm_ctx* c, const Point* d_pts, uint32_t n, const double* T16, cudaStream_t s)
+{
+    if (n == 0) return SSM_OK;
+    Pose12 T;
+    for (int i = 0; i < 12; ++i) T.m[i] = T16[i];
+    const unsigned grid = (unsigned)std::min<size_t>(((size_t)n + 255) / 256, (size_t)c->sm_count * 16);
+    k_transform_fuse<<<grid, 256, 0, s>>>(d_pts, n, T, c->d_table, c->table_slots - 1, c->d_counters, c->dp);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }

@@ -163,6 +163,8 @@ struct ssm_ctx {
     size_t inbox_cap = 0;                            // points per parity buffer
     bool p2p = false;
     uint64_t p2p_step = 0;                           // parity source
+    void* keyframes = nullptr;                       // cached camera-space keyframe clouds (api.cu: ssm_keyframe_*)
+    void* labels_ws = nullptr;                       // label production workspace (labels.cu)
     void* cues_ws = nullptr;                         // dense motion cues workspace (cues.cu), allocated on first use
 };
 
@@ -170,6 +172,7 @@ namespace ssm {
 
 void set_error(const std::string& s);
 void cues_free(ssm_ctx* c);   // cues.cu
+void labels_free(ssm_ctx* c); // labels.cu
 int cuda_fail(cudaError_t e, const char* what);
 
 #define SSM_CUDA(expr)                                                      \
@@ -205,6 +208,7 @@ int launch_points(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t* d_s
                   const double* d_pose, bool fuse_into_map, cudaStream_t s);
 int launch_fuse_points(ssm_ctx* c, const Point* d_pts, const uint32_t* d_count, uint32_t max_count, cudaStream_t s);
 int launch_map_clear(ssm_ctx* c, cudaStream_t s);
+int launch_transform_fuse(ssm_ctx* c, const Point* d_pts, uint32_t n, const double* T16, cudaStream_t s);
 int launch_export(ssm_ctx* c, Voxel* d_out, uint32_t max_out, cudaStream_t s);
 int launch_route_bucket(ssm_ctx* c, uint32_t max_points, cudaStream_t s);   // d_points -> d_send grouped by owner rank
 int route_and_fuse(ssm_ctx* c, cudaStream_t s);   // multi-GPU: bucket by owner, NCCL all-to-all, fuse received

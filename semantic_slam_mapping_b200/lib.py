@@ -23,6 +23,9 @@ SYMBOLS = [
     "ssm_pipeline_batch_device", "ssm_pipeline_batch_host", "ssm_pipeline_batch_host_async", "ssm_synchronize", "ssm_comm_get_unique_id",
     "ssm_comm_init", "ssm_comm_ipc_export", "ssm_comm_ipc_connect", "ssm_comm_destroy", "ssm_voxel_owner",
     "ssm_triangulate10d", "ssm_correct_3d_points", "ssm_set_image_roi", "ssm_v_disparity", "ssm_u_disparity",
+    "ssm_keyframe_add", "ssm_keyframe_set_pose", "ssm_keyframe_release", "ssm_keyframe_count", "ssm_map_redraw",
+    "ssm_map_integrate_keyframes",
+    "ssm_labels_from_indices", "ssm_labels_from_indices_batch_device",
     "ssm_motion_cues_stage1_device", "ssm_motion_cues_stage2_device", "ssm_motion_cues_overflow",
 ]
 
@@ -84,6 +87,14 @@ def load() -> C.CDLL:
     L.ssm_comm_destroy.argtypes = [vp]
     L.ssm_voxel_owner.argtypes = [C.c_int32, C.c_int32, C.c_int32, i]
     d = C.c_double
+    L.ssm_labels_from_indices.argtypes = [vp, vp, sz, i, i, i, i, vp, vp, sz, vp, sz]
+    L.ssm_labels_from_indices_batch_device.argtypes = [vp, i, vp, i, i, i, i, vp, vp, vp, vp]
+    L.ssm_keyframe_add.argtypes = [vp, vp, vp, vp, i, i, vp, C.POINTER(i)]
+    L.ssm_keyframe_set_pose.argtypes = [vp, i, vp]
+    L.ssm_keyframe_release.argtypes = [vp, i]
+    L.ssm_keyframe_count.argtypes = [vp, C.POINTER(i), C.POINTER(u64)]
+    L.ssm_map_redraw.argtypes = [vp, vp, i]
+    L.ssm_map_integrate_keyframes.argtypes = [vp, vp, i]
     L.ssm_triangulate10d.argtypes = [vp, vp, sz, vp, sz, i, i, d, d, d, d, d, d, d, vp]
     L.ssm_correct_3d_points.argtypes = [vp, vp, i, i, d, d, d, d, d]
     L.ssm_set_image_roi.argtypes = [vp, vp, i, i, vp, sz]
@@ -211,6 +222,36 @@ class Context:
         label = np.ascontiguousarray(label, np.uint8)
         self._check(self._L.ssm_map_integrate_points(self._h, _ptr(xyz), _ptr(rgba), _ptr(label), xyz.shape[0]))
 
+    def keyframe_add(self, depth, semantic_bgr, rgb_bgr, T) -> int:
+        depth = np.ascontiguousarray(depth, np.uint16)
+        sem = np.ascontiguousarray(semantic_bgr, np.uint8)
+        rgb = np.ascontiguousarray(rgb_bgr, np.uint8)
+        T = np.ascontiguousarray(T, np.float64).reshape(16)
+        h, w = depth.shape
+        kid = C.c_int(-1)
+        self._check(self._L.ssm_keyframe_add(self._h, _ptr(depth), _ptr(sem), _ptr(rgb), w, h, _ptr(T), C.byref(kid)))
+        return int(kid.value)
+
+    def keyframe_set_pose(self, kid: int, T):
+        T = np.ascontiguousarray(T, np.float64).reshape(16)
+        self._check(self._L.ssm_keyframe_set_pose(self._h, kid, _ptr(T)))
+
+    def keyframe_release(self, kid: int):
+        self._check(self._L.ssm_keyframe_release(self._h, kid))
+
+    def keyframe_count(self):
+        n, pts = C.c_int(0), C.c_uint64(0)
+        self._check(self._L.ssm_keyframe_count(self._h, C.byref(n), C.byref(pts)))
+        return int(n.value), int(pts.value)
+
+    def map_redraw(self, ids=None):
+        a = None if ids is None else np.ascontiguousarray(ids, np.int32)
+        self._check(self._L.ssm_map_redraw(self._h, _ptr(a), 0 if a is None else len(a)))
+
+    def map_integrate_keyframes(self, ids=None):
+        a = None if ids is None else np.ascontiguousarray(ids, np.int32)
+        self._check(self._L.ssm_map_integrate_keyframes(self._h, _ptr(a), 0 if a is None else len(a)))
+
     def map_clear(self):
         self._check(self._L.ssm_map_clear(self._h))
 
@@ -234,6 +275,21 @@ class Context:
 
     def map_save_pcd(self, path: str):
         self._check(self._L.ssm_map_save_pcd(self._h, path.encode()))
+
+    # -- label production (experiment/segnet.cpp:121-135) ---------------------------------------------------------------
+    def labels_from_indices(self, index_img, dw: int, dh: int, lut_bgr, want_raw: bool = True):
+        idx = np.ascontiguousarray(index_img, np.uint8)
+        lut = np.ascontiguousarray(lut_bgr, np.uint8).reshape(256, 3)
+        sh, sw = idx.shape
+        sem = np.empty((dh, dw, 3), np.uint8)
+        raw = np.empty((dh, dw), np.uint8) if want_raw else None
+        self._check(self._L.ssm_labels_from_indices(self._h, _ptr(idx), sw, sw, sh, dw, dh, _ptr(lut), _ptr(sem), dw * 3, _ptr(raw), dw))
+        return sem, raw
+
+    def labels_from_indices_batch_device(self, d_index, d_sem, batch, sw, sh, dw, dh, lut_bgr, d_raw=None, stream=None):
+        lut = np.ascontiguousarray(lut_bgr, np.uint8).reshape(256, 3)
+        self._check(self._L.ssm_labels_from_indices_batch_device(self._h, batch, _ptr(d_index), sw, sh, dw, dh, _ptr(lut), _ptr(d_sem), _ptr(d_raw),
+                                                                 C.c_void_p(stream) if stream else None))
 
     # -- dense motion cues (stereo.h triangulate10D / correct3DPoints / setImageROI, UVDisparity::cal[UV]Disparity) --------
     def triangulate10d(self, img, disp, f, cx, cy, b, roi=(30000.0, -1000.0, 30000.0)) -> np.ndarray:

@@ -184,3 +184,49 @@ def test_split_batch_streams_match_oracle(monkeypatch):
         got = ctx.map_export()
     assert int((disp != np.stack(disps)).sum()) == 0 and nvox == len(vm)
     _compare_maps(got, vm.export())
+
+
+def test_keyframe_cache_redraw_after_pose_update():
+    """Mapper::viewer's periodic redraw (mapper.cpp:121-131) from cached camera-space clouds (:17-20, :90-91) after the
+    pose graph rewrote the keyframe poses (pose_graph.cpp:253-260): the map equals one built from scratch."""
+    H, W, D, N = 96, 320, 64, 6
+    p = Params(num_disparities=D, max_width=W, max_height=H, resolution=0.05, map_capacity=1 << 18)
+    mp = _mp(p)
+    frames = []
+    for i in range(N):
+        L, R, sem, rgb = _frame(H, W, D, 40 + i, p)
+        depth = oracle.disparity_to_depth(oracle.sgbm(L, R, _op(p)), mp)
+        frames.append((depth, sem, rgb))
+    poses0 = synth.poses(N, 1)
+    # "optimised" poses: a different trajectory seed plus a small extra rotation / shift per frame
+    poses1 = synth.poses(N, 2).copy()
+    for i in range(N):
+        a = 0.01 * (i + 1)
+        Rz = np.array([[np.cos(a), -np.sin(a), 0, 0.03 * i], [np.sin(a), np.cos(a), 0, -0.02 * i], [0, 0, 1, 0.01], [0, 0, 0, 1]])
+        poses1[i] = Rz @ poses1[i]
+
+    def oracle_map(ids, poses):
+        vm = oracle.VoxelMap(p.resolution, p.num_labels)
+        for i in ids:
+            pc = oracle.generate_point_cloud(*frames[i], mp, poses[i])
+            vm.insert(pc["xyz"], pc["rgba"], pc["label"])
+        return vm.export()
+
+    with Context(p) as ctx:
+        ids = [ctx.keyframe_add(*frames[i], poses0[i]) for i in range(N)]
+        n_live, n_pts = ctx.keyframe_count()
+        assert n_live == N and n_pts == sum(len(oracle.generate_point_cloud(*frames[i], mp, poses0[i])["xyz"]) for i in range(N))
+        ctx.map_redraw()                                     # every keyframe, original poses
+        _compare_maps(ctx.map_export(), oracle_map(range(N), poses0))
+        for i in range(N):
+            ctx.keyframe_set_pose(ids[i], poses1[i])
+        ctx.map_redraw(ids[::2])                             # the reference redraws every second keyframe (i += 2)
+        _compare_maps(ctx.map_export(), oracle_map(range(0, N, 2), poses1))
+        ctx.map_integrate_keyframes(ids[1::2])               # incremental branch: += without clearing
+        _compare_maps(ctx.map_export(), oracle_map(list(range(0, N, 2)) + list(range(1, N, 2)), poses1))
+        ctx.keyframe_release(ids[0])
+        assert ctx.keyframe_count()[0] == N - 1
+        ctx.map_redraw()
+        _compare_maps(ctx.map_export(), oracle_map(range(1, N), poses1))
+        with pytest.raises(Exception):
+            ctx.keyframe_set_pose(ids[0], poses1[0])         # released id
