@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) k_aggr_path(AggrArgs a)
     }
     const int d0 = lane * 2 * NR;
     const bool active = d0 < a.D;
-    const PathLane pl = make_path_lane(lane, a.one);
+    const PathLane pl = make_path_lane(lane, a.one, (uint32_t)a.P1);
     const uint32_t P1w = (uint32_t)a.P1 * 0x10001u, P2w = (uint32_t)a.P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)a.P2) * 0x10001u;
     const size_t frame = (size_t)b * a.H * a.W1;

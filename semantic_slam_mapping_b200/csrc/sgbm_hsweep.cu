@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128) k_hsweep(const int16_t* __restrict__ C, u
     constexpr int LOG_DPL = NR == 1 ? 1 : (NR == 2 ? 2 : (NR == 4 ? 3 : 4));
     const int d0 = lane * 2 * NR;
     const bool active = d0 < D;
-    const PathLane pl = make_path_lane(lane, one);
+    const PathLane pl = make_path_lane(lane, one, (uint32_t)P1);
     const uint32_t P1w = (uint32_t)P1 * 0x10001u, P2w = (uint32_t)P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)P2) * 0x10001u;
     const uint16_t* Crow = reinterpret_cast<const uint16_t*>(C) + (size_t)row * W1 * D + d0;

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) k_hfwd(const int16_t* __restrict__ C, uin
     constexpr int LW = 32 * NR;
     const int d0 = lane * 2 * NR;
     const bool active = FULL || d0 < D;
-    const PathLane pl = make_path_lane(lane, one);
+    const PathLane pl = make_path_lane(lane, one, (uint32_t)P1);
     const uint32_t P1w = (uint32_t)P1 * 0x10001u, P2w = (uint32_t)P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)P2) * 0x10001u;
     const uint8_t* Cg = reinterpret_cast<const uint8_t*>(C) + (size_t)row * W1 * colbytes;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128) k_hrev(const HrevArgs a)
     constexpr int LW = 32 * NR;
     const int d0 = lane * 2 * NR;
     const bool active = FULL || d0 < D;
-    const PathLane pl = make_path_lane(lane, a.one);
+    const PathLane pl = make_path_lane(lane, a.one, (uint32_t)a.P1);
     const uint32_t P1w = (uint32_t)a.P1 * 0x10001u, P2w = (uint32_t)a.P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)a.P2) * 0x10001u;
     const uint32_t lanemask = active ? (NR == 2 ? 0x80808080u : 0x00008080u) : 0u;

@@ -86,57 +86,73 @@ struct PathLane {
     uint32_t one;      // 1
     uint32_t sh16;     // 65536
     uint32_t keep0;    // lane 0: 0, else 1          -- d = -1 reads "+inf": up = shfl * keep0 + add0
-    uint32_t add0;     // lane 0: kBig, else 0
+    uint32_t add0;     // lane 0: kBig | P1 << 16 (the upper half carries the +P1 the shuffled word would have brought), else 0
     uint32_t mul31;    // lane 31: 0, else 65536     -- d past the last lane reads "+inf": s = dn * mul31 + (hi + add31)
     uint32_t add31;    // lane 31: kBig << 16, else 0
+    uint32_t seg_lo;   // LANES == 16 only: all-ones in lanes 16..31 (masks this lane out of the lower segment's REDUX)
+    uint32_t seg_hi;   //                   all-ones in lanes 0..15
 };
-__device__ __forceinline__ PathLane make_path_lane(int lane, uint32_t one)
+// LANES = lanes that share one pixel's disparity range: 32 (a warp per pixel) or 16 (two pixels per warp, one per
+// half-warp: the per-step overhead -- shuffles, border fix-ups, reduction, addressing -- is paid once for both)
+template <int LANES = 32>
+__device__ __forceinline__ PathLane make_path_lane(int lane, uint32_t one, uint32_t P1)
 {
+    const int sl = lane & (LANES - 1);
     PathLane p;
     p.one = one;
     p.sh16 = one << 16;
-    p.keep0 = lane == 0 ? 0u : one;
-    p.add0 = lane == 0 ? kBig : 0u;
-    p.mul31 = lane == 31 ? 0u : one << 16;
-    p.add31 = lane == 31 ? kBig << 16 : 0u;
+    p.keep0 = sl == 0 ? 0u : one;
+    p.add0 = sl == 0 ? (kBig | (P1 << 16)) : 0u;
+    p.mul31 = sl == LANES - 1 ? 0u : one << 16;
+    p.add31 = sl == LANES - 1 ? kBig << 16 : 0u;
+    p.seg_lo = lane >= 16 ? 0xffffffffu : 0u;
+    p.seg_hi = lane >= 16 ? 0u : 0xffffffffu;
     keep(p.sh16); keep(p.keep0); keep(p.add0); keep(p.mul31); keep(p.add31);
+    if (LANES == 16) { keep(p.seg_lo); keep(p.seg_hi); }
     return p;
 }
 
 // One step of the recurrence for this lane's 2*NR disparities.
-//   mw   packed (m, m): the warp-wide minimum of the incoming state, in both 16-bit halves
+//   mw   packed (m, m): the minimum of the incoming state over the pixel's disparities, in both 16-bit halves
 //   P1w, P2w   packed penalties
-// Returns the packed minimum of the new state.  The NR+1 distinct "shifted by one disparity" words
-// s[k] = (w[k-1].hi, w[k].lo) are built once each as w[k] * 65536 + hi(w[k-1]); the lane minimum stays packed
-// (PRMT + VIMNMX.U16x2) so the REDUX result is directly the next step's mw.
-template <int NR>
+// Returns the packed minimum of the new state.  The NR+1 distinct "shifted by one disparity, plus P1" words
+// s[k] = (w[k-1].hi, w[k].lo) + P1 are built once each: hp = (w >> 16) + P1w carries P1 in BOTH halves (one LEA.HI), so
+// s[k] = w[k] * 65536 + hp[k-1] is one IMAD; then min(L[d], m + P2, L[d-1] + P1) is one VIMNMX3 and L[d+1] + P1 one
+// VIMNMX.  The lane minimum stays packed (PRMT + VIMNMX.U16x2) so the REDUX result is directly the next step's mw.
+template <int NR, int LANES = 32>
 __device__ __forceinline__ uint32_t path_step(uint32_t (&L)[NR], const uint32_t (&Cw)[NR], uint32_t mw, uint32_t P1w,
                                               uint32_t P2w, const PathLane& pl)
 {
-    uint32_t hi[NR];
+    uint32_t hp[NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) hi[r] = L[r] >> 16;
-    const uint32_t up_hi = __shfl_up_sync(0xffffffffu, hi[NR - 1], 1) * pl.keep0 + pl.add0;
-    const uint32_t dn = __shfl_down_sync(0xffffffffu, L[0], 1);
+    for (int r = 0; r < NR; ++r) hp[r] = (L[r] >> 16) + P1w;
+    const uint32_t up_hp = __shfl_up_sync(0xffffffffu, hp[NR - 1], 1, LANES) * pl.keep0 + pl.add0;
+    const uint32_t dn = __shfl_down_sync(0xffffffffu, L[0], 1, LANES);
     uint32_t sft[NR + 1];
-    sft[0] = L[0] * pl.sh16 + up_hi;
+    sft[0] = L[0] * pl.sh16 + up_hp;
 #pragma unroll
-    for (int r = 1; r < NR; ++r) sft[r] = L[r] * pl.sh16 + hi[r - 1];
-    sft[NR] = dn * pl.mul31 + (hi[NR - 1] * pl.one + pl.add31);
+    for (int r = 1; r < NR; ++r) sft[r] = L[r] * pl.sh16 + hp[r - 1];
+    sft[NR] = dn * pl.mul31 + (hp[NR - 1] * pl.one + pl.add31);
     const uint32_t mP2w = mw * pl.one + P2w;
     const uint32_t nmw = 0u - mw;
     uint32_t mn = 0xffffffffu;
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const uint32_t cm = Cw[r] * pl.one + nmw;                // C - m, off the critical path
-        uint32_t t = __viaddmin_u16x2(sft[r], P1w, L[r]);        // min(L[d-1] + P1, L[d])
-        t = __viaddmin_u16x2(sft[r + 1], P1w, t);                // min(L[d+1] + P1, .)
-        t = __vminu2(t, mP2w);
+        uint32_t t = __vimin3_u16x2(L[r], mP2w, sft[r]);         // min(L[d], m + P2, L[d-1] + P1)
+        t = __vminu2(t, sft[r + 1]);                             // min(., L[d+1] + P1)
         L[r] = t * pl.one + cm;                                  // every lane of t >= m: plain 32-bit arithmetic is exact
         mn = r == 0 ? L[r] : __vminu2(mn, L[r]);
     }
     mn = __vminu2(mn, __byte_perm(mn, 0, 0x1032));               // both halves = the lane minimum
-    return __reduce_min_sync(0xffffffffu, mn);
+    if constexpr (LANES == 32) {
+        return __reduce_min_sync(0xffffffffu, mn);
+    } else {
+        // one REDUX per half-warp segment: the other segment's lanes contribute all-ones
+        const uint32_t a = __reduce_min_sync(0xffffffffu, mn | pl.seg_lo);
+        const uint32_t b = __reduce_min_sync(0xffffffffu, mn | pl.seg_hi);
+        return (a & pl.seg_hi) | (b & pl.seg_lo);
+    }
 }
 
 }  // namespace ssm

@@ -74,7 +74,7 @@ __device__ __forceinline__ void st_async_word(uint32_t remote_addr, uint32_t v, 
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
 }
 
-template <int NR, int NWARPS, bool FULL /* D == 64 * NR: every lane owns disparities */>
+template <int NR, int NWARPS, bool FULL /* D == 2 * NR * LANES: every lane owns disparities */, int LANES = 32 /* lanes per column */>
 __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __restrict__ C, uint16_t* __restrict__ S, int W1, int H,
                                                              int D, int P1, int P2, int T, uint32_t one, int pf_rows)
 {
@@ -83,8 +83,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
     const int CS = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int frame = blockIdx.x / CS;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int LW = 32 * NR;                  // words per (column, direction) line
+    // a "virtual warp" of LANES lanes takes a column; with LANES == 16 a physical warp walks two columns at once
+    constexpr int VPW = 32 / LANES;              // virtual warps per warp
+    constexpr int NVW = NWARPS * VPW;            // virtual warps per CTA
+    const int lane = threadIdx.x & (LANES - 1);  // lane within the virtual warp
+    const int warp = (int)(threadIdx.x / LANES); // virtual warp
+    const int pwarp = threadIdx.x >> 5;          // physical warp
+    constexpr int LW = LANES * NR;               // words per (column, direction) line
     constexpr int LWB = LW * 4;                  // bytes per line
     constexpr uint32_t kHandBytes = LWB + 4;     // one hand-over: a state line + its packed minimum
 
@@ -130,13 +135,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
     const bool active = FULL || d0 < D;
     const uint32_t P1w = (uint32_t)P1 * 0x10001u, P2w = (uint32_t)P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)P2) * 0x10001u;
-    const PathLane pl = make_path_lane(lane, one);
+    const PathLane pl = make_path_lane<LANES>((int)(threadIdx.x & 31), one, (uint32_t)P1);
     const size_t rowbytes = (size_t)W1 * D * 2;
     const char* Crow = reinterpret_cast<const char*>(C) + ((size_t)frame * H * W1 + x0) * D * 2 + d0 * 2;
     char* Srow = reinterpret_cast<char*>(S) + ((size_t)frame * H * W1 + x0) * D * 2 + d0 * 2;
-    const int nk = Tc > warp ? (Tc - warp + NWARPS - 1) / NWARPS : 0;   // my columns: warp, warp + NWARPS, ...
-    const uint32_t cstep = (uint32_t)NWARPS * D * 2;                    // bytes between my consecutive columns
-    const int wl = Tc > 0 ? (Tc - 1) % NWARPS : -1;                     // the warp that owns the strip's last column
+    const int nk = Tc > warp ? (Tc - warp + NVW - 1) / NVW : 0;         // my columns: warp, warp + NVW, ...
+    const int nk_w = Tc > pwarp * VPW ? (Tc - pwarp * VPW + NVW - 1) / NVW : 0;   // trip count of the physical warp (its first virtual warp's)
+    const uint32_t cstep = (uint32_t)NVW * D * 2;                       // bytes between my consecutive columns
+    const int wl = Tc > 0 ? (Tc - 1) % NVW : -1;                        // the virtual warp that owns the strip's last column
 
     uint32_t Cw[NR], Cn[NR];
 #pragma unroll
@@ -159,40 +165,49 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
         // the hand-overs of the neighbours' previous row must have landed before the border columns are touched
         if (y > 0) {
             const uint32_t parity = (uint32_t)(y - 1) & 1u;
-            if (warp == 0 && has_left) {
+            if (pwarp == 0 && has_left) {
                 mbar_wait_cluster(bar_l, parity);
-                if (lane == 0) mbar_arrive_expect_tx(bar_l, kHandBytes);      // arm the next phase (this row's hand-over)
+                if (threadIdx.x == 0) mbar_arrive_expect_tx(bar_l, kHandBytes);      // arm the next phase (this row's hand-over)
             }
-            if (warp == wl && has_right) {
+            if (pwarp == wl / VPW && has_right) {
                 mbar_wait_cluster(bar_r, parity);
-                if (lane == 0) mbar_arrive_expect_tx(bar_r, kHandBytes);
+                if ((threadIdx.x & 31) == 0) mbar_arrive_expect_tx(bar_r, kHandBytes);
             }
         }
         uint32_t off = (uint32_t)warp * D * 2;
         int c = warp;
         int s1 = c + o1; s1 = (int)min((unsigned)s1, (unsigned)(s1 - R));
         int s2 = c + o2; s2 = (int)min((unsigned)s2, (unsigned)(s2 - R));
-        for (int k = 0; k < nk; ++k) {
+        for (int k = 0; k < nk_w; ++k) {
+            const bool mine = VPW == 1 || k < nk;    // the last trip of a warp may cover only its first column(s)
             // prefetch the cost of my next column (next row's first one at the end of the row)
             if (active) {
                 if (k + 1 < nk) load_words<NR>(Crow + off + cstep, Cn);
-                else if (y + 1 < H) load_words<NR>(Crow + rowbytes + (size_t)warp * D * 2, Cn);
+                else if (k + 1 == nk && y + 1 < H) load_words<NR>(Crow + rowbytes + (size_t)warp * D * 2, Cn);
             }
             const uint32_t p0 = a0 + c * LWB, p1 = a1 + s1 * LWB, p2 = a2 + s2 * LWB;
             const uint32_t q0 = am0 + c * 4, q1 = am1 + s1 * 4, q2 = am2 + s2 * 4;
             uint32_t L0[NR], L1[NR], L2[NR];
-            lds_words<NR>(p0, L0);
-            lds_words<NR>(p1, L1);
-            lds_words<NR>(p2, L2);
-            uint32_t m0 = lds_u32(q0), m1 = lds_u32(q1), m2 = lds_u32(q2);
-            m0 = path_step<NR>(L0, Cw, m0, P1w, P2w, pl);
-            m1 = path_step<NR>(L1, Cw, m1, P1w, P2w, pl);
-            m2 = path_step<NR>(L2, Cw, m2, P1w, P2w, pl);
-            sts_words<NR>(p0, L0);
-            sts_words<NR>(p1, L1);
-            sts_words<NR>(p2, L2);
-            if (lane == 0) { sts_u32(q0, m0); sts_u32(q1, m1); sts_u32(q2, m2); }
-            if (active) {
+            uint32_t m0 = 0u, m1 = 0u, m2 = 0u;
+            if (mine) {
+                lds_words<NR>(p0, L0);
+                lds_words<NR>(p1, L1);
+                lds_words<NR>(p2, L2);
+                m0 = lds_u32(q0); m1 = lds_u32(q1); m2 = lds_u32(q2);
+            } else {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) { L0[r] = 0u; L1[r] = 0u; L2[r] = 0u; }
+            }
+            m0 = path_step<NR, LANES>(L0, Cw, m0, P1w, P2w, pl);
+            m1 = path_step<NR, LANES>(L1, Cw, m1, P1w, P2w, pl);
+            m2 = path_step<NR, LANES>(L2, Cw, m2, P1w, P2w, pl);
+            if (mine) {
+                sts_words<NR>(p0, L0);
+                sts_words<NR>(p1, L1);
+                sts_words<NR>(p2, L2);
+                if (lane == 0) { sts_u32(q0, m0); sts_u32(q1, m1); sts_u32(q2, m2); }
+            }
+            if (active && mine) {
                 uint32_t o[NR];
 #pragma unroll
                 for (int r = 0; r < NR; ++r) o[r] = __viaddmin_u16x2(__viaddmin_u16x2(L0[r], L1[r], kSatW), L2[r], kSatW);
@@ -201,9 +216,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
 #pragma unroll
             for (int r = 0; r < NR; ++r) Cw[r] = Cn[r];
             off += cstep;
-            c += NWARPS;
-            s1 += NWARPS; s1 = (int)min((unsigned)s1, (unsigned)(s1 - R));
-            s2 += NWARPS; s2 = (int)min((unsigned)s2, (unsigned)(s2 - R));
+            c += NVW;
+            s1 += NVW; s1 = (int)min((unsigned)s1, (unsigned)(s1 - R));
+            s2 += NVW; s2 = (int)min((unsigned)s2, (unsigned)(s2 - R));
         }
         // hand the strip's border columns to the neighbours (asynchronous stores that credit the peer's mbarrier; no
         // fence, no cluster barrier), or feed zeros at the image border.  Nothing is sent after the last row: the
@@ -263,11 +278,11 @@ struct VerticalPlan {
     size_t smem = 0;
 };
 
-template <int NR, int NWARPS, bool FULL>
+template <int NR, int NWARPS, bool FULL, int LANES = 32>
 static int launch_vertical_t(ssm_ctx* c, int B, const VerticalPlan& plan, cudaStream_t s, bool* done)
 {
     const DevParams& p = c->dp;
-    auto kern = k_vertical3<NR, NWARPS, FULL>;
+    auto kern = k_vertical3<NR, NWARPS, FULL, LANES>;
     SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     if (plan.cluster > 8) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
@@ -329,6 +344,9 @@ int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done)
     const bool full = D == 64 || D == 128 || D == 256 || D == 512;
     if (D <= 64) return full ? launch_vertical_t<1, 32, true>(c, B, plan, s, done) : launch_vertical_t<1, 32, false>(c, B, plan, s, done);
     if (D <= 128) {
+        // D == 128: two columns per warp (16 lanes x 4 words each) halve the per-column overhead of the recurrence
+        if (D == 128 && c->tune[2] == 0) return launch_vertical_t<4, 16, true, 16>(c, B, plan, s, done);
+        if (D == 128 && c->tune[2] == 2) return launch_vertical_t<4, 24, true, 16>(c, B, plan, s, done);
         if (full && c->tune[2] == 1) return launch_vertical_t<2, 24, true>(c, B, plan, s, done);
         return full ? launch_vertical_t<2, 32, true>(c, B, plan, s, done) : launch_vertical_t<2, 32, false>(c, B, plan, s, done);
     }
