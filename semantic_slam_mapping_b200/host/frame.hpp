@@ -77,6 +77,7 @@ struct Frame {
     Camera camera;
     std::array<double, 16> T_f_w{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}};   // camera -> world, row-major
     std::mutex mutexT;
+    int cloud_id = -1;   // frame->pointcloud (rgbdframe.h:58): id of the cached camera-space cloud on the Mapper's device, -1 = not built
 
     void setTransform(const std::array<double, 16>& T)
     {

@@ -1,5 +1,6 @@
 // host.cpp -- C++ host layer above the C ABI: calDisparity_SGBM and rgbd_tutor::Mapper mirrors.
 // Links against libssm.so only (no CUDA headers, no OpenCV/PCL).  See stereo.hpp / mapper.hpp.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -66,6 +67,66 @@ void disparityToDepth(const ImageS16& disp, ImageU16& depth)
 }
 
 // ---------------------------------------------------------------------------------------------
+// stereo.h / uvdisparity.hpp: dense motion cues
+// ---------------------------------------------------------------------------------------------
+static void need_dense(bool ok, const char* what)
+{
+    if (!ok) throw Error(SSM_ERR_INVALID_ARGUMENT, std::string(what) + ": images must be non-empty, equally sized and densely packed");
+}
+
+void triangulate10D(const ImageU8& img, const ImageS16& disp, ImageXYZ10& xyz, const double f, const double cx, const double cy,
+                    const double b, ROI3D roi)
+{
+    need_dense(!img.empty() && !disp.empty() && img.rows == disp.rows && img.cols == disp.cols, "triangulate10D");
+    xyz.create(disp.rows, disp.cols);
+    check(ssm_triangulate10d(stereoContext(), img.data, img.step, disp.data, disp.step, disp.cols, disp.rows, f, cx, cy, b, roi.x_max,
+                             roi.y_max, roi.z_max, xyz.data));
+}
+
+void correct3DPoints(ImageXYZ10& xyz, ROI3D& roi_, const double& pitch1, const double& pitch2)
+{
+    need_dense(!xyz.empty(), "correct3DPoints");
+    check(ssm_correct_3d_points(stereoContext(), xyz.data, xyz.cols, xyz.rows, roi_.x_max, roi_.y_max, roi_.z_max, pitch1, pitch2));
+}
+
+void setImageROI(ImageXYZ10& xyz, ImageU8& roi_mask)
+{
+    need_dense(!xyz.empty(), "setImageROI");
+    roi_mask.create(xyz.rows, xyz.cols);
+    check(ssm_set_image_roi(stereoContext(), xyz.data, xyz.cols, xyz.rows, roi_mask.data, roi_mask.step));
+}
+
+void UVDisparity::calVDisparity(const ImageS16& img_dis, ImageXYZ10& xyz)
+{
+    need_dense(!img_dis.empty() && xyz.rows == img_dis.rows && xyz.cols == img_dis.cols, "calVDisparity");
+    int v_cols = 0;
+    ssm_ctx* c = stereoContext();
+    check(ssm_v_disparity(c, img_dis.data, img_dis.step, img_dis.cols, img_dis.rows, nullptr, nullptr, nullptr, 0, &v_cols));   // size
+    v_dis_int = ImageS32(); v_dis_ = ImageU8();
+    v_dis_int.create(img_dis.rows, v_cols);
+    v_dis_.create(img_dis.rows, v_cols);
+    check(ssm_v_disparity(c, img_dis.data, img_dis.step, img_dis.cols, img_dis.rows, xyz.data, v_cols ? v_dis_int.data : nullptr,
+                          v_cols ? v_dis_.data : nullptr, v_cols, &v_cols));
+}
+
+void UVDisparity::calUDisparity(const ImageS16& img_dis, ImageXYZ10& xyz, ImageU8& roi_mask, ImageU8& ground_mask)
+{
+    need_dense(!img_dis.empty() && xyz.rows == img_dis.rows && xyz.cols == img_dis.cols && roi_mask.rows == img_dis.rows &&
+                   roi_mask.cols == img_dis.cols && ground_mask.rows == img_dis.rows && ground_mask.cols == img_dis.cols &&
+                   roi_mask.step == (size_t)img_dis.cols && ground_mask.step == (size_t)img_dis.cols,
+               "calUDisparity");
+    int u_rows = 0;
+    ssm_ctx* c = stereoContext();
+    check(ssm_u_disparity(c, img_dis.data, img_dis.step, img_dis.cols, img_dis.rows, nullptr, roi_mask.data, ground_mask.data, nullptr, nullptr, 0,
+                          &u_rows));
+    u_dis_int = ImageS32(); u_dis_ = ImageU8();
+    u_dis_int.create(u_rows, img_dis.cols);
+    u_dis_.create(u_rows, img_dis.cols);
+    check(ssm_u_disparity(c, img_dis.data, img_dis.step, img_dis.cols, img_dis.rows, xyz.data, roi_mask.data, ground_mask.data, u_dis_int.data,
+                          u_dis_.data, u_rows, &u_rows));
+}
+
+// ---------------------------------------------------------------------------------------------
 // mapper.h
 // ---------------------------------------------------------------------------------------------
 Mapper::Mapper(const MapperConfig& para, KeyframeSource& graph, bool start_thread) : config(para), poseGraph(graph)
@@ -121,11 +182,16 @@ std::shared_ptr<Mapper::PointCloud> Mapper::generatePointCloud(const Frame::Ptr&
     return cloud;
 }
 
-void Mapper::integrate(const Frame::Ptr& frame)
+// frame->pointcloud of the reference (mapper.cpp:17-20): the keyframe's cloud is built once, kept on the device in camera
+// coordinates and re-transformed by the frame's current pose whenever the map is (re)drawn
+int Mapper::cloudOf(const Frame::Ptr& frame)
 {
-    const int w = frame->depth.cols, h = frame->depth.rows;
-    const std::array<double, 16> T = frame->getTransform();
-    check(ssm_map_integrate_frame(ctx, frame->depth.data, frame->semantic.data, frame->rgb.data, w, h, T.data()));
+    if (frame->cloud_id < 0) {
+        const int w = frame->depth.cols, h = frame->depth.rows;
+        const std::array<double, 16> T = frame->getTransform();
+        check(ssm_keyframe_add(ctx, frame->depth.data, frame->semantic.data, frame->rgb.data, w, h, T.data(), &frame->cloud_id));
+    }
+    return frame->cloud_id;
 }
 
 void Mapper::viewer()
@@ -141,11 +207,24 @@ void Mapper::viewer()
             continue;
         }
         const auto t0 = std::chrono::steady_clock::now();
+        std::vector<int> ids;
         if (config.redraw_every > 0 && cntGlobalUpdate % config.redraw_every == 0) {
-            check(ssm_map_clear(ctx));                                   // globalMap->clear(), mapper.cpp:125
-            for (const Frame::Ptr& f : kfs) integrate(f);
+            // periodic full redraw (mapper.cpp:121-131): poses may have been rewritten by the pose graph since the last one
+            for (size_t i = 0; i < kfs.size(); i += (size_t)std::max(1, config.redraw_stride)) {
+                const int id = cloudOf(kfs[i]);
+                const std::array<double, 16> T = kfs[i]->getTransform();
+                check(ssm_keyframe_set_pose(ctx, id, T.data()));
+                ids.push_back(id);
+            }
+            check(ssm_map_redraw(ctx, ids.data(), (int)ids.size()));     // globalMap->clear(); += every listed keyframe
         } else {
-            for (size_t i = keyframe_size; i < kfs.size(); ++i) integrate(kfs[i]);
+            for (size_t i = keyframe_size; i < kfs.size(); ++i) {
+                const int id = cloudOf(kfs[i]);
+                const std::array<double, 16> T = kfs[i]->getTransform();
+                check(ssm_keyframe_set_pose(ctx, id, T.data()));
+                ids.push_back(id);
+            }
+            check(ssm_map_integrate_keyframes(ctx, ids.data(), (int)ids.size()));
         }
         cntGlobalUpdate++;
         keyframe_size = kfs.size();

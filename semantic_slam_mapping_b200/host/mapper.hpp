@@ -32,6 +32,7 @@ struct MapperConfig {
     int max_width = 1241, max_height = 376;
     uint64_t map_capacity = 1ull << 22;
     int redraw_every = 15;               // mapper.cpp:121
+    int redraw_stride = 1;               // keyframes taken on a full redraw: every one (the reference's loop takes every 2nd, mapper.cpp:126)
     std::string save_path;               // mapper.cpp:168 hard-codes a path; empty = do not save at shutdown
 };
 
@@ -68,7 +69,7 @@ public:
     ImageU8 moving_mask;
 
 protected:
-    void integrate(const Frame::Ptr& frame);
+    int cloudOf(const Frame::Ptr& frame);   // device-resident camera-space cloud of a keyframe (built on first use)
 
     std::shared_ptr<std::thread> viewerThread;
     MapperConfig config;

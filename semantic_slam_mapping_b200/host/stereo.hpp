@@ -27,6 +27,32 @@ void calDisparity_SGBM(const ImageU8& img_L, const ImageU8& img_R, ImageS16& dis
 // FrameReader::next glue (src/rgbdframe.cpp:85-116): disparity -> depth in camera.scale units
 void disparityToDepth(const ImageS16& disp, ImageU16& depth);
 
+// ---- dense motion cues: the tracker thread's consumers of the disparity map (src/track.cpp:67-79) ----------------
+// include/basicStructure.hpp:15-38
+struct ROI3D {
+    double x_max = 30000, y_max = -1000, z_max = 30000;
+    ROI3D() = default;
+    ROI3D(double x, double y, double z) : x_max(x), y_max(y), z_max(z) {}
+};
+using ImageXYZ10 = Image<float, 10>;   // CV_32FC(10): X, Y, Z, u, v, disparity, intensity, I_u, I_v, motion mark
+using ImageS32 = Image<int32_t, 1>;
+
+// include/stereo.h:25, :36, :43 -- same names, argument order and meaning
+void triangulate10D(const ImageU8& img, const ImageS16& disp, ImageXYZ10& xyz, const double f, const double cx, const double cy,
+                    const double b, ROI3D roi);
+void correct3DPoints(ImageXYZ10& xyz, ROI3D& roi_, const double& pitch1, const double& pitch2);
+void setImageROI(ImageXYZ10& xyz, ImageU8& roi_mask);
+
+// the two histogram members of UVDisparity (include/uvdisparity.hpp:88,91; src/uvdisparity.cpp:195-366) with the state
+// they leave behind (u_dis_int / u_dis_ / v_dis_int / v_dis_)
+class UVDisparity {
+public:
+    void calUDisparity(const ImageS16& img_dis, ImageXYZ10& xyz, ImageU8& roi_mask, ImageU8& ground_mask);
+    void calVDisparity(const ImageS16& img_dis, ImageXYZ10& xyz);
+    ImageS32 u_dis_int, v_dis_int;
+    ImageU8 u_dis_, v_dis_;
+};
+
 }  // namespace ssm_host
 
 #ifdef SSM_WITH_OPENCV

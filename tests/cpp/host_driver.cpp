@@ -80,6 +80,29 @@ int main(int argc, char** argv)
         fwrite(v.label.data(), 1, v.label.size(), fo);
         fwrite(&np, 8, 1, fo);
         for (const auto& p : *pc) { fwrite(&p.x, 4, 3, fo); fwrite(&p.rgba, 4, 1, fo); }
+        // the tracker thread's dense cues on keyframe 0, in the order of UVDisparity::Process (uvdisparity.cpp:842-903)
+        {
+            const Frame::Ptr& f0 = graph.keyframes[0];
+            ImageU8 grey(H, W), roi_mask, ground(H, W);
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x) { grey.ptr(y)[x] = f0->rgb.ptr(y)[3 * x]; ground.ptr(y)[x] = y >= H / 2 ? 255 : 0; }
+            ImageXYZ10 xyz;
+            ROI3D roi(15.0, 1.5, 35.0);
+            const Camera cam;
+            triangulate10D(grey, f0->disparity, xyz, cam.fx, cam.cx, cam.cy, cam.baseline, roi);   // track.cpp:67-71
+            UVDisparity uv;
+            uv.calVDisparity(f0->disparity, xyz);
+            const double pitch1 = 0.02, pitch2 = 0.0;
+            correct3DPoints(xyz, roi, pitch1, pitch2);
+            setImageROI(xyz, roi_mask);
+            uv.calUDisparity(f0->disparity, xyz, roi_mask, ground);
+            const int dims[2] = {uv.v_dis_int.cols, uv.u_dis_int.rows};
+            fwrite(dims, 4, 2, fo);
+            fwrite(xyz.data, 4, (size_t)H * W * 10, fo);
+            fwrite(roi_mask.data, 1, (size_t)H * W, fo);
+            fwrite(uv.v_dis_int.data, 4, (size_t)H * dims[0], fo);
+            fwrite(uv.u_dis_.data, 1, (size_t)dims[1] * W, fo);
+        }
         releaseStereoContext();
         // error behaviour: mismatched sizes throw, like the reference's cv::Exception
         bool threw = false;

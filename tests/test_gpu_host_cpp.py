@@ -68,5 +68,24 @@ def test_cpp_host_path_matches_oracle(tmp_path):
     assert npts == len(first_pc["xyz"])
     pts = take(np.uint32, npts * 4).reshape(npts, 4)
     assert (pts[:, :3] == first_pc["xyz"].view(np.uint32)).all() and (pts[:, 3] == first_pc["rgba"]).all()
+    # dense motion cues through the C++ mirrors (triangulate10D, UVDisparity::calVDisparity, correct3DPoints, setImageROI,
+    # UVDisparity::calUDisparity) on keyframe 0
+    v_cols, u_rows = [int(v) for v in take(np.int32, 2)]
+    got_xyz = take(np.float32, H * W * 10).reshape(H, W, 10)
+    got_roi = take(np.uint8, H * W).reshape(H, W)
+    got_vint = take(np.int32, H * v_cols).reshape(H, v_cols)
+    got_u8 = take(np.uint8, u_rows * W).reshape(u_rows, W)
+    disp0 = oracle.sgbm(seq["left"][0], seq["right"][0], oracle.SgbmParams(num_disparities=D))
+    grey = np.ascontiguousarray(seq["rgb"][0][..., 0])
+    ground = np.zeros((H, W), np.uint8)
+    ground[H // 2:] = 255
+    x = oracle.triangulate10d(grey, disp0, mp.fx, mp.cx, mp.cy, mp.baseline)
+    x, wvint, _ = oracle.v_disparity(disp0, x)
+    x = oracle.correct_3d_points(x, (15.0, 1.5, 35.0), 0.02, 0.0)
+    wroi = oracle.set_image_roi(x)
+    x, _, wu8 = oracle.u_disparity(disp0, x, wroi, ground)
+    assert wvint.shape == (H, v_cols) and wu8.shape == (u_rows, W)
+    assert (got_vint == wvint).all() and (got_u8 == wu8).all() and (got_roi == wroi).all()
+    assert np.array_equal(got_xyz.view(np.uint32), x.view(np.uint32))
     head = open(pcd, "rb").read(300).decode("ascii", "ignore")
     assert f"POINTS {nv}" in head

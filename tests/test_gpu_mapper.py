@@ -230,3 +230,36 @@ def test_keyframe_cache_redraw_after_pose_update():
         _compare_maps(ctx.map_export(), oracle_map(range(1, N), poses1))
         with pytest.raises(Exception):
             ctx.keyframe_set_pose(ids[0], poses1[0])         # released id
+
+
+def test_full_size_stress_properties_19_classes_2cm_voxels():
+    """BASELINE configs[3]/[4] flavour at full KITTI size: 19-class palette, 0.02 m voxels, a batch through the whole path.
+    Size-independent properties: every generated point lands in exactly one voxel (sum of counts == points), label votes
+    never exceed counts, re-fusing the same batch doubles every count and leaves voxel membership unchanged, and frame 0's
+    disparity equals the oracle's."""
+    from semantic_slam_mapping_b200.params import CITYSCAPES19_BGR
+    H, W, D, B, L = 376, 1241, 128, 6, 19
+    p = Params(num_disparities=D, max_width=W, max_height=H, max_batch=B, resolution=0.02, map_capacity=1 << 22,
+               palette_bgr=list(CITYSCAPES19_BGR), drop_mask=1 << 0, dynamic_mask=(1 << 11) | (1 << 12))
+    seq = synth.sequence(B, H, W, D, L, seed=23)             # 19-class masks rendered through the Cityscapes palette
+    mp = _mp(p)
+    with Context(p) as ctx:
+        nvox, disp = ctx.pipeline_batch_host(seq["left"], seq["right"], seq["semantic"], seq["rgb"], seq["pose"], want_disp=True)
+        m1 = ctx.map_export()
+        npts = 0
+        for i in range(B):
+            depth = ctx.disparity_to_depth(disp[i])
+            npts += len(ctx.generate_point_cloud(depth, seq["semantic"][i], seq["rgb"][i], seq["pose"][i])["xyz"])
+        assert nvox == len(m1["count"]) and nvox > 100000
+        assert int(m1["count"].sum()) == npts
+        assert (m1["votes"].sum(axis=1) <= m1["count"]).all() and int(m1["votes"].sum()) == npts   # every kept point has a palette label
+        assert (m1["label"] < L).all() and not (m1["votes"][:, 0] > 0).any()                      # class 0 is dropped from the cloud
+        ctx.pipeline_batch_host(seq["left"], seq["right"], seq["semantic"], seq["rgb"], seq["pose"])
+        m2 = ctx.map_export()
+        assert (m2["ijk"] == m1["ijk"]).all() and (m2["count"] == 2 * m1["count"]).all() and (m2["votes"] == 2 * m1["votes"]).all()
+        assert (m2["label"] == m1["label"]).all() and (m2["rgba"] == m1["rgba"]).all()
+        assert np.allclose(m2["xyz"], m1["xyz"], rtol=0, atol=1e-6)
+    want0 = oracle.sgbm(seq["left"][0], seq["right"][0], _op(p))
+    assert int((disp[0] != want0).sum()) == 0
+    pc0 = oracle.generate_point_cloud(oracle.disparity_to_depth(want0, mp), seq["semantic"][0], seq["rgb"][0], mp, seq["pose"][0])
+    assert len(pc0["xyz"]) > 50000
