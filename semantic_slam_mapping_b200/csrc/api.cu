@@ -135,13 +135,17 @@ static int run_sgbm(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, int
     return SSM_OK;
 }
 
-// the mapper half on device buffers
-static int run_map(ssm_ctx* c, int B, const int16_t* d_disp, const uint8_t* d_sem, const uint8_t* d_rgb,
-                   const double* d_pose, cudaStream_t s)
+// the mapper half on device buffers: per-frame preparation (depth image, label ids, moving mask) ...
+static int run_map_prepare(ssm_ctx* c, int B, const int16_t* d_disp, const uint8_t* d_sem, cudaStream_t s)
 {
     int rc;
     if ((rc = launch_depth(c, B, d_disp, c->d_depth, s))) return rc;
-    if ((rc = launch_labels_mask(c, B, d_sem, s))) return rc;
+    return launch_labels_mask(c, B, d_sem, s);
+}
+// ... and point generation + voxel fusion (the only part with shared state; across ranks: routing to the owner)
+static int run_map_points(ssm_ctx* c, int B, const uint8_t* d_sem, const uint8_t* d_rgb, const double* d_pose, cudaStream_t s)
+{
+    int rc;
     if (c->nranks > 1 && c->p2p) {
         mark(c, 6, s);   // points are made, fused or sent to their owner in one kernel; then barrier + inbox fusion
         if ((rc = points_route_p2p(c, B, c->d_depth, d_sem, d_rgb, d_pose, s))) return rc;
@@ -159,6 +163,13 @@ static int run_map(ssm_ctx* c, int B, const int16_t* d_disp, const uint8_t* d_se
         c->ev_set = (c->ev_set + 1) % ssm_ctx::kEvSets;
     }
     return SSM_OK;
+}
+static int run_map(ssm_ctx* c, int B, const int16_t* d_disp, const uint8_t* d_sem, const uint8_t* d_rgb,
+                   const double* d_pose, cudaStream_t s)
+{
+    int rc;
+    if ((rc = run_map_prepare(c, B, d_disp, d_sem, s))) return rc;
+    return run_map_points(c, B, d_sem, d_rgb, d_pose, s);
 }
 
 // Shift every per-frame work buffer of the context by `frames` frames (positive or negative): a sub-batch then runs
@@ -188,7 +199,7 @@ static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR,
     // different sub-batches are bound by different units (shared memory, issue slots, HBM) and fill each other's tails
     const int want = c->tune[3] >= 0 ? c->tune[3] : (B >= 96 ? 3 : (B >= 64 ? 2 : 1));
     const int nsplit = std::min({want, (int)ssm_ctx::kMaxSplit, B});
-    if (nsplit <= 1 || c->nranks > 1 || c->timing) {
+    if (nsplit <= 1 || c->timing) {
         if ((rc = run_sgbm(c, B, dL, dR, d_disp, s))) return rc;
         return run_map(c, B, d_disp, d_sem, d_rgb, d_pose, s);
     }
@@ -209,7 +220,11 @@ static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR,
         SSM_CUDA(cudaStreamWaitEvent(ss, c->sub_fork, 0));
         offset_buffers(c, first);
         rc = run_sgbm(c, n, dL + first * npix, dR + first * npix, d_disp + first * npix, ss);
-        if (rc == SSM_OK) rc = run_map(c, n, d_disp + first * npix, d_sem + first * npix * 3, d_rgb + first * npix * 3, d_pose + (size_t)first * 16, ss);
+        if (rc == SSM_OK) {
+            // one GPU: the sub-batch fuses its own points; several ranks: routing is one exchange per batch (below)
+            if (c->nranks > 1) rc = run_map_prepare(c, n, d_disp + first * npix, d_sem + first * npix * 3, ss);
+            else rc = run_map(c, n, d_disp + first * npix, d_sem + first * npix * 3, d_rgb + first * npix * 3, d_pose + (size_t)first * 16, ss);
+        }
         offset_buffers(c, -first);
         if (rc == SSM_OK) {
             SSM_CUDA(cudaEventRecord(c->sub_join[i], ss));
@@ -217,6 +232,7 @@ static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR,
         }
         first += n;
     }
+    if (rc == SSM_OK && c->nranks > 1) rc = run_map_points(c, B, d_sem, d_rgb, d_pose, s);
     return rc;
 }
 

@@ -103,7 +103,9 @@ def test_two_rank_gloo_routing_equals_single_map():
 
 
 # ---- GPU: NCCL all-to-all inside libssm.so --------------------------------------------------------------------
-def _nccl_worker(rank, world, port, q, p2p):
+def _nccl_worker(rank, world, port, q, p2p, split=0):
+    if split:
+        os.environ["SSM_TUNE3"] = str(split)     # sub-batch streams: SGBM per sub-batch, one routing exchange per batch
     import torch
     import torch.distributed as dist
     from semantic_slam_mapping_b200 import Context, Params
@@ -128,8 +130,8 @@ def _nccl_worker(rank, world, port, q, p2p):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("p2p", [True, False])
-def test_two_gpu_map_equals_oracle_map(p2p):
+@pytest.mark.parametrize("p2p,split", [(True, 0), (False, 0), (True, 2), (False, 3)])
+def test_two_gpu_map_equals_oracle_map(p2p, split):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
@@ -137,7 +139,7 @@ def test_two_gpu_map_equals_oracle_map(p2p):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q, p2p)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q, p2p, split)) for r in range(2)]
     for p in procs:
         p.start()
     merged = q.get(timeout=300)
