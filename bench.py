@@ -299,7 +299,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom)
+        tj = json.load(open(tpath))
+        if tj.get(dom) is not None:      # measured for launches of _frames_per_launch frames; a launch of the stage pass has B
+            traffic = round(tj[dom] * B / tj.get("_frames_per_launch", 33))
 
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
@@ -331,9 +333,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": f"stage '{dom}': {kernels[dom]}", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "frames_per_launch": B, "peak_source": peak_src,
                      "note": "achieved = SURVEY 8d algorithmic bytes of the stage x frames per launch / CUDA-event time of the stage; "
-                             "traffic = ncu dram bytes per launch of the stage's kernels (profiles/dominant_kernel_traffic.json)",
+                             "traffic = ncu dram bytes of the stage's kernels (profiles/dominant_kernel_traffic.json), scaled to the same frames per launch",
                      "whole_path": {"alg_bytes_per_frame": ab["total"], "achieved": ab["total"] * total_frames / world / (dev_ms * 1e-3) / 1e9,
                                     "frac": ab["total"] * total_frames / world / (dev_ms * 1e-3) / 1e9 / peak},
                      "stages": stage_roof},

@@ -31,6 +31,7 @@ def main():
         out[STAGE_OF[k]] = out.get(STAGE_OF[k], 0.0) + b
     out = {k: round(v) for k, v in out.items()}
     out["_source"] = f"{rep}: dram__bytes_read.sum + dram__bytes_write.sum per launch, B = 33 frames per launch"
+    out["_frames_per_launch"] = 33
     out["_kernels"] = {k: round(v) for k, v in per_kernel.items()}
     json.dump(out, open("profiles/dominant_kernel_traffic.json", "w"), indent=1)
     print(json.dumps(out, indent=1))
