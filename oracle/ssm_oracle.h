@@ -16,10 +16,18 @@
  *   - src/mapper.cpp:96-178       Mapper::viewer -> pcl::VoxelGrid fusion (PCL 1.7, un-vendored;
  *                                 semantics restated from SURVEY.md App. B)
  *
- * Parity pinning: the SGBM chain is pinned against cv2 4.13 (tests/test_oracle_vs_cv2.py and
- * the committed vectors in tests/golden/).  The reference itself ships no tests or golden
- * vectors for this path and PCL cannot be executed here, so the voxel-fusion part is
- * "parity unpinned" beyond its written definition.
+ *   - src/stereo.cpp:41-192      triangulate10D, correct3DPoints, setImageROI
+ *   - src/uvdisparity.cpp:195-366 UVDisparity::calUDisparity / calVDisparity
+ *   (label production, experiment/segnet.cpp:121-135, is restated in numpy in oracle/__init__.py)
+ *
+ * Parity pinning: the SGBM chain is pinned against cv2 4.13 (tests/test_oracle_golden.py and
+ * the committed vectors in tests/golden/); triangulate10D / correct3DPoints / setImageROI and
+ * calDisparity_SGBM's parameter block against the reference's OWN src/stereo.cpp, compiled by
+ * oracle/Makefile against oracle/cvstub into oracle/_ref/libref_stereo.so
+ * (tests/test_oracle_cues.py, tests/golden/cues_ref.npz); cv::resize + cv::LUT against cv2 4.13.
+ * The reference itself ships no tests or golden vectors for this path; PCL and
+ * src/uvdisparity.cpp cannot be compiled or executed here, so the voxel-fusion part and the
+ * U/V-disparity histograms are "parity unpinned" beyond their written definition.
  */
 #ifndef SSM_ORACLE_H
 #define SSM_ORACLE_H
