@@ -86,7 +86,7 @@ static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<
 static void free_all(ssm_ctx* c)
 {
     void* ptrs[] = {c->d_left, c->d_right, c->d_recL, c->d_recR, c->d_C, c->d_S, c->d_disp_raw, c->d_disp_lr, c->d_disp_med,
-                    c->d_disp, c->d_disp2key, c->d_wta_rec, c->d_ck, c->d_uniq_thr, c->d_cc_label, c->d_cc_size, c->d_depth, c->d_label, c->d_mask, c->d_sem,
+                    c->d_disp, c->d_disp2key, c->d_wta_rec, c->d_ck, c->d_uniq_thr, c->d_cc_label, c->d_cc_size, c->d_depth, c->d_label, c->d_mask, c->d_label_lut, c->d_sem,
                     c->d_rgb, c->d_pose, c->d_min_disp, c->d_points, c->d_blk_count, c->d_counters, c->d_table, c->d_send,
                     c->d_recv, c->d_send_counts};
     for (void* q : ptrs)
@@ -366,7 +366,7 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
     A(dalloc(&c->d_disp2key, npix)); A(dalloc(&c->d_wta_rec, npix * 2));
     if (p->num_disparities <= 128)
         A(dalloc(&c->d_ck, hsweep2_ck_words(c->cap_w - p->num_disparities, p->num_disparities, c->cap_h, c->cap_b))); A(dalloc(&c->d_uniq_thr, (size_t)32768)); A(dalloc(&c->d_cc_label, npix)); A(dalloc(&c->d_cc_size, npix));
-    A(dalloc(&c->d_depth, npix)); A(dalloc(&c->d_label, npix)); A(dalloc(&c->d_mask, npix));
+    A(dalloc(&c->d_depth, npix)); A(dalloc(&c->d_label, npix)); A(dalloc(&c->d_mask, npix)); A(dalloc(&c->d_label_lut, (size_t)1 << 24));
     A(dalloc(&c->d_sem, npix * 3)); A(dalloc(&c->d_rgb, npix * 3));
     A(dalloc(&c->d_pose, (size_t)16 * c->cap_b)); A(dalloc(&c->d_min_disp, (size_t)c->cap_b));
     A(dalloc(&c->d_points, npix)); A(dalloc(&c->d_blk_count, npix / 1024 + 2)); A(dalloc(&c->d_counters, 8));
@@ -388,6 +388,19 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
             free_all(c);
             delete c;
             return cuda_fail(cudaGetLastError(), "uniqueness table upload");
+        }
+    }
+    {   // colour -> class table: 255 everywhere, then the palette entries (highest id first, so the lowest id wins a duplicate colour)
+        cudaError_t le = cudaMemset(c->d_label_lut, SSM_LABEL_UNKNOWN, (size_t)1 << 24);
+        for (int i = p->num_labels - 1; i >= 0 && le == cudaSuccess; --i) {
+            const uint8_t id = (uint8_t)i;
+            const size_t key = (size_t)p->palette_bgr[i][0] | ((size_t)p->palette_bgr[i][1] << 8) | ((size_t)p->palette_bgr[i][2] << 16);
+            le = cudaMemcpy(c->d_label_lut + key, &id, 1, cudaMemcpyHostToDevice);
+        }
+        if (le != cudaSuccess) {
+            free_all(c);
+            delete c;
+            return cuda_fail(le, "label table upload");
         }
     }
     rc = launch_map_clear(c, c->stream);

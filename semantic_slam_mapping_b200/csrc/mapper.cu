@@ -26,34 +26,70 @@ __global__ void __launch_bounds__(256) k_min_disp(const int16_t* __restrict__ di
 {
     const int b = blockIdx.y;
     if (b >= B) return;
+    const int16_t* d = disp + (size_t)b * per_frame;
     int m = 32767;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_frame; i += (size_t)gridDim.x * blockDim.x)
-        m = min(m, (int)disp[(size_t)b * per_frame + i]);
+    // 8 values per 16-byte load where the frame is aligned; scalar otherwise / for the tail
+    const size_t nvec = (reinterpret_cast<uintptr_t>(d) & 15) == 0 ? per_frame / 8 : 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = reinterpret_cast<const uint4*>(d)[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m = min(m, min((int)(int16_t)(w[k] & 0xffffu), (int)(int16_t)(w[k] >> 16)));
+    }
+    for (size_t i = nvec * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_frame; i += (size_t)gridDim.x * blockDim.x)
+        m = min(m, (int)d[i]);
     m = __reduce_min_sync(0xffffffffu, m);
     if ((threadIdx.x & 31) == 0) atomicMin(&min_disp[b], m);
 }
 
-// rgbdframe.cpp:97-116
-__global__ void __launch_bounds__(256) k_depth(const int16_t* __restrict__ disp, const int* __restrict__ min_disp,
-                                               uint16_t* __restrict__ depth, size_t total, SSM_DP)
+// rgbdframe.cpp:97-116.  One thread makes 4 consecutive pixels of the flat [B][H][W] array (8-byte load / store when the
+// buffers are aligned).
+__device__ __forceinline__ uint16_t depth_of(const DevParams& p, int d, int dmin, int u, int v)
 {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int u = (int)(idx % p.W);
-    const size_t r = idx / p.W;
-    const int v = (int)(r % p.H);
-    const int b = (int)(r / p.H);
-    const int d = disp[idx];
-    uint16_t out = 0;
-    if (d != 0 && d != min_disp[b]) {
-        const double pw = __ddiv_rn(p.baseline, (double)d);
-        const double px = __dmul_rn(__dmul_rn(__dsub_rn((double)u, p.cx), pw), 16.0);
-        const double py = __dmul_rn(__dmul_rn(__dsub_rn((double)v, p.cy), pw), 16.0);
-        const double pz = __dmul_rn(__dmul_rn(p.fx, pw), 16.0);
-        if (fabs(px) < p.roix && fabs(py) < p.roiy && fabs(pz) < p.roiz && pz > 0)
-            out = (uint16_t)(int)__dmul_rn(pz, p.scale);   // truncation, pz*scale < 65536 because roiz*scale is checked at create
+    if (d == 0 || d == dmin) return 0;
+    const double pw = __ddiv_rn(p.baseline, (double)d);
+    const double px = __dmul_rn(__dmul_rn(__dsub_rn((double)u, p.cx), pw), 16.0);
+    const double py = __dmul_rn(__dmul_rn(__dsub_rn((double)v, p.cy), pw), 16.0);
+    const double pz = __dmul_rn(__dmul_rn(p.fx, pw), 16.0);
+    if (fabs(px) < p.roix && fabs(py) < p.roiy && fabs(pz) < p.roiz && pz > 0)
+        return (uint16_t)(int)__dmul_rn(pz, p.scale);   // truncation, pz*scale < 65536 because roiz*scale is checked at create
+    return 0;
+}
+__global__ void __launch_bounds__(256) k_depth(const int16_t* __restrict__ disp, const int* __restrict__ min_disp,
+                                               uint16_t* __restrict__ depth, size_t total, int aligned8, SSM_DP)
+{
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= total) return;
+    int u = (int)(i0 % p.W);
+    const size_t r = i0 / p.W;
+    int v = (int)(r % p.H);
+    int b = (int)(r / p.H);
+    int d[4];
+    const bool full = i0 + 4 <= total;
+    if (full && aligned8) {
+        const uint2 q = *reinterpret_cast<const uint2*>(disp + i0);
+        d[0] = (int16_t)(q.x & 0xffffu); d[1] = (int16_t)(q.x >> 16); d[2] = (int16_t)(q.y & 0xffffu); d[3] = (int16_t)(q.y >> 16);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[k] = i0 + k < total ? disp[i0 + k] : 0;
     }
-    depth[idx] = out;
+    uint32_t o[4];
+    int dmin = min_disp[b];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        o[k] = depth_of(p, d[k], dmin, u, v);
+        if (++u == p.W) {
+            u = 0;
+            if (++v == p.H) { v = 0; ++b; if (i0 + k + 1 < total) dmin = min_disp[b]; }
+        }
+    }
+    if (full && aligned8) {
+        *reinterpret_cast<uint2*>(depth + i0) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k < total) depth[i0 + k] = (uint16_t)o[k];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -68,43 +104,120 @@ __device__ __forceinline__ int label_of(const DevParams& p, uint32_t bgr)
     return l;
 }
 
-__global__ void __launch_bounds__(256) k_labels(const uint8_t* __restrict__ sem, uint8_t* __restrict__ label, size_t total, SSM_DP)
+// One thread labels 4 consecutive pixels of the flat [B][H][W] array (three 4-byte loads, one 4-byte store when the
+// buffers are aligned) and records the "dynamic class" predicate as one bit per pixel in `dynbits`
+// ([B][H][ceil(W/32)] words, zeroed beforehand; bit i of word wx <-> pixel x = 32 * wx + i).
+__global__ void __launch_bounds__(256) k_labels(const uint8_t* __restrict__ sem, uint8_t* __restrict__ label, uint32_t* __restrict__ dynbits,
+                                                const uint8_t* __restrict__ lut, size_t total, int aligned4, SSM_DP)
 {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const uint8_t* s = sem + idx * 3;
-    label[idx] = (uint8_t)label_of(p, (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16));
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= total) return;
+    const bool full = i0 + 4 <= total;
+    uint32_t bgr[4];
+    if (full && aligned4) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(sem + i0 * 3);
+        const uint32_t a = q[0], b = q[1], c = q[2];
+        bgr[0] = a & 0xffffffu; bgr[1] = (a >> 24) | ((b & 0xffffu) << 8); bgr[2] = (b >> 16) | ((c & 0xffu) << 16); bgr[3] = c >> 8;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint8_t* t = sem + (i0 + k) * 3;
+            bgr[k] = i0 + k < total ? ((uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16)) : 0xffffffffu;
+        }
+    }
+    uint32_t l[4], dyn = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // 2^24-entry colour -> class table (only num_labels of its lines are ever touched: cache resident)
+        l[k] = lut ? (bgr[k] <= 0xffffffu ? (uint32_t)lut[bgr[k]] : (uint32_t)SSM_LABEL_UNKNOWN) : (uint32_t)label_of(p, bgr[k]);
+        if (l[k] != SSM_LABEL_UNKNOWN && ((p.dynamic_mask >> l[k]) & 1u) && i0 + k < total) dyn |= 1u << k;
+    }
+    if (full && aligned4) {
+        *reinterpret_cast<uint32_t*>(label + i0) = l[0] | (l[1] << 8) | (l[2] << 16) | (l[3] << 24);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k < total) label[i0 + k] = (uint8_t)l[k];
+    }
+    if (dyn) {
+        // the 4 pixels usually share one word: one atomic for the run, a second only where the run crosses a word / row end
+        const int wpr = (p.W + 31) >> 5;
+        size_t cur = (size_t)-1;
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((dyn >> k) & 1u) {
+                const size_t idx = i0 + k;
+                const int x = (int)(idx % p.W);
+                const size_t row = idx / p.W;              // b * H + y
+                const size_t word = row * wpr + (x >> 5);
+                if (word != cur) {
+                    if (bits) atomicOr(&dynbits[cur], bits);
+                    cur = word; bits = 0u;
+                }
+                bits |= 1u << (x & 31);
+            }
+        if (bits) atomicOr(&dynbits[cur], bits);
+    }
 }
 
-// cv::dilate(img, img, ones(3,3), anchor centre, iterations) == (2*it+1)^2 max filter, out-of-image ignored.
-// One warp covers 32 - 2R consecutive pixels of a row plus R halo pixels per side: each of the 2R+1 rows in reach
-// costs one label load per lane; the "dynamic class" predicate becomes one ballot word per row, the horizontal
-// dilation is 2R shifts of that word, the vertical one an OR over the rows.
-__global__ void __launch_bounds__(256) k_moving_mask(const uint8_t* __restrict__ label, uint8_t* __restrict__ mask, int segs_per_row,
-                                                     size_t total_segs, SSM_DP)
+// cv::dilate(img, img, ones(3,3), anchor centre, iterations) == (2*it+1)^2 max filter, out-of-image ignored, on the
+// bit image, separably: k_dilate_rows ORs the 2R+1 rows in reach (one thread per word), then every output word is 2R
+// shifts of that row-dilated word with carry from its two neighbour words.
+__global__ void __launch_bounds__(256) k_dilate_rows(const uint32_t* __restrict__ dynbits, uint32_t* __restrict__ vbits, int wpr, int H, int R,
+                                                     size_t nwords)
 {
-    const int lane = threadIdx.x & 31;
-    const size_t seg = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (seg >= total_segs) return;
-    const int R = p.dilate_radius;
-    const int span = 32 - 2 * R;
-    const size_t row = seg / segs_per_row;
-    const int y = (int)(row % p.H);
-    const int x = (int)(seg % segs_per_row) * span - R + lane;      // lanes [R, 32 - R) own an output pixel
-    const uint8_t* img = label + (row / p.H) * (size_t)p.W * p.H;
-    uint32_t acc = 0u;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    const int wx = (int)(i % wpr);
+    const size_t row = i / wpr;
+    const int y = (int)(row % H);
+    uint32_t c = 0u;
     for (int dy = -R; dy <= R; ++dy) {
         const int yy = y + dy;
-        bool dyn = false;
-        if (yy >= 0 && yy < p.H && x >= 0 && x < p.W) {
-            const int l = img[(size_t)yy * p.W + x];
-            dyn = (l != SSM_LABEL_UNKNOWN) && ((p.dynamic_mask >> l) & 1u);
-        }
-        acc |= __ballot_sync(0xffffffffu, dyn);
+        if (yy >= 0 && yy < H) c |= dynbits[(row - y + yy) * wpr + wx];
     }
-    uint32_t dil = acc;
-    for (int k = 1; k <= R; ++k) dil |= (acc << k) | (acc >> k);
-    if (lane >= R && lane < 32 - R && x < p.W) mask[row * p.W + x] = ((dil >> lane) & 1u) ? 255 : 0;
+    vbits[i] = c;
+}
+__device__ __forceinline__ uint32_t dilated_word(const uint32_t* __restrict__ vbits, int wpr, size_t row, int wx, int R)
+{
+    const uint32_t* w = vbits + row * wpr + wx;
+    const uint32_t c = w[0], l = wx > 0 ? w[-1] : 0u, r = wx + 1 < wpr ? w[1] : 0u;
+    uint32_t dil = c;
+    for (int k = 1; k <= R; ++k) dil |= (c << k) | (l >> (32 - k)) | (c >> k) | (r << (32 - k));
+    return dil;
+}
+// one thread writes 4 consecutive mask bytes of the flat array
+__global__ void __launch_bounds__(256) k_moving_mask(const uint32_t* __restrict__ dynbits, uint8_t* __restrict__ mask, size_t total,
+                                                     int aligned4, SSM_DP)
+{
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= total) return;
+    const int wpr = (p.W + 31) >> 5;
+    const int R = p.dilate_radius;
+    uint32_t out = 0u;
+    int cur_wx = -1;
+    size_t cur_row = (size_t)-1;
+    uint32_t dil = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const size_t idx = i0 + k;
+        if (idx >= total) break;
+        const int x = (int)(idx % p.W);
+        const size_t row = idx / p.W;
+        if (row != cur_row || (x >> 5) != cur_wx) {
+            cur_row = row; cur_wx = x >> 5;
+            dil = dilated_word(dynbits, wpr, row, cur_wx, R);
+        }
+        if ((dil >> (x & 31)) & 1u) out |= 0xffu << (8 * k);
+    }
+    if (i0 + 4 <= total && aligned4) {
+        *reinterpret_cast<uint32_t*>(mask + i0) = out;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k < total) mask[i0 + k] = (uint8_t)(out >> (8 * k));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -173,10 +286,10 @@ __device__ __forceinline__ void fuse_point(const DevParams& p, Voxel* __restrict
             atomicAdd(&v->sx, (unsigned long long)__double2ll_rn(__dmul_rn((double)pt.x, kFixScale)));
             atomicAdd(&v->sy, (unsigned long long)__double2ll_rn(__dmul_rn((double)pt.y, kFixScale)));
             atomicAdd(&v->sz, (unsigned long long)__double2ll_rn(__dmul_rn((double)pt.z, kFixScale)));
-            atomicAdd(&v->n, 1u);
-            atomicAdd(&v->sr, (pt.rgba >> 16) & 255u);
-            atomicAdd(&v->sg, (pt.rgba >> 8) & 255u);
-            atomicAdd(&v->sb, pt.rgba & 255u);
+            // (n, sr) and (sg, sb) are adjacent 32-bit fields on 8-byte boundaries: one 64-bit add each (no field can carry
+            // into its neighbour before 2^32 points / 2^24 points of full intensity)
+            atomicAdd(reinterpret_cast<unsigned long long*>(&v->n), 1ull | ((unsigned long long)((pt.rgba >> 16) & 255u) << 32));
+            atomicAdd(reinterpret_cast<unsigned long long*>(&v->sg), (unsigned long long)((pt.rgba >> 8) & 255u) | ((unsigned long long)(pt.rgba & 255u) << 32));
             if (pt.label < (uint32_t)p.num_labels) atomicAdd(&v->votes[pt.label], 1u);
             return;
         }
@@ -192,12 +305,12 @@ __global__ void __launch_bounds__(256) k_points_fuse(const uint16_t* __restrict_
                                                      size_t total, SSM_DP)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
     Point pt;
-    if (make_point(p, idx, depth, label, mask, sem, rgb, pose, pt)) {
-        fuse_point(p, table, slot_mask, pt, counters);
-        atomicAdd(&counters[0], 1u);
-    }
+    const bool ok = idx < total && make_point(p, idx, depth, label, mask, sem, rgb, pose, pt);
+    if (ok) fuse_point(p, table, slot_mask, pt, counters);
+    // points of this call: one atomic per warp instead of one per point
+    const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&counters[0], (uint32_t)__popc(ballot));
 }
 
 // P2P mode (multi-GPU): straight from pixels; locally owned points go into this rank's hash, the others are appended
@@ -385,7 +498,8 @@ int launch_depth(ssm_ctx* c, int B, const int16_t* d_disp, uint16_t* d_depth, cu
     SSM_CUDA(cudaMemsetAsync(c->d_min_disp, 0x7f, sizeof(int) * B, s));
     k_min_disp<<<dim3(64, B), 256, 0, s>>>(d_disp, c->d_min_disp, per_frame, B);
     SSM_LAUNCH_CHECK(c);
-    k_depth<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_disp, c->d_min_disp, d_depth, total, p);
+    const int aligned8 = ((reinterpret_cast<uintptr_t>(d_disp) | reinterpret_cast<uintptr_t>(d_depth)) & 7) == 0;
+    k_depth<<<(unsigned)((total / 4 + 256) / 256), 256, 0, s>>>(d_disp, c->d_min_disp, d_depth, total, aligned8, p);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }
@@ -394,13 +508,21 @@ int launch_labels_mask(ssm_ctx* c, int B, const uint8_t* d_sem, cudaStream_t s)
 {
     const DevParams& p = c->dp;
     const size_t total = (size_t)p.W * p.H * B;
-    const unsigned grid = (unsigned)((total + 255) / 256);
-    k_labels<<<grid, 256, 0, s>>>(d_sem, c->d_label, total, p);
+    const unsigned grid = (unsigned)((total / 4 + 256) / 256);
+    // the speckle filter's size array is free once the post stage is done: it holds the one-bit-per-pixel predicate and
+    // its row-dilated copy
+    const int wpr = (p.W + 31) >> 5;
+    const size_t nwords = (size_t)wpr * p.H * B;
+    uint32_t* dynbits = reinterpret_cast<uint32_t*>(c->d_cc_size);
+    uint32_t* vbits = dynbits + nwords;
+    SSM_CUDA(cudaMemsetAsync(dynbits, 0, nwords * sizeof(uint32_t), s));
+    const int a_sem = ((reinterpret_cast<uintptr_t>(d_sem) | reinterpret_cast<uintptr_t>(c->d_label)) & 3) == 0;
+    k_labels<<<grid, 256, 0, s>>>(d_sem, c->d_label, dynbits, c->d_label_lut, total, a_sem, p);
     SSM_LAUNCH_CHECK(c);
-    const int span = 32 - 2 * p.dilate_radius;   // dilate_iterations <= 8 keeps this positive
-    const int segs_per_row = (p.W + span - 1) / span;
-    const size_t total_segs = (size_t)segs_per_row * p.H * B;
-    k_moving_mask<<<(unsigned)((total_segs + 7) / 8), 256, 0, s>>>(c->d_label, c->d_mask, segs_per_row, total_segs, p);
+    k_dilate_rows<<<(unsigned)((nwords + 255) / 256), 256, 0, s>>>(dynbits, vbits, wpr, p.H, p.dilate_radius, nwords);
+    SSM_LAUNCH_CHECK(c);
+    const int a_mask = (reinterpret_cast<uintptr_t>(c->d_mask) & 3) == 0;
+    k_moving_mask<<<grid, 256, 0, s>>>(vbits, c->d_mask, total, a_mask, p);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }

@@ -139,6 +139,7 @@ struct ssm_ctx {
     // mapper
     uint16_t* d_depth = nullptr;                     // [B][H][W]
     uint8_t *d_label = nullptr, *d_mask = nullptr;   // [B][H][W]
+    uint8_t* d_label_lut = nullptr;                  // [2^24] semantic colour (B | G << 8 | R << 16) -> class id, 255 = not in the palette
     uint8_t *d_sem = nullptr, *d_rgb = nullptr;      // [B][H][W][3] staging
     double* d_pose = nullptr;                        // [B][16]
     int32_t* d_min_disp = nullptr;                   // [B]
