@@ -239,6 +239,11 @@ int ssm_comm_init(ssm_ctx* ctx, const uint8_t id[SSM_UNIQUE_ID_BYTES], int rank,
 int ssm_comm_ipc_export(ssm_ctx* ctx, uint8_t handle[SSM_IPC_HANDLE_BYTES]);
 int ssm_comm_ipc_connect(ssm_ctx* ctx, const uint8_t* handles, int nranks);
 int ssm_comm_destroy(ssm_ctx* ctx);
+/* Streaming option for batched calls with a communicator (default off): the per-batch exchange (points to their owning
+ * rank, barrier, inbox fusion) runs on an internal stream, so a pipeline call's stream only covers the stereo half and the
+ * next batch's SGBM overlaps this batch's exchange.  The batch is in the map after ssm_synchronize (or any ssm_map_*
+ * call, which wait for it).  Every rank must use the same setting. */
+int ssm_set_route_overlap(ssm_ctx* ctx, int enabled);
 /* owner rank of a voxel (pure function of ijk, brick shift and nranks; exposed for host-side tests) */
 int ssm_voxel_owner(int32_t i, int32_t j, int32_t k, int nranks);
 

@@ -106,6 +106,8 @@ static void free_all(ssm_ctx* c)
         if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
         if (c->ev_consumed[k]) cudaEventDestroy(c->ev_consumed[k]);
     }
+    if (c->route_stream) cudaStreamDestroy(c->route_stream);
+    if (c->ev_route_done) cudaEventDestroy(c->ev_route_done);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
@@ -200,6 +202,10 @@ static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR,
     const int want = c->tune[3] >= 0 ? c->tune[3] : (B >= 96 ? 3 : (B >= 64 ? 2 : 1));
     const int nsplit = std::min({want, (int)ssm_ctx::kMaxSplit, B});
     if (nsplit <= 1 || c->timing) {
+        if (c->route_pending) {   // an overlapped exchange is still in flight: order this call after it
+            SSM_CUDA(cudaStreamWaitEvent(s, c->ev_route_done, 0));
+            c->route_pending = false;
+        }
         if ((rc = run_sgbm(c, B, dL, dR, d_disp, s))) return rc;
         return run_map(c, B, d_disp, d_sem, d_rgb, d_pose, s);
     }
@@ -210,6 +216,19 @@ static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR,
             SSM_CUDA(cudaStreamCreateWithFlags(&c->sub_stream[i], cudaStreamNonBlocking));
             SSM_CUDA(cudaEventCreateWithFlags(&c->sub_join[i], cudaEventDisableTiming));
         }
+    }
+    const bool overlap = c->route_overlap && c->nranks > 1;
+    if (overlap && !c->route_stream) {
+        // highest priority: the exchange's small kernels (and the NCCL barrier) take the first free SM slots instead of
+        // queueing behind a full wave of SGBM blocks, so the ranks meet at the barrier early
+        int prio_lo = 0, prio_hi = 0;
+        SSM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        SSM_CUDA(cudaStreamCreateWithPriority(&c->route_stream, cudaStreamNonBlocking, prio_hi));
+        SSM_CUDA(cudaEventCreateWithFlags(&c->ev_route_done, cudaEventDisableTiming));
+    }
+    if (!overlap && c->route_pending) {   // an overlapped exchange is still in flight: order this call after it
+        SSM_CUDA(cudaStreamWaitEvent(s, c->ev_route_done, 0));
+        c->route_pending = false;
     }
     SSM_CUDA(cudaEventRecord(c->sub_fork, s));
     int first = 0;
@@ -222,17 +241,32 @@ static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR,
         rc = run_sgbm(c, n, dL + first * npix, dR + first * npix, d_disp + first * npix, ss);
         if (rc == SSM_OK) {
             // one GPU: the sub-batch fuses its own points; several ranks: routing is one exchange per batch (below)
-            if (c->nranks > 1) rc = run_map_prepare(c, n, d_disp + first * npix, d_sem + first * npix * 3, ss);
+            if (c->nranks > 1) {
+                // the previous batch's exchange may still be reading the depth / label / mask buffers
+                if (c->route_pending) SSM_CUDA(cudaStreamWaitEvent(ss, c->ev_route_done, 0));
+                rc = run_map_prepare(c, n, d_disp + first * npix, d_sem + first * npix * 3, ss);
+            }
             else rc = run_map(c, n, d_disp + first * npix, d_sem + first * npix * 3, d_rgb + first * npix * 3, d_pose + (size_t)first * 16, ss);
         }
         offset_buffers(c, -first);
         if (rc == SSM_OK) {
             SSM_CUDA(cudaEventRecord(c->sub_join[i], ss));
             SSM_CUDA(cudaStreamWaitEvent(s, c->sub_join[i], 0));
+            if (overlap) SSM_CUDA(cudaStreamWaitEvent(c->route_stream, c->sub_join[i], 0));
         }
         first += n;
     }
-    if (rc == SSM_OK && c->nranks > 1) rc = run_map_points(c, B, d_sem, d_rgb, d_pose, s);
+    if (rc == SSM_OK && c->nranks > 1) {
+        // The exchange (points to their owners, barrier, inbox fusion) is one step per batch.  With route overlap it runs
+        // on its own stream: `s` only covers the stereo half, so the next batch's SGBM starts while this batch's points
+        // travel and the ranks' skew at the barrier is absorbed; ssm_synchronize / ssm_map_* wait for it.
+        cudaStream_t rs = overlap ? c->route_stream : s;
+        rc = run_map_points(c, B, d_sem, d_rgb, d_pose, rs);
+        if (rc == SSM_OK && overlap) {
+            SSM_CUDA(cudaEventRecord(c->ev_route_done, rs));
+            c->route_pending = true;
+        }
+    }
     return rc;
 }
 
@@ -254,8 +288,19 @@ static int finish_timing(ssm_ctx* c)
     return SSM_OK;
 }
 
+static int sync_route(ssm_ctx* c)
+{
+    if (c->route_stream && c->route_pending) {
+        SSM_CUDA(cudaStreamSynchronize(c->route_stream));
+        c->route_pending = false;
+    }
+    return SSM_OK;
+}
+
 static int check_overflow(ssm_ctx* c, cudaStream_t s, uint64_t* n_voxels)
 {
+    int rr = sync_route(c);
+    if (rr) return rr;
     uint32_t h[4];
     SSM_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
     SSM_CUDA(cudaStreamSynchronize(s));
@@ -448,6 +493,15 @@ int ssm_synchronize(ssm_ctx* c)
 {
     if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
     SSM_CUDA(cudaStreamSynchronize(c->stream));
+    return sync_route(c);
+}
+
+int ssm_set_route_overlap(ssm_ctx* c, int enabled)
+{
+    if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
+    int rc = sync_route(c);
+    if (rc) return rc;
+    c->route_overlap = enabled != 0;
     return SSM_OK;
 }
 
@@ -731,7 +785,9 @@ int ssm_map_integrate_points(ssm_ctx* c, const float* xyz, const uint32_t* rgba,
 int ssm_map_clear(ssm_ctx* c)
 {
     if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
-    int rc = launch_map_clear(c, c->stream);
+    int rc = sync_route(c);
+    if (rc) return rc;
+    rc = launch_map_clear(c, c->stream);
     if (rc) return rc;
     SSM_CUDA(cudaStreamSynchronize(c->stream));
     return SSM_OK;
@@ -884,8 +940,10 @@ int ssm_pipeline_batch_host_async(ssm_ctx* c, int batch, const uint8_t* left, co
     SSM_CUDA(cudaStreamWaitEvent(s, c->ev_copied[k], 0));
     if ((rc = run_pipeline(c, batch, c->stage_left[k], c->stage_right[k], c->stage_sem[k], c->stage_rgb[k], c->stage_pose[k], c->d_disp, s)))
         return rc;
-    SSM_CUDA(cudaEventRecord(c->ev_consumed[k], s));
-    if (n_voxels_pinned) SSM_CUDA(cudaMemcpyAsync(n_voxels_pinned, c->d_counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    // with route overlap the exchange of this batch runs on the route stream and reads the staged semantic / rgb / poses
+    cudaStream_t done = (c->route_pending && c->route_stream) ? c->route_stream : s;
+    SSM_CUDA(cudaEventRecord(c->ev_consumed[k], done));
+    if (n_voxels_pinned) SSM_CUDA(cudaMemcpyAsync(n_voxels_pinned, c->d_counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, done));
     return SSM_OK;
 }
 

@@ -164,6 +164,10 @@ struct ssm_ctx {
     size_t inbox_cap = 0;                            // points per parity buffer
     bool p2p = false;
     uint64_t p2p_step = 0;                           // parity source
+    // route overlap (ssm_set_route_overlap): the per-batch exchange runs on its own stream behind the next batch's SGBM
+    cudaStream_t route_stream = nullptr;
+    cudaEvent_t ev_route_done = nullptr;
+    bool route_overlap = false, route_pending = false;
     void* keyframes = nullptr;                       // cached camera-space keyframe clouds (api.cu: ssm_keyframe_*)
     void* labels_ws = nullptr;                       // label production workspace (labels.cu)
     void* cues_ws = nullptr;                         // dense motion cues workspace (cues.cu), allocated on first use

@@ -23,7 +23,7 @@ SYMBOLS = [
     "ssm_pipeline_batch_device", "ssm_pipeline_batch_host", "ssm_pipeline_batch_host_async", "ssm_synchronize", "ssm_comm_get_unique_id",
     "ssm_comm_init", "ssm_comm_ipc_export", "ssm_comm_ipc_connect", "ssm_comm_destroy", "ssm_voxel_owner",
     "ssm_triangulate10d", "ssm_correct_3d_points", "ssm_set_image_roi", "ssm_v_disparity", "ssm_u_disparity",
-    "ssm_keyframe_add", "ssm_keyframe_set_pose", "ssm_keyframe_release", "ssm_keyframe_count", "ssm_map_redraw",
+    "ssm_set_route_overlap", "ssm_keyframe_add", "ssm_keyframe_set_pose", "ssm_keyframe_release", "ssm_keyframe_count", "ssm_map_redraw",
     "ssm_map_integrate_keyframes",
     "ssm_labels_from_indices", "ssm_labels_from_indices_batch_device",
     "ssm_motion_cues_stage1_device", "ssm_motion_cues_stage2_device", "ssm_motion_cues_overflow",
@@ -89,6 +89,7 @@ def load() -> C.CDLL:
     d = C.c_double
     L.ssm_labels_from_indices.argtypes = [vp, vp, sz, i, i, i, i, vp, vp, sz, vp, sz]
     L.ssm_labels_from_indices_batch_device.argtypes = [vp, i, vp, i, i, i, i, vp, vp, vp, vp]
+    L.ssm_set_route_overlap.argtypes = [vp, i]
     L.ssm_keyframe_add.argtypes = [vp, vp, vp, vp, i, i, vp, C.POINTER(i)]
     L.ssm_keyframe_set_pose.argtypes = [vp, i, vp]
     L.ssm_keyframe_release.argtypes = [vp, i]
@@ -376,6 +377,9 @@ class Context:
     def pipeline_batch_device(self, d_left, d_right, d_sem, d_rgb, d_poses, batch: int, w: int, h: int, d_disp=None, stream=None):
         self._check(self._L.ssm_pipeline_batch_device(self._h, batch, _ptr(d_left), _ptr(d_right), _ptr(d_sem), _ptr(d_rgb),
                                                       _ptr(d_poses), w, h, _ptr(d_disp), C.c_void_p(stream) if stream else None))
+
+    def set_route_overlap(self, on: bool):
+        self._check(self._L.ssm_set_route_overlap(self._h, 1 if on else 0))
 
     def synchronize(self):
         self._check(self._L.ssm_synchronize(self._h))

@@ -121,7 +121,18 @@ def _nccl_worker(rank, world, port, q, p2p, split=0):
             D.init_comm(ctx, p2p=p2p)
             mine = D.shard_frames(n, rank, world)
             sl = slice(mine.start, mine.stop)
-            ctx.pipeline_batch_host(seq["left"][sl], seq["right"][sl], seq["semantic"][sl], seq["rgb"][sl], seq["pose"][sl])
+            if split == 2:
+                # streaming: route overlap on, two async batches (the second one's SGBM overlaps the first one's exchange)
+                ctx.set_route_overlap(True)
+                half = (mine.stop - mine.start + 1) // 2
+                keep = []                                   # host buffers stay alive until synchronize()
+                for a, b in ((mine.start, mine.start + half), (mine.start + half, mine.stop)):
+                    pins = [np.ascontiguousarray(seq[k][a:b]) for k in ("left", "right", "semantic", "rgb", "pose")]
+                    keep.append(pins)
+                    ctx.pipeline_batch_host_async(*pins)
+                ctx.synchronize()
+            else:
+                ctx.pipeline_batch_host(seq["left"][sl], seq["right"][sl], seq["semantic"][sl], seq["rgb"][sl], seq["pose"][sl])
             merged = D.gather_map(ctx)
         if rank == 0:
             q.put(merged)
