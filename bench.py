@@ -34,6 +34,25 @@ SEQ_FRAMES = 100
 METRIC = "semantic-map frames/s at 1241x376, 128 disparities (SGM disparity + labelled cloud + voxel fusion)"
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+# communicator), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 # ------------------------------------------------------------------------------------------------------------
 def algorithmic_bytes(points_per_frame: float) -> dict:
     """SURVEY.md section 8d per-frame algorithmic bytes of each stage (materialised cost volume formulation)."""
@@ -163,7 +182,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -344,7 +363,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                      "stages": stage_roof},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -362,6 +381,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL send/recv all-to-all instead of peer-memory routing")
     args = ap.parse_args()
+    capture_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
