@@ -379,7 +379,7 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
         for (int t = 0; t < 4; ++t) {
             const std::string name = "SSM_TUNE" + std::to_string(t);
             const char* v = getenv(name.c_str());
-            static const int defaults[4] = {2 /* vertical: L2 prefetch distance in rows */, 0 /* hsweep: L2 prefetch off */, 0,
+            static const int defaults[4] = {2 /* vertical: L2 prefetch distance in rows */, 0 /* hsweep: L2 prefetch off */, 0 /* fused selection: rows per band (0 = 8) */,
                                              -1 /* sub-batch streams: automatic */};
             c->tune[t] = v ? atoi(v) : defaults[t];
         }
@@ -387,6 +387,8 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
         c->force_legacy_hsweep = lh && lh[0] == '1';
         const char* lc = getenv("SSM_LEGACY_COST");
         c->force_legacy_cost = lc && lc[0] == '1';
+        const char* ls = getenv("SSM_LEGACY_SELECT");
+        c->force_legacy_select = ls && ls[0] == '1';
         const char* m = getenv("SSM_MAX_CLUSTER");
         if (m && atoi(m) > 0) c->max_cluster = atoi(m);
         const char* n = getenv("SSM_MIN_CLUSTER");

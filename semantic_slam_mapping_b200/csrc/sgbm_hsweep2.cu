@@ -21,6 +21,7 @@
 #include <type_traits>
 
 #include "sgbm_path.cuh"
+#include "sgbm_wta.cuh"
 
 namespace ssm {
 
@@ -274,26 +275,11 @@ __global__ void __launch_bounds__(256) k_wta_finalize2(const uint4* __restrict__
     const int xp = (int)(idx % W1);
     const size_t row = idx / W1;
     const uint4 r = rec[idx];
-    const int minS = (int)(r.x & 0xffffu), best = (int)((r.x >> 16) & 0x7fffu);
     const int x = xp + D;
-    int out = kInvalidDisp;
-    if (!(r.x >> 31)) {
-        atomicMin(&disp2key[row * W + (x - best)], ((uint32_t)minS << 16) | (uint32_t)(0xffff - x));
-        int d16 = best * kDispScale;
-        if (best > 0 && best < D - 1) {
-            // half-words {up, v0, .., v(2NR-1), down}; the winner is element q + 1
-            uint32_t w[3];
-            w[0] = (r.w & 0xffffu) | (r.y << 16);
-            if (NR == 2) { w[1] = (r.y >> 16) | (r.z << 16); w[2] = (r.z >> 16) | (r.w & 0xffff0000u); }
-            else { w[1] = (r.y >> 16) | (r.w & 0xffff0000u); w[2] = 0u; }
-            const int q = best & (2 * NR - 1);
-            auto elem = [&](int i) { const uint32_t v = i < 2 ? w[0] : (i < 4 ? w[1] : w[2]); return (int)((i & 1) ? (v >> 16) : (v & 0xffffu)); };
-            const int sm = elem(q), sp = elem(q + 2);
-            const int denom2 = max(sm + sp - 2 * minS, 1);
-            d16 += ((sm - sp) * kDispScale + denom2) / (denom2 * 2);
-        }
-        out = d16;
-    }
+    int minS, best;
+    bool valid;
+    const int out = wta2_decode<NR>(r, D, minS, best, valid);
+    if (valid) atomicMin(&disp2key[row * W + (x - best)], ((uint32_t)minS << 16) | (uint32_t)(0xffff - x));
     disp_raw[row * W + x] = (int16_t)out;
 }
 

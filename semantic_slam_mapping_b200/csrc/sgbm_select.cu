@@ -5,7 +5,7 @@
 //   k_lrcheck     left-right consistency (A-6); also writes the always-invalid columns [0, D)
 //   k_median3     cv::medianBlur(disp, 3) on int16 with replicate border
 //   k_cc_*        cv::filterSpeckles == connected components under |a-b| <= maxDiff; union-find with atomicMin
-#include "ssm_internal.cuh"
+#include "sgbm_wta.cuh"
 
 namespace ssm {
 
@@ -175,10 +175,351 @@ __global__ void __launch_bounds__(256) k_cc_apply(const int16_t* __restrict__ im
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused selection (checkpointed-sweep record format, D <= 128): one CTA per band of R image rows does, entirely in
+// shared memory, what the five kernels above do through HBM:
+//   records -> raw disparity + disp2 candidates (shared-memory atomicMin; no 4-byte key image, no memset)
+//   -> L-R check in place -> 3x3 median, two pixels per thread on packed s16x2 min / max
+//   -> speckle components INSIDE the band: run-start labels, unions with shared-memory atomics, flattening, sizes.
+// The rows above and below the band are recomputed (R + 2 rows of records per R rows of output).  What leaves the
+// CTA: disp_lr (debug tap), disp_med, label = global index of the pixel's band-local root (-1: invalid pixel),
+// size = band-local component size at roots, 0 elsewhere.  Components are completed across band borders by
+// k_cc_merge_bands (one row of vertical edges per band) and k_cc_count_roots (one atomic per hooked band root).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kNoLabel = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t s_find(const volatile uint32_t* lab, uint32_t x)
+{
+    uint32_t p = lab[x];
+    while (p != x) {
+        x = p;
+        p = lab[x];
+    }
+    return x;
+}
+__device__ __forceinline__ void s_union(uint32_t* lab, uint32_t a, uint32_t b)
+{
+    while (true) {
+        a = s_find(lab, a);
+        b = s_find(lab, b);
+        if (a == b) return;
+        if (a < b) { const uint32_t t = a; a = b; b = t; }
+        const uint32_t old = atomicMin(&lab[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+__device__ __forceinline__ void cswap2(uint32_t& a, uint32_t& b)
+{
+    const uint32_t lo = __vmins2(a, b), hi = __vmaxs2(a, b);
+    a = lo; b = hi;
+}
+
+struct SelArgs {
+    const uint4* rec;
+    int16_t *disp_lr, *disp_med;
+    int *label, *size;
+    int W, H, D, d12, R, WS, max_diff, do_cc;
+};
+
+template <int NR>
+__global__ void __launch_bounds__(512) k_select_fused(SelArgs a)
+{
+    extern __shared__ __align__(16) uint32_t sel_smem[];
+    const int W = a.W, H = a.H, D = a.D, W1 = W - D, R = a.R, WS = a.WS;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int y0 = blockIdx.x * R, b = blockIdx.y;
+    const int nr = min(R, H - y0), ns = nr + 2;                               // band rows; slots (slot j <-> image row y0 - 1 + j, clamped)
+    uint32_t* keys = sel_smem;                                                // [R + 2][W]   disp2 candidates (minS << 16 | 0xffff - x)
+    int16_t* dsp = reinterpret_cast<int16_t*>(keys + (size_t)(R + 2) * W);    // [R + 2][WS]  element x + 2 <-> pixel x, replicated borders
+    int16_t* med = dsp + (size_t)(R + 2) * WS;                                // [R][W]
+    const size_t frame_row0 = (size_t)b * H;
+
+    for (int i = tid; i < ns * W; i += nt) keys[i] = 0xffffffffu;
+    __syncthreads();
+    // ---- records -> raw disparity, disp2 candidates
+    {
+        int j = 0, xp = tid;
+        while (xp >= W1) { xp -= W1; ++j; }
+        while (j < ns) {
+            const int y = min(max(y0 - 1 + j, 0), H - 1);
+            const uint4 r = a.rec[(frame_row0 + y) * W1 + xp];
+            int minS, best;
+            bool valid;
+            const int out = wta2_decode<NR>(r, D, minS, best, valid);
+            const int x = xp + D;
+            if (valid) atomicMin(&keys[j * W + (x - best)], ((uint32_t)minS << 16) | (uint32_t)(0xffff - x));
+            dsp[j * WS + x + 2] = (int16_t)out;
+            xp += nt;
+            while (xp >= W1) { xp -= W1; ++j; }
+        }
+    }
+    __syncthreads();
+    // ---- L-R check in place (A-6); columns [0, D) are always invalid; border replication for the median
+    {
+        int j = 0, x = tid;
+        while (x >= W) { x -= W; ++j; }
+        while (j < ns) {
+            int16_t* row = dsp + j * WS;
+            int out = kInvalidDisp;
+            if (x >= D) {
+                const int d1 = row[x + 2];
+                out = d1;
+                if (d1 != kInvalidDisp) {
+                    const uint32_t* krow = keys + j * W;
+                    const int dlo = d1 >> 4, dhi = (d1 + kDispScale - 1) >> 4;
+                    const int xlo = x - dlo, xhi = x - dhi;
+                    bool bad_lo = false, bad_hi = false;
+                    if (xlo >= 0 && xlo < W) {
+                        const uint32_t k = krow[xlo];
+                        if (k != 0xffffffffu) bad_lo = abs((0xffff - (int)(k & 0xffffu)) - xlo - dlo) > a.d12;
+                    }
+                    if (xhi >= 0 && xhi < W) {
+                        const uint32_t k = krow[xhi];
+                        if (k != 0xffffffffu) bad_hi = abs((0xffff - (int)(k & 0xffffu)) - xhi - dhi) > a.d12;
+                    }
+                    if (bad_lo && bad_hi) out = kInvalidDisp;
+                }
+            }
+            row[x + 2] = (int16_t)out;
+            if (x == 0) { row[0] = (int16_t)out; row[1] = (int16_t)out; }
+            if (x == W - 1)
+                for (int e = W + 2; e < WS; ++e) row[e] = (int16_t)out;
+            if (j >= 1 && j <= nr) a.disp_lr[(frame_row0 + y0 + j - 1) * W + x] = (int16_t)out;
+            x += nt;
+            while (x >= W) { x -= W; ++j; }
+        }
+    }
+    __syncthreads();
+    // ---- 3x3 median (cv::medianBlur(3), replicate border), pixels (x, x + 1) in the two halves of packed words
+    {
+        const int hp = (W + 1) >> 1;
+        const uint32_t* dw = reinterpret_cast<const uint32_t*>(dsp);
+        int r = 0, k = tid;
+        while (k >= hp) { k -= hp; ++r; }
+        while (r < nr) {
+            const int x = 2 * k;
+            uint32_t p[9];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const uint32_t* q = dw + (((r + t) * WS + x) >> 1);
+                const uint32_t A0 = q[0], A1 = q[1], A2 = q[2];
+                p[3 * t] = __byte_perm(A0, A1, 0x5432);        // pixels (x - 1, x)
+                p[3 * t + 1] = A1;                             // pixels (x, x + 1)
+                p[3 * t + 2] = __byte_perm(A1, A2, 0x5432);    // pixels (x + 1, x + 2)
+            }
+            cswap2(p[1], p[2]); cswap2(p[4], p[5]); cswap2(p[7], p[8]); cswap2(p[0], p[1]); cswap2(p[3], p[4]); cswap2(p[6], p[7]);
+            cswap2(p[1], p[2]); cswap2(p[4], p[5]); cswap2(p[7], p[8]); cswap2(p[0], p[3]); cswap2(p[5], p[8]); cswap2(p[4], p[7]);
+            cswap2(p[3], p[6]); cswap2(p[1], p[4]); cswap2(p[2], p[5]); cswap2(p[4], p[7]); cswap2(p[4], p[2]); cswap2(p[6], p[4]);
+            cswap2(p[4], p[2]);
+            const int16_t m0 = (int16_t)(p[4] & 0xffffu), m1 = (int16_t)(p[4] >> 16);
+            int16_t* g = a.disp_med + (frame_row0 + y0 + r) * W + x;
+            med[r * W + x] = m0;
+            g[0] = m0;
+            if (x + 1 < W) { med[r * W + x + 1] = m1; g[1] = m1; }
+            k += nt;
+            while (k >= hp) { k -= hp; ++r; }
+        }
+    }
+    if (!a.do_cc) return;
+    __syncthreads();
+    // ---- speckle components inside the band.  label = smallest linear index (r * W + x) of the component's pixels
+    uint32_t* lab = keys;                                       // [nr * W], over the key rows
+    uint32_t* szw = reinterpret_cast<uint32_t*>(dsp);           // band-local sizes as packed u16 pairs, over the disparity rows
+    const int npx = nr * W;
+    const int md = a.max_diff;
+    for (int i = tid; i < (npx + 1) / 2; i += nt) szw[i] = 0u;
+    {
+        const int segs = (W + 31) >> 5, lane = tid & 31;
+        for (int sgi = tid >> 5; sgi < nr * segs; sgi += nt >> 5) {
+            const int r = sgi / segs, x0 = (sgi - r * segs) * 32, x = x0 + lane;
+            const int v = x < W ? (int)med[r * W + x] : kInvalidDisp;
+            const int vl = __shfl_up_sync(0xffffffffu, v, 1);
+            const bool head = v != kInvalidDisp && !(lane > 0 && cc_conn(v, vl, md));
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            if (x < W) {
+                const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+                lab[r * W + x] = v == kInvalidDisp ? kNoLabel : (uint32_t)(r * W + x0 + start);
+            }
+        }
+    }
+    __syncthreads();
+    {
+        int r = 0, x = tid;
+        while (x >= W) { x -= W; ++r; }
+        while (r < nr) {
+            const int li = r * W + x;
+            const int v = med[li];
+            if (v != kInvalidDisp) {
+                const int vl = x > 0 ? (int)med[li - 1] : kInvalidDisp;
+                const bool cl = cc_conn(v, vl, md);
+                if (cl && (x & 31) == 0) s_union(lab, (uint32_t)li, (uint32_t)(li - 1));
+                if (r > 0) {
+                    const int vu = med[li - W];
+                    if (cc_conn(v, vu, md)) {
+                        bool skip = false;
+                        if (cl) {
+                            const int vul = med[li - W - 1];
+                            skip = cc_conn(vl, vul, md) && cc_conn(vul, vu, md);
+                        }
+                        if (!skip) s_union(lab, (uint32_t)li, (uint32_t)(li - W));
+                    }
+                }
+            }
+            x += nt;
+            while (x >= W) { x -= W; ++r; }
+        }
+    }
+    __syncthreads();
+    {
+        const int lane = tid & 31;
+        for (int base = tid - lane; base < npx; base += nt) {   // warp-uniform trip count
+            const int li = base + lane;
+            uint32_t root = kNoLabel;
+            if (li < npx && lab[li] != kNoLabel) {
+                root = s_find(lab, (uint32_t)li);
+                lab[li] = root;                                 // roots are fixed points by now: concurrent finds stay correct
+            }
+            const uint32_t rp = __shfl_up_sync(0xffffffffu, root, 1);
+            const bool head = lane == 0 || root != rp;
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            if (root != kNoLabel && head) {
+                const uint32_t after = lane == 31 ? 0u : (heads >> (lane + 1));
+                const uint32_t run = after ? (uint32_t)__ffs(after) : (uint32_t)(32 - lane);
+                atomicAdd(&szw[root >> 1], run << ((root & 1u) * 16));   // sizes <= R * W < 65536: no carry between the halves
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const size_t gbase = (frame_row0 + y0) * W;
+        const uint16_t* sz16 = reinterpret_cast<const uint16_t*>(szw);
+        for (int li = tid; li < npx; li += nt) {
+            const uint32_t root = lab[li];
+            a.label[gbase + li] = root == kNoLabel ? -1 : (int)(gbase + root);
+            a.size[gbase + li] = root == (uint32_t)li ? (int)sz16[li] : 0;
+        }
+    }
+}
+
+// vertical edges between the last row of a band and the first row of the next (same redundant-edge rule as k_cc_merge)
+__global__ void __launch_bounds__(256) k_cc_merge_bands(const int16_t* __restrict__ img, int* __restrict__ label, int W, int H, int R,
+                                                        int inner /* bands per frame - 1 */, int max_diff, size_t total)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = (int)(idx % W);
+    const size_t t = idx / W;
+    const int y = ((int)(t % inner) + 1) * R;
+    const size_t p = ((t / inner) * H + y) * W + x;
+    const int v = img[p];
+    if (v == kInvalidDisp) return;
+    const int vu = img[p - W];
+    if (!cc_conn(v, vu, max_diff)) return;
+    if (x > 0) {
+        const int vl = img[p - 1];
+        if (cc_conn(v, vl, max_diff)) {
+            const int vul = img[p - W - 1];
+            if (cc_conn(vl, vul, max_diff) && cc_conn(vul, vu, max_diff)) return;
+        }
+    }
+    cc_union(label, (int)p, (int)(p - W));
+}
+// band roots hooked under another band's root hand their size to the component's root and point straight at it
+__global__ void __launch_bounds__(256) k_cc_count_roots(int* __restrict__ label, int* __restrict__ size, size_t total)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int s = size[idx];
+    if (s <= 0) return;
+    const int g = cc_find(label, (int)idx);
+    if (g != (int)idx) {
+        atomicAdd(&size[g], s);   // only roots of whole components receive additions; a hooked root keeps its band-local size
+        label[idx] = g;
+    }
+}
+// a pixel stays unless its component has at most max_size pixels; a band-local size above the bound already settles it
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_cc_apply_bands(const int16_t* __restrict__ img, const int* __restrict__ label,
+                                                        const int* __restrict__ size, int16_t* __restrict__ out, int max_size,
+                                                        size_t total)
+{
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= total) return;
+    int v[4], l[4];
+    const int n = (int)min((size_t)4, total - i0);
+    if (VEC && n == 4) {
+        const uint2 vv = *reinterpret_cast<const uint2*>(img + i0);
+        const int4 ll = *reinterpret_cast<const int4*>(label + i0);
+        v[0] = (int16_t)(vv.x & 0xffffu); v[1] = (int16_t)(vv.x >> 16); v[2] = (int16_t)(vv.y & 0xffffu); v[3] = (int16_t)(vv.y >> 16);
+        l[0] = ll.x; l[1] = ll.y; l[2] = ll.z; l[3] = ll.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = k < n ? (int)img[i0 + k] : kInvalidDisp;
+            l[k] = k < n ? label[i0 + k] : -1;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (l[k] < 0) continue;
+        int s = size[l[k]];
+        if (s <= max_size) {
+            const int g = cc_find(const_cast<int*>(label), l[k]);
+            if (g != l[k]) s = size[g];
+            if (s <= max_size) v[k] = kInvalidDisp;
+        }
+    }
+    if (VEC && n == 4) {
+        uint2 o;
+        o.x = (uint32_t)(v[0] & 0xffff) | ((uint32_t)(v[1] & 0xffff) << 16);
+        o.y = (uint32_t)(v[2] & 0xffff) | ((uint32_t)(v[3] & 0xffff) << 16);
+        *reinterpret_cast<uint2*>(out + i0) = o;
+    } else {
+        for (int k = 0; k < n; ++k) out[i0 + k] = (int16_t)v[k];
+    }
+}
+
+// rows per band of the fused selection kernel (0: not applicable -> the separate kernels run)
+static int select_fused_rows(const ssm_ctx* c, size_t* smem_out)
+{
+    const DevParams& p = c->dp;
+    if (c->force_legacy_select || !hsweep2_supported(c)) return 0;
+    const int WS = (p.W + 4 + 1) & ~1;
+    const int first = c->tune[2] > 0 ? c->tune[2] : 8;
+    for (int R = first; R >= 1; R >>= 1) {
+        const size_t smem = (size_t)(R + 2) * p.W * 4 + (size_t)(R + 2) * WS * 2 + (size_t)R * p.W * 2 + 16;
+        if ((size_t)R * p.W < 65535 && smem <= (R > 1 ? 110u : 220u) * 1024u) {
+            if (smem_out) *smem_out = smem;
+            return R;
+        }
+    }
+    return 0;
+}
+
+template <int NR>
+static int launch_select_fused_t(ssm_ctx* c, int B, int R, size_t smem, cudaStream_t s)
+{
+    const DevParams& p = c->dp;
+    SelArgs a;
+    a.rec = reinterpret_cast<const uint4*>(c->d_wta_rec);
+    a.disp_lr = c->d_disp_lr; a.disp_med = c->d_disp_med; a.label = c->d_cc_label; a.size = c->d_cc_size;
+    a.W = p.W; a.H = p.H; a.D = p.D; a.d12 = p.d12; a.R = R; a.WS = (p.W + 4 + 1) & ~1;
+    a.max_diff = p.speckle_diff; a.do_cc = p.speckle_win > 0;
+    SSM_CUDA(cudaFuncSetAttribute(k_select_fused<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((p.H + R - 1) / R), (unsigned)B);
+    k_select_fused<NR><<<grid, 512, smem, s>>>(a);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 int launch_select(ssm_ctx* c, int B, cudaStream_t s)
 {
     const DevParams& p = c->dp;
     const size_t npix = (size_t)B * p.H * p.W;
+    size_t smem = 0;
+    if (const int R = select_fused_rows(c, &smem))   // records -> L-R checked, median-filtered disparity + band-local speckle labels
+        return p.D <= 64 ? launch_select_fused_t<1>(c, B, R, smem, s) : launch_select_fused_t<2>(c, B, R, smem, s);
     SSM_CUDA(cudaMemsetAsync(c->d_disp2key, 0xff, npix * sizeof(uint32_t), s));
     int rc = hsweep2_supported(c) ? launch_wta_finalize2(c, B, s) : launch_wta_finalize(c, B, s);
     if (rc) return rc;
@@ -192,8 +533,29 @@ int launch_post(ssm_ctx* c, int B, int16_t* d_out, cudaStream_t s)
     const DevParams& p = c->dp;
     const size_t npix = (size_t)B * p.H * p.W;
     const unsigned grid = (unsigned)((npix + 255) / 256);
-    k_median3<<<grid, 256, 0, s>>>(c->d_disp_lr, c->d_disp_med, p.W, p.H, npix);
-    SSM_LAUNCH_CHECK(c);
+    const int R = select_fused_rows(c, nullptr);
+    if (R && p.speckle_win > 0) {
+        // the fused selection kernel left the median image, band-local labels and sizes: join the bands, total the sizes, filter
+        const int inner = (p.H + R - 1) / R - 1;
+        if (inner > 0) {
+            const size_t edges = (size_t)B * inner * p.W;
+            k_cc_merge_bands<<<(unsigned)((edges + 255) / 256), 256, 0, s>>>(c->d_disp_med, c->d_cc_label, p.W, p.H, R, inner, p.speckle_diff, edges);
+            SSM_LAUNCH_CHECK(c);
+            k_cc_count_roots<<<grid, 256, 0, s>>>(c->d_cc_label, c->d_cc_size, npix);
+            SSM_LAUNCH_CHECK(c);
+        }
+        const unsigned grid4 = (unsigned)(((npix + 3) / 4 + 255) / 256);
+        const bool vec = (reinterpret_cast<uintptr_t>(c->d_disp_med) % 8 == 0) && (reinterpret_cast<uintptr_t>(d_out) % 8 == 0) &&
+                         (reinterpret_cast<uintptr_t>(c->d_cc_label) % 16 == 0);
+        if (vec) k_cc_apply_bands<true><<<grid4, 256, 0, s>>>(c->d_disp_med, c->d_cc_label, c->d_cc_size, d_out, p.speckle_win, npix);
+        else k_cc_apply_bands<false><<<grid4, 256, 0, s>>>(c->d_disp_med, c->d_cc_label, c->d_cc_size, d_out, p.speckle_win, npix);
+        SSM_LAUNCH_CHECK(c);
+        return SSM_OK;
+    }
+    if (!R) {
+        k_median3<<<grid, 256, 0, s>>>(c->d_disp_lr, c->d_disp_med, p.W, p.H, npix);
+        SSM_LAUNCH_CHECK(c);
+    }
     if (p.speckle_win <= 0) {
         SSM_CUDA(cudaMemcpyAsync(d_out, c->d_disp_med, npix * sizeof(int16_t), cudaMemcpyDeviceToDevice, s));
         return SSM_OK;

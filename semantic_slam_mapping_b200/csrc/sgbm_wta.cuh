@@ -1,0 +1,34 @@
+// sgbm_wta.cuh -- decoding of the 16-byte winner-take-all records written by k_hrev (sgbm_hsweep2.cu): shared by the
+// stand-alone finalize kernel and the fused selection kernel (sgbm_select.cu).
+#pragma once
+
+#include "ssm_internal.cuh"
+
+namespace ssm {
+
+// One record -> the pixel's raw disparity (x16, sub-pixel refined; kInvalidDisp when the uniqueness test rejected it),
+// SURVEY.md App. A-5.  Record: x = minS | best << 16 | reject << 31; y, z, w = the winner lane's packed costs with the two
+// values across its lane borders: half-words {up, v0, .., v(2NR-1), down}, the winner is element q + 1.
+template <int NR>
+__device__ __forceinline__ int wta2_decode(const uint4& r, int D, int& minS, int& best, bool& valid)
+{
+    minS = (int)(r.x & 0xffffu);
+    best = (int)((r.x >> 16) & 0x7fffu);
+    valid = !(r.x >> 31);
+    if (!valid) return kInvalidDisp;
+    int d16 = best * kDispScale;
+    if (best > 0 && best < D - 1) {
+        uint32_t w[3];
+        w[0] = (r.w & 0xffffu) | (r.y << 16);
+        if (NR == 2) { w[1] = (r.y >> 16) | (r.z << 16); w[2] = (r.z >> 16) | (r.w & 0xffff0000u); }
+        else { w[1] = (r.y >> 16) | (r.w & 0xffff0000u); w[2] = 0u; }
+        const int q = best & (2 * NR - 1);
+        auto elem = [&](int i) { const uint32_t v = i < 2 ? w[0] : (i < 4 ? w[1] : w[2]); return (int)((i & 1) ? (v >> 16) : (v & 0xffffu)); };
+        const int sm = elem(q), sp = elem(q + 2);
+        const int denom2 = max(sm + sp - 2 * minS, 1);
+        d16 += ((sm - sp) * kDispScale + denom2) / (denom2 * 2);
+    }
+    return d16;
+}
+
+}  // namespace ssm

@@ -100,6 +100,7 @@ struct ssm_ctx {
     bool force_legacy_hsweep = false;     // SSM_LEGACY_HSWEEP=1: one-kernel horizontal sweep (S_f through HBM) instead of checkpointed recomputation
     bool force_legacy_cost = false;       // SSM_LEGACY_COST=1: k_pix_hsum + k_vsum instead of the fused cost kernel
     bool force_legacy_vertical = false;   // SSM_LEGACY_VERTICAL=1: per-direction kernels instead of the cluster kernel
+    bool force_legacy_select = false;     // SSM_LEGACY_SELECT=1: finalize / L-R check / median / speckle as separate kernels instead of the fused band kernel
     cudaStream_t stream = nullptr;
     // sub-batch streams of the split pipeline (SSM_TUNE3 = number of concurrent sub-batches): kernels bound by different
     // units (shared-memory LSU, issue, HBM) overlap across sub-batches

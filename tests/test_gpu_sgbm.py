@@ -209,3 +209,41 @@ def test_cityscapes_width_256_disparities_band():
     with Context(p) as ctx:
         got = ctx.sgbm(L, R)
     assert int((got != oracle.sgbm(L, R, _oparams(p))).sum()) == 0
+
+
+@pytest.mark.parametrize("rows", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("H,W,D,seed", [(61, 233, 64, 101), (40, 300, 128, 102), (19, 150, 32, 103)])
+def test_fused_selection_band_heights(monkeypatch, rows, H, W, D, seed):
+    """Fused selection kernel (records -> L-R check -> median -> band-local speckle components) for several band
+    heights: odd widths, bands that do not divide H, components that cross several band borders."""
+    monkeypatch.setenv("SSM_TUNE2", str(rows))
+    L, R, _ = synth.stereo_pair(H, W, D, seed)
+    rng = np.random.default_rng(seed)
+    R = np.clip(R.astype(int) + rng.integers(-10, 11, R.shape), 0, 255).astype(np.uint8)   # speckles and rejected pixels
+    p = _params(D, W, H)
+    want, vols = oracle.sgbm(L, R, _oparams(p), want_volumes=True)
+    with Context(p) as ctx:
+        got = ctx.sgbm(L, R)
+        raw = ctx.debug_volume("disp_raw", W, H)
+        med = ctx.debug_volume("disp_median", W, H)
+    assert int((raw != vols["disp_raw"]).sum()) == 0, "L-R checked disparity"
+    assert int((med != vols["disp_median"]).sum()) == 0, "median"
+    assert int((got != want).sum()) == 0, "speckle filter"
+
+
+@pytest.mark.parametrize("spw,spr", [(0, 0), (20, 1), (400, 2), (100, 32)])
+def test_fused_selection_speckle_parameters(spw, spr):
+    L, R, _ = synth.stereo_pair(90, 260, 64, 111)
+    rng = np.random.default_rng(3)
+    R = np.clip(R.astype(int) + rng.integers(-14, 15, R.shape), 0, 255).astype(np.uint8)
+    p = _params(64, 260, 90, speckle_window_size=spw, speckle_range=spr)
+    with Context(p) as ctx:
+        assert int((ctx.sgbm(L, R) != oracle.sgbm(L, R, _oparams(p))).sum()) == 0
+
+
+def test_legacy_separate_selection_kernels_still_exact(monkeypatch):
+    monkeypatch.setenv("SSM_LEGACY_SELECT", "1")
+    L, R, _ = synth.stereo_pair(64, 300, 128, 121)
+    p = _params(128, 300, 64)
+    with Context(p) as ctx:
+        assert int((ctx.sgbm(L, R) != oracle.sgbm(L, R, _oparams(p))).sum()) == 0
