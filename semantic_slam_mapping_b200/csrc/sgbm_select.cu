@@ -219,14 +219,20 @@ struct SelArgs {
     int16_t *disp_lr, *disp_med;
     int *label, *size;
     int W, H, D, d12, R, WS, max_diff, do_cc;
+    uint32_t mW1, mW, mHp;    // ceil(2^32 / d) for d = W1, W, (W + 1) / 2: i / d == umulhi(i, m) for every index the kernel forms
 };
+__device__ __forceinline__ void divmod_magic(int i, uint32_t m, int d, int& q, int& r)
+{
+    q = (int)__umulhi((uint32_t)i, m);
+    r = i - q * d;
+}
 
 template <int NR>
 __global__ void __launch_bounds__(512) k_select_fused(SelArgs a)
 {
     extern __shared__ __align__(16) uint32_t sel_smem[];
     const int W = a.W, H = a.H, D = a.D, W1 = W - D, R = a.R, WS = a.WS;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int y0 = blockIdx.x * R, b = blockIdx.y;
     const int nr = min(R, H - y0), ns = nr + 2;                               // band rows; slots (slot j <-> image row y0 - 1 + j, clamped)
     uint32_t* keys = sel_smem;                                                // [R + 2][W]   disp2 candidates (minS << 16 | 0xffff - x)
@@ -236,29 +242,38 @@ __global__ void __launch_bounds__(512) k_select_fused(SelArgs a)
 
     for (int i = tid; i < ns * W; i += nt) keys[i] = 0xffffffffu;
     __syncthreads();
-    // ---- records -> raw disparity, disp2 candidates
+    // ---- records -> raw disparity, disp2 candidates; two records in flight per thread
     {
-        int j = 0, xp = tid;
-        while (xp >= W1) { xp -= W1; ++j; }
-        while (j < ns) {
-            const int y = min(max(y0 - 1 + j, 0), H - 1);
-            const uint4 r = a.rec[(frame_row0 + y) * W1 + xp];
+        const uint4* recf = a.rec + frame_row0 * W1;
+        const int n1 = ns * W1;
+        auto item = [&](const uint4& r, int j, int xp) {
             int minS, best;
             bool valid;
             const int out = wta2_decode<NR>(r, D, minS, best, valid);
             const int x = xp + D;
             if (valid) atomicMin(&keys[j * W + (x - best)], ((uint32_t)minS << 16) | (uint32_t)(0xffff - x));
             dsp[j * WS + x + 2] = (int16_t)out;
-            xp += nt;
-            while (xp >= W1) { xp -= W1; ++j; }
+        };
+        for (int i = tid; i < n1; i += 2 * nt) {
+            const int i2 = i + nt;
+            const bool two = i2 < n1;
+            int j, xp, j2, xp2;
+            divmod_magic(i, a.mW1, W1, j, xp);
+            divmod_magic(two ? i2 : i, a.mW1, W1, j2, xp2);
+            const uint4 r = recf[min(max(y0 - 1 + j, 0), H - 1) * W1 + xp];
+            const uint4 r2 = recf[min(max(y0 - 1 + j2, 0), H - 1) * W1 + xp2];
+            item(r, j, xp);
+            if (two) item(r2, j2, xp2);
         }
     }
     __syncthreads();
     // ---- L-R check in place (A-6); columns [0, D) are always invalid; border replication for the median
     {
-        int j = 0, x = tid;
-        while (x >= W) { x -= W; ++j; }
-        while (j < ns) {
+        int16_t* lrg = a.disp_lr + (frame_row0 + y0) * W;
+        const int n2 = ns * W;
+        for (int i = tid; i < n2; i += nt) {
+            int j, x;
+            divmod_magic(i, a.mW, W, j, x);
             int16_t* row = dsp + j * WS;
             int out = kInvalidDisp;
             if (x >= D) {
@@ -267,16 +282,10 @@ __global__ void __launch_bounds__(512) k_select_fused(SelArgs a)
                 if (d1 != kInvalidDisp) {
                     const uint32_t* krow = keys + j * W;
                     const int dlo = d1 >> 4, dhi = (d1 + kDispScale - 1) >> 4;
-                    const int xlo = x - dlo, xhi = x - dhi;
-                    bool bad_lo = false, bad_hi = false;
-                    if (xlo >= 0 && xlo < W) {
-                        const uint32_t k = krow[xlo];
-                        if (k != 0xffffffffu) bad_lo = abs((0xffff - (int)(k & 0xffffu)) - xlo - dlo) > a.d12;
-                    }
-                    if (xhi >= 0 && xhi < W) {
-                        const uint32_t k = krow[xhi];
-                        if (k != 0xffffffffu) bad_hi = abs((0xffff - (int)(k & 0xffffu)) - xhi - dhi) > a.d12;
-                    }
+                    const int xlo = x - dlo, xhi = x - dhi;   // 0 < x - (D - 1) <= xhi <= xlo <= x: always inside the row
+                    const uint32_t klo = krow[xlo], khi = krow[xhi];
+                    const bool bad_lo = klo != 0xffffffffu && abs((0xffff - (int)(klo & 0xffffu)) - xlo - dlo) > a.d12;
+                    const bool bad_hi = khi != 0xffffffffu && abs((0xffff - (int)(khi & 0xffffu)) - xhi - dhi) > a.d12;
                     if (bad_lo && bad_hi) out = kInvalidDisp;
                 }
             }
@@ -284,9 +293,7 @@ __global__ void __launch_bounds__(512) k_select_fused(SelArgs a)
             if (x == 0) { row[0] = (int16_t)out; row[1] = (int16_t)out; }
             if (x == W - 1)
                 for (int e = W + 2; e < WS; ++e) row[e] = (int16_t)out;
-            if (j >= 1 && j <= nr) a.disp_lr[(frame_row0 + y0 + j - 1) * W + x] = (int16_t)out;
-            x += nt;
-            while (x >= W) { x -= W; ++j; }
+            if (j >= 1 && j <= nr) lrg[(j - 1) * W + x] = (int16_t)out;
         }
     }
     __syncthreads();
@@ -294,9 +301,10 @@ __global__ void __launch_bounds__(512) k_select_fused(SelArgs a)
     {
         const int hp = (W + 1) >> 1;
         const uint32_t* dw = reinterpret_cast<const uint32_t*>(dsp);
-        int r = 0, k = tid;
-        while (k >= hp) { k -= hp; ++r; }
-        while (r < nr) {
+        int16_t* mg = a.disp_med + (frame_row0 + y0) * W;
+        for (int i = tid; i < nr * hp; i += nt) {
+            int r, k;
+            divmod_magic(i, a.mHp, hp, r, k);
             const int x = 2 * k;
             uint32_t p[9];
 #pragma unroll
@@ -312,12 +320,10 @@ __global__ void __launch_bounds__(512) k_select_fused(SelArgs a)
             cswap2(p[3], p[6]); cswap2(p[1], p[4]); cswap2(p[2], p[5]); cswap2(p[4], p[7]); cswap2(p[4], p[2]); cswap2(p[6], p[4]);
             cswap2(p[4], p[2]);
             const int16_t m0 = (int16_t)(p[4] & 0xffffu), m1 = (int16_t)(p[4] >> 16);
-            int16_t* g = a.disp_med + (frame_row0 + y0 + r) * W + x;
-            med[r * W + x] = m0;
-            g[0] = m0;
-            if (x + 1 < W) { med[r * W + x + 1] = m1; g[1] = m1; }
-            k += nt;
-            while (k >= hp) { k -= hp; ++r; }
+            const int li = r * W + x;
+            med[li] = m0;
+            mg[li] = m0;
+            if (x + 1 < W) { med[li + 1] = m1; mg[li + 1] = m1; }
         }
     }
     if (!a.do_cc) return;
@@ -328,56 +334,62 @@ __global__ void __launch_bounds__(512) k_select_fused(SelArgs a)
     const int npx = nr * W;
     const int md = a.max_diff;
     for (int i = tid; i < (npx + 1) / 2; i += nt) szw[i] = 0u;
-    {
-        const int segs = (W + 31) >> 5, lane = tid & 31;
-        for (int sgi = tid >> 5; sgi < nr * segs; sgi += nt >> 5) {
-            const int r = sgi / segs, x0 = (sgi - r * segs) * 32, x = x0 + lane;
-            const int v = x < W ? (int)med[r * W + x] : kInvalidDisp;
-            const int vl = __shfl_up_sync(0xffffffffu, v, 1);
-            const bool head = v != kInvalidDisp && !(lane > 0 && cc_conn(v, vl, md));
+    // initial label = start of the pixel's horizontal run: one warp walks a row, the open run is carried across its 32-pixel steps
+    for (int r = warp; r < nr; r += nwarps) {
+        const int16_t* mrow = med + r * W;
+        uint32_t* lrow = lab + r * W;
+        int carry_start = 0, carry_v = kInvalidDisp;            // start of the run the previous step ended in, its last value
+        for (int x0 = 0; x0 < W; x0 += 32) {
+            const int x = x0 + lane;
+            const int v = x < W ? (int)mrow[x] : kInvalidDisp;
+            int vl = __shfl_up_sync(0xffffffffu, v, 1);
+            if (lane == 0) vl = carry_v;
+            const bool head = v != kInvalidDisp && !cc_conn(v, vl, md);
             const uint32_t heads = __ballot_sync(0xffffffffu, head);
-            if (x < W) {
-                const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-                lab[r * W + x] = v == kInvalidDisp ? kNoLabel : (uint32_t)(r * W + x0 + start);
-            }
+            const uint32_t upto = heads & (0xffffffffu >> (31 - lane));
+            const int start = upto ? x0 + 31 - __clz(upto) : carry_start;
+            if (x < W) lrow[x] = v == kInvalidDisp ? kNoLabel : (uint32_t)(r * W + start);
+            carry_start = __shfl_sync(0xffffffffu, start, 31);
+            carry_v = __shfl_sync(0xffffffffu, v, 31);
         }
     }
     __syncthreads();
-    {
-        int r = 0, x = tid;
-        while (x >= W) { x -= W; ++r; }
-        while (r < nr) {
-            const int li = r * W + x;
-            const int v = med[li];
-            if (v != kInvalidDisp) {
-                const int vl = x > 0 ? (int)med[li - 1] : kInvalidDisp;
-                const bool cl = cc_conn(v, vl, md);
-                if (cl && (x & 31) == 0) s_union(lab, (uint32_t)li, (uint32_t)(li - 1));
-                if (r > 0) {
-                    const int vu = med[li - W];
-                    if (cc_conn(v, vu, md)) {
-                        bool skip = false;
-                        if (cl) {
-                            const int vul = med[li - W - 1];
-                            skip = cc_conn(vl, vul, md) && cc_conn(vul, vu, md);
-                        }
-                        if (!skip) s_union(lab, (uint32_t)li, (uint32_t)(li - W));
-                    }
-                }
-            }
-            x += nt;
-            while (x >= W) { x -= W; ++r; }
+    // vertical edges (rows 1 .. nr - 1), skipping an edge whenever the left neighbour's vertical edge and the two horizontal
+    // edges already connect the same pair
+    for (int li = W + tid; li < npx; li += nt) {
+        const int v = med[li];
+        if (v == kInvalidDisp) continue;
+        const int vu = med[li - W];
+        if (!cc_conn(v, vu, md)) continue;
+        int r, x;
+        divmod_magic(li, a.mW, W, r, x);
+        if (x > 0) {
+            const int vl = med[li - 1], vul = med[li - W - 1];
+            if (cc_conn(v, vl, md) && cc_conn(vl, vul, md) && cc_conn(vul, vu, md)) continue;
         }
+        s_union(lab, (uint32_t)li, (uint32_t)(li - W));
+    }
+    __syncthreads();
+    // run heads look their root up; every other pixel then reaches it in two loads (its run's head, the head's root)
+    for (int li = tid; li < npx; li += nt) {
+        const int v = med[li];
+        if (v == kInvalidDisp) continue;
+        int r, x;
+        divmod_magic(li, a.mW, W, r, x);
+        if (x > 0 && cc_conn(v, (int)med[li - 1], md)) continue;
+        lab[li] = s_find(lab, (uint32_t)li);
     }
     __syncthreads();
     {
-        const int lane = tid & 31;
+        int* lg = a.label + (frame_row0 + y0) * W;
+        const int gbase = (int)((frame_row0 + y0) * W);
         for (int base = tid - lane; base < npx; base += nt) {   // warp-uniform trip count
             const int li = base + lane;
             uint32_t root = kNoLabel;
-            if (li < npx && lab[li] != kNoLabel) {
-                root = s_find(lab, (uint32_t)li);
-                lab[li] = root;                                 // roots are fixed points by now: concurrent finds stay correct
+            if (li < npx) {
+                const uint32_t h = lab[li];
+                if (h != kNoLabel) root = lab[h];
+                lg[li] = root == kNoLabel ? -1 : gbase + (int)root;
             }
             const uint32_t rp = __shfl_up_sync(0xffffffffu, root, 1);
             const bool head = lane == 0 || root != rp;
@@ -391,13 +403,9 @@ __global__ void __launch_bounds__(512) k_select_fused(SelArgs a)
     }
     __syncthreads();
     {
-        const size_t gbase = (frame_row0 + y0) * W;
+        int* sg = a.size + (frame_row0 + y0) * W;
         const uint16_t* sz16 = reinterpret_cast<const uint16_t*>(szw);
-        for (int li = tid; li < npx; li += nt) {
-            const uint32_t root = lab[li];
-            a.label[gbase + li] = root == kNoLabel ? -1 : (int)(gbase + root);
-            a.size[gbase + li] = root == (uint32_t)li ? (int)sz16[li] : 0;
-        }
+        for (int li = tid; li < npx; li += nt) sg[li] = (int)sz16[li];   // non-zero exactly at the band-local roots
     }
 }
 
@@ -483,7 +491,8 @@ __global__ void __launch_bounds__(256) k_cc_apply_bands(const int16_t* __restric
 static int select_fused_rows(const ssm_ctx* c, size_t* smem_out)
 {
     const DevParams& p = c->dp;
-    if (c->force_legacy_select || !hsweep2_supported(c)) return 0;
+    // index / d as one multiply-high needs d >= 2 and index * d < 2^32 for every index formed (at most (R + 2) * W + 2 * 512)
+    if (c->force_legacy_select || !hsweep2_supported(c) || p.W1 < 2 || p.W > 8192) return 0;
     const int WS = (p.W + 4 + 1) & ~1;
     const int first = c->tune[2] > 0 ? c->tune[2] : 8;
     for (int R = first; R >= 1; R >>= 1) {
@@ -505,6 +514,8 @@ static int launch_select_fused_t(ssm_ctx* c, int B, int R, size_t smem, cudaStre
     a.disp_lr = c->d_disp_lr; a.disp_med = c->d_disp_med; a.label = c->d_cc_label; a.size = c->d_cc_size;
     a.W = p.W; a.H = p.H; a.D = p.D; a.d12 = p.d12; a.R = R; a.WS = (p.W + 4 + 1) & ~1;
     a.max_diff = p.speckle_diff; a.do_cc = p.speckle_win > 0;
+    auto magic = [](int d) { return (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
+    a.mW1 = magic(p.W1); a.mW = magic(p.W); a.mHp = magic((p.W + 1) / 2);
     SSM_CUDA(cudaFuncSetAttribute(k_select_fused<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((p.H + R - 1) / R), (unsigned)B);
     k_select_fused<NR><<<grid, 512, smem, s>>>(a);
