@@ -62,8 +62,8 @@ def algorithmic_bytes(points_per_frame: float) -> dict:
         "cost": 2 * px + 2 * N,                 # K1: read L,R; write C
         "vertical": 2 * N + 2 * N,              # K2: read C, write S_v
         "horizontal": 2 * N + 2 * N + 2 * px,   # K3: read C, S_v; write disp1 records
-        "select": 2 * px,                       # K4: L-R check
-        "post": 6 * 2 * px,                     # K5 + K6
+        "select": 2 * px + 2 * 2 * px,          # K4 + K5: L-R check, median (fused with the band-local part of K6 since r1 v10)
+        "post": 4 * 2 * px,                     # K6: speckle filter (K5 + K6 = 6 passes over the int16 image in SURVEY 8d)
         "points": 2 * px + 3 * px + 3 * px + 20 * points_per_frame,   # K7
         "fuse": 20 * points_per_frame + 64 * points_per_frame,       # K8 upper bound: one record RMW per point
         "total": 10 * N + 30 * px + 84 * points_per_frame,
@@ -312,7 +312,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     ab = algorithmic_bytes(pts)
     kernels = {"cost": "k_prefilter8 + k_cost_fused", "vertical": "k_vertical3 (cluster kernel)", "horizontal": "k_hfwd + k_hrev",
-               "select": "k_wta_finalize2 + k_lrcheck", "post": "k_median3 + k_cc_*", "points": "k_depth + k_labels + k_moving_mask",
+               "select": "k_select_fused (records -> L-R check -> median -> band-local speckle components)", "post": "k_cc_merge_bands + k_cc_count_roots + k_cc_apply_bands", "points": "k_depth + k_labels + k_moving_mask",
                "fuse": "k_points_fuse" if world == 1 else "k_points_p2p + barrier + k_fuse_list"}
     dom = max(stage, key=stage.get)
     achieved = ab[dom] * B / (stage[dom] * 1e-3) / 1e9
