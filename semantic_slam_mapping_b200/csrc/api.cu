@@ -44,11 +44,22 @@ static int validate(const ssm_params& p)
     return SSM_OK;
 }
 
+// Disparities per column of the cost-volume layout.  D = 80 (the reference's src/stereo.cpp:18), 96, 112 run on the D = 128
+// kernels and D = 48 on the D = 64 ones: the lanes above D are switched off, their cells are computed but never read.
+static int layout_disparities(const ssm_ctx* c, int D)
+{
+    if (c->no_pad || c->force_legacy_cost || c->force_legacy_hsweep || c->force_legacy_vertical) return D;
+    if (D > 64 && D < 128) return 128;
+    if (D > 32 && D < 64) return 64;
+    return D;
+}
+
 static void fill_dev_params(ssm_ctx* c, int w, int h)
 {
     const ssm_params& p = c->p;
     DevParams& d = c->dp;
     d.W = w; d.H = h; d.D = p.num_disparities; d.W1 = w - p.num_disparities;
+    d.Dl = layout_disparities(c, d.D);
     d.bs = p.block_size;
     d.P1 = p.p1 > 0 ? p.p1 : 2;
     d.P2 = std::max(p.p2 > 0 ? p.p2 : 5, d.P1 + 1);
@@ -179,12 +190,12 @@ static int run_map(ssm_ctx* c, int B, const int16_t* d_disp, const uint8_t* d_se
 static void offset_buffers(ssm_ctx* c, ptrdiff_t frames)
 {
     const ptrdiff_t npix = (ptrdiff_t)c->dp.W * c->dp.H * frames;
-    const ptrdiff_t cells = (ptrdiff_t)c->dp.W1 * c->dp.H * c->dp.D * frames;
+    const ptrdiff_t cells = (ptrdiff_t)c->dp.W1 * c->dp.H * c->dp.Dl * frames;
     c->d_recL += npix; c->d_recR += npix;
     c->d_C += cells; c->d_S += cells; c->d_hs += cells;
     c->d_disp_raw += npix; c->d_disp_lr += npix; c->d_disp_med += npix; c->d_disp += npix;
     c->d_disp2key += npix; c->d_wta_rec += 2 * npix; c->d_cc_label += npix;
-    if (c->d_ck) c->d_ck += (ptrdiff_t)hsweep2_ck_words(c->dp.W1, c->dp.D, c->dp.H, 1) * frames; c->d_cc_size += npix;
+    if (c->d_ck) c->d_ck += (ptrdiff_t)hsweep2_ck_words(c->dp.W1, c->dp.Dl, c->dp.H, 1) * frames; c->d_cc_size += npix;
     c->d_depth += npix; c->d_label += npix; c->d_mask += npix;
     c->d_min_disp += frames;
 }
@@ -379,7 +390,7 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
         for (int t = 0; t < 4; ++t) {
             const std::string name = "SSM_TUNE" + std::to_string(t);
             const char* v = getenv(name.c_str());
-            static const int defaults[4] = {2 /* vertical: L2 prefetch distance in rows */, 0 /* hsweep: L2 prefetch off */, 0 /* fused selection: rows per band (0 = 8) */,
+            static const int defaults[4] = {2 /* vertical: L2 prefetch distance in rows */, 0 /* hsweep: L2 prefetch off */, 0 /* vertical kernel variant */,
                                              -1 /* sub-batch streams: automatic */};
             c->tune[t] = v ? atoi(v) : defaults[t];
         }
@@ -389,6 +400,10 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
         c->force_legacy_cost = lc && lc[0] == '1';
         const char* ls = getenv("SSM_LEGACY_SELECT");
         c->force_legacy_select = ls && ls[0] == '1';
+        const char* np = getenv("SSM_NO_PAD");
+        c->no_pad = np && np[0] == '1';
+        const char* sr = getenv("SSM_SELECT_ROWS");
+        if (sr && atoi(sr) > 0) c->select_rows = atoi(sr);
         const char* m = getenv("SSM_MAX_CLUSTER");
         if (m && atoi(m) > 0) c->max_cluster = atoi(m);
         const char* n = getenv("SSM_MIN_CLUSTER");
@@ -396,7 +411,7 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
     }
     c->cap_w = p->max_width; c->cap_h = p->max_height; c->cap_b = p->max_batch;
     const size_t npix = (size_t)c->cap_w * c->cap_h * c->cap_b;
-    const size_t ncell = (size_t)(c->cap_w - p->num_disparities) * c->cap_h * c->cap_b * p->num_disparities;
+    const size_t ncell = (size_t)(c->cap_w - p->num_disparities) * c->cap_h * c->cap_b * layout_disparities(c, p->num_disparities);
     uint64_t slots = 1024;
     while (slots < p->map_capacity) slots <<= 1;
     c->table_slots = slots;
@@ -412,7 +427,7 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
     A(dalloc(&c->d_disp_raw, npix)); A(dalloc(&c->d_disp_lr, npix)); A(dalloc(&c->d_disp_med, npix)); A(dalloc(&c->d_disp, npix));
     A(dalloc(&c->d_disp2key, npix)); A(dalloc(&c->d_wta_rec, npix * 2));
     if (p->num_disparities <= 128)
-        A(dalloc(&c->d_ck, hsweep2_ck_words(c->cap_w - p->num_disparities, p->num_disparities, c->cap_h, c->cap_b))); A(dalloc(&c->d_uniq_thr, (size_t)32768)); A(dalloc(&c->d_cc_label, npix)); A(dalloc(&c->d_cc_size, npix));
+        A(dalloc(&c->d_ck, hsweep2_ck_words(c->cap_w - p->num_disparities, layout_disparities(c, p->num_disparities), c->cap_h, c->cap_b))); A(dalloc(&c->d_uniq_thr, (size_t)32768)); A(dalloc(&c->d_cc_label, npix)); A(dalloc(&c->d_cc_size, npix));
     A(dalloc(&c->d_depth, npix)); A(dalloc(&c->d_label, npix)); A(dalloc(&c->d_mask, npix)); A(dalloc(&c->d_label_lut, (size_t)1 << 24));
     A(dalloc(&c->d_sem, npix * 3)); A(dalloc(&c->d_rgb, npix * 3));
     A(dalloc(&c->d_pose, (size_t)16 * c->cap_b)); A(dalloc(&c->d_min_disp, (size_t)c->cap_b));
@@ -537,19 +552,22 @@ int ssm_debug_copy_volume(ssm_ctx* c, int which, int bi, void* dst, size_t bytes
 {
     if (!c || !dst || bi < 0 || bi >= c->cap_b) return fail(SSM_ERR_INVALID_ARGUMENT, "bad argument");
     const DevParams& p = c->dp;
-    const size_t cells = (size_t)p.H * p.W1 * p.D, npix = (size_t)p.H * p.W;
+    const size_t cells = (size_t)p.H * p.W1 * p.D, lcells = (size_t)p.H * p.W1 * p.Dl, npix = (size_t)p.H * p.W;
     const void* src = nullptr;
     size_t need = 0;
     switch (which) {
-        case 0: src = c->d_C + cells * bi; need = cells * 2; break;
-        case 1: src = c->d_S + cells * bi; need = cells * 2; break;
+        case 0: src = c->d_C + lcells * bi; need = cells * 2; break;
+        case 1: src = c->d_S + lcells * bi; need = cells * 2; break;
         case 2: src = c->d_disp_lr + npix * bi; need = npix * 2; break;
         case 3: src = c->d_disp_med + npix * bi; need = npix * 2; break;
         default: return fail(SSM_ERR_INVALID_ARGUMENT, "unknown volume id");
     }
     if (bytes < need) return fail(SSM_ERR_INVALID_ARGUMENT, "destination too small");
     SSM_CUDA(cudaStreamSynchronize(c->stream));
-    SSM_CUDA(cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
+    if (which <= 1 && p.Dl != p.D)   // padded layout: the caller gets the D valid disparities of every column, densely packed
+        SSM_CUDA(cudaMemcpy2D(dst, (size_t)p.D * 2, src, (size_t)p.Dl * 2, (size_t)p.D * 2, (size_t)p.H * p.W1, cudaMemcpyDeviceToHost));
+    else
+        SSM_CUDA(cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
     return SSM_OK;
 }
 

@@ -17,7 +17,7 @@ namespace ssm {
 struct AggrArgs {
     const int16_t* C;
     uint16_t* S;
-    int W1, H, D;
+    int W1, H, D, Dl;   // D valid disparities, Dl disparities per column in the layout
     int P1, P2;
     int dir;       // 0: ->  1: down-right  2: down  3: down-left  4: <-
     int first;     // 1: S = L, 0: S = sat(S + L)
@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(256) k_aggr_path(AggrArgs a)
     const uint32_t P1w = (uint32_t)a.P1 * 0x10001u, P2w = (uint32_t)a.P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)a.P2) * 0x10001u;
     const size_t frame = (size_t)b * a.H * a.W1;
-    const ptrdiff_t stride = ((ptrdiff_t)dy * a.W1 + dx) * a.D;
-    size_t off = (frame + (size_t)y * a.W1 + x) * a.D + d0;
+    const ptrdiff_t stride = ((ptrdiff_t)dy * a.W1 + dx) * a.Dl;
+    size_t off = (frame + (size_t)y * a.W1 + x) * a.Dl + d0;
 
     uint32_t L[NR], Cw[NR], Cn[NR];
 #pragma unroll
@@ -94,8 +94,8 @@ int launch_aggregate_vertical(ssm_ctx* c, int B, cudaStream_t s)
 {
     const DevParams& p = c->dp;
     AggrArgs a;
-    a.C = c->d_C; a.S = c->d_S; a.W1 = p.W1; a.H = p.H; a.D = p.D; a.P1 = p.P1; a.P2 = p.P2; a.one = 1u;
-    const int nr = p.D <= 64 ? 1 : (p.D <= 128 ? 2 : (p.D <= 256 ? 4 : 8));
+    a.C = c->d_C; a.S = c->d_S; a.W1 = p.W1; a.H = p.H; a.D = p.D; a.Dl = p.Dl; a.P1 = p.P1; a.P2 = p.P2; a.one = 1u;
+    const int nr = p.Dl <= 64 ? 1 : (p.Dl <= 128 ? 2 : (p.Dl <= 256 ? 4 : 8));
     // preferred: all three top-down directions in one cluster launch (sgbm_vertical.cu)
     bool done = false;
     int rc = launch_vertical(c, B, s, &done);

@@ -297,13 +297,15 @@ struct CostGeom {
 
 template <int TX, int RAD /* block_size / 2, or -1: run-time radius (slow generic window sums) */>
 __global__ void __launch_bounds__(256, 2) k_cost_fused(const uint2* __restrict__ recL, const uint2* __restrict__ recR,
-                                                       int16_t* __restrict__ C, int W, int H, int radius, int band_rows,
+                                                       int16_t* __restrict__ C, int W, int H, int Dv /* valid disparities <= D: the image geometry */,
+                                                       int radius, int band_rows,
                                                        uint32_t mone /* 0xffffffff, opaque: x * mone + K is one IMAD */)
 {
     using G = CostGeom<TX>;
     constexpr int D = G::D, WPP = G::WPP, TW = G::TW, PS = G::PS, LPP = G::LPP, WPL = G::WPL;
     extern __shared__ __align__(16) uint32_t smem[];
-    const int W1 = W - D;
+    const int W1 = W - Dv;                           // D is the layout (words per column); disparities >= Dv are computed from
+                                                     // whatever lies left of the image (zeros) and never read by the aggregation kernels
     const int t0 = blockIdx.x * TX, b = blockIdx.z;
     const int y0 = blockIdx.y * band_rows, y1 = min(H, y0 + band_rows);
     const int e_lo = max(t0 - radius, 0), e_hi = min(t0 + TX - 1 + radius, W1 - 1);
@@ -335,12 +337,12 @@ __global__ void __launch_bounds__(256, 2) k_cost_fused(const uint2* __restrict__
 #pragma unroll
         for (int k = 0; k < G::RPT; ++k) {
             const int i = threadIdx.x + k * 256;
-            if (i < n_r) qr[k] = recR[rowbase + (e_hi + D - i)];
+            if (i < n_r) qr[k] = e_hi + Dv - i >= 0 ? recR[rowbase + (e_hi + Dv - i)] : make_uint2(0u, 0u);
         }
 #pragma unroll
         for (int k = 0; k < G::LPT; ++k) {
             const int i = threadIdx.x + k * 256;
-            if (i < n_e) ql[k] = recL[rowbase + (e_lo + i + D)];
+            if (i < n_e) ql[k] = recL[rowbase + (e_lo + i + Dv)];
         }
     };
     const int j_begin = y0 - radius, j_end = y1 + radius;
@@ -530,7 +532,7 @@ __global__ void __launch_bounds__(256, 2) k_cost_fused(const uint2* __restrict__
 // ------------------------------------------------------------------------------------------------
 static bool use_fused_cost(const ssm_ctx* c)
 {
-    const int D = c->dp.D;
+    const int D = c->dp.Dl;
     return !c->force_legacy_cost && (D == 16 || D == 32 || D == 64 || D == 128 || D == 256 || D == 512);
 }
 
@@ -566,7 +568,7 @@ static int launch_cost_fused_t(ssm_ctx* c, int B, cudaStream_t s)
     const int band_rows = (p.H + bands - 1) / bands;
     bands = (p.H + band_rows - 1) / band_rows;
     dim3 grid(tiles, bands, B);
-    k_cost_fused<TX, RAD><<<grid, 256, smem, s>>>(reinterpret_cast<const uint2*>(c->d_recL), reinterpret_cast<const uint2*>(c->d_recR), c->d_C, p.W, p.H, radius, band_rows, 0xffffffffu);
+    k_cost_fused<TX, RAD><<<grid, 256, smem, s>>>(reinterpret_cast<const uint2*>(c->d_recL), reinterpret_cast<const uint2*>(c->d_recR), c->d_C, p.W, p.H, p.D, radius, band_rows, 0xffffffffu);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }
@@ -577,7 +579,7 @@ int launch_cost_volume(ssm_ctx* c, int B, cudaStream_t s)
     if (use_fused_cost(c)) {
         // TX * D/2 = 2048 words per CTA row
         const bool r5 = p.bs == 11;   // the reference's block size gets the compile-time window; others the generic one
-        switch (p.D) {
+        switch (p.Dl) {
             case 16: return r5 ? launch_cost_fused_t<256, 5>(c, B, s) : launch_cost_fused_t<256, -1>(c, B, s);
             case 32: return r5 ? launch_cost_fused_t<128, 5>(c, B, s) : launch_cost_fused_t<128, -1>(c, B, s);
             case 64: return r5 ? launch_cost_fused_t<64, 5>(c, B, s) : launch_cost_fused_t<64, -1>(c, B, s);

@@ -60,8 +60,8 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
 // are fully unrolled, so every shared-memory load has an immediate offset and the loop carries no address arithmetic.
 // Only full blocks are walked: the last block of a row is never needed as a checkpoint source.
 template <int NR, bool FULL /* D == 64 * NR: every lane owns disparities */>
-__global__ void __launch_bounds__(128) k_hfwd(const int16_t* __restrict__ C, uint32_t* __restrict__ ck, int W1, int D, int P1, int P2,
-                                              int nrows, int nb, uint32_t one)
+__global__ void __launch_bounds__(128) k_hfwd(const int16_t* __restrict__ C, uint32_t* __restrict__ ck, int W1, int D /* layout */, int P1, int P2,
+                                              int nrows, int nb, uint32_t one, int Dv /* valid disparities <= D */)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) k_hfwd(const int16_t* __restrict__ C, uin
     if (row >= nrows) return;
     constexpr int LW = 32 * NR;
     const int d0 = lane * 2 * NR;
-    const bool active = FULL || d0 < D;
+    const bool active = FULL || d0 < Dv;
     const PathLane pl = make_path_lane(lane, one, (uint32_t)P1);
     const uint32_t P1w = (uint32_t)P1 * 0x10001u, P2w = (uint32_t)P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)P2) * 0x10001u;
@@ -126,7 +126,7 @@ struct HrevArgs {
     const uint16_t* Sv;
     const uint32_t* ck;
     uint4* rec;
-    int W1, D, P1, P2, nrows, nb;
+    int W1, D, Dv, P1, P2, nrows, nb;   // D: disparities per column in the layout, Dv <= D: valid ones
     uint32_t one;
     // uniqueness threshold thr = min(umulhi(minS * mul + add, magic), 32768): exact ceil(minS * 100 / (100 - ratio)) with
     // magic = ceil(2^32 / den) (floor(n / den) == umulhi(n, magic) for n < 2^32 / den); see the launcher for ratio >= 100
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128) k_hrev(const HrevArgs a)
 
     constexpr int LW = 32 * NR;
     const int d0 = lane * 2 * NR;
-    const bool active = FULL || d0 < D;
+    const bool active = FULL || d0 < a.Dv;
     const PathLane pl = make_path_lane(lane, a.one, (uint32_t)a.P1);
     const uint32_t P1w = (uint32_t)a.P1 * 0x10001u, P2w = (uint32_t)a.P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)a.P2) * 0x10001u;
@@ -291,7 +291,7 @@ size_t hsweep2_ck_words(int W1, int D, int H, int B)
     return (size_t)B * H * nb * (32 * NR + 32);
 }
 
-bool hsweep2_supported(const ssm_ctx* c) { return c->dp.D <= 128 && !c->force_legacy_hsweep && c->d_ck != nullptr; }
+bool hsweep2_supported(const ssm_ctx* c) { return c->dp.Dl <= 128 && !c->force_legacy_hsweep && c->d_ck != nullptr; }
 
 template <int NR>
 static int launch_hsweep2_t(ssm_ctx* c, int B, cudaStream_t s)
@@ -302,19 +302,19 @@ static int launch_hsweep2_t(ssm_ctx* c, int B, cudaStream_t s)
     const int wpb = 4;
     const unsigned grid = (unsigned)((nrows + wpb - 1) / wpb);
     if (nb > 1) {
-        const size_t smem_f = (size_t)wpb * 2 * kBlk * p.D * 2 + wpb * 16;
+        const size_t smem_f = (size_t)wpb * 2 * kBlk * p.Dl * 2 + wpb * 16;
         if (p.D == 64 * NR) {
             SSM_CUDA(cudaFuncSetAttribute(k_hfwd<NR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-            k_hfwd<NR, true><<<grid, wpb * 32, smem_f, s>>>(c->d_C, c->d_ck, p.W1, p.D, p.P1, p.P2, nrows, nb, 1u);
+            k_hfwd<NR, true><<<grid, wpb * 32, smem_f, s>>>(c->d_C, c->d_ck, p.W1, p.Dl, p.P1, p.P2, nrows, nb, 1u, p.D);
         } else {
             SSM_CUDA(cudaFuncSetAttribute(k_hfwd<NR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-            k_hfwd<NR, false><<<grid, wpb * 32, smem_f, s>>>(c->d_C, c->d_ck, p.W1, p.D, p.P1, p.P2, nrows, nb, 1u);
+            k_hfwd<NR, false><<<grid, wpb * 32, smem_f, s>>>(c->d_C, c->d_ck, p.W1, p.Dl, p.P1, p.P2, nrows, nb, 1u, p.D);
         }
         SSM_LAUNCH_CHECK(c);
     }
     HrevArgs a;
     a.C = c->d_C; a.Sv = c->d_S; a.ck = c->d_ck; a.rec = reinterpret_cast<uint4*>(c->d_wta_rec);
-    a.W1 = p.W1; a.D = p.D; a.P1 = p.P1; a.P2 = p.P2; a.nrows = nrows; a.nb = nb; a.one = 1u;
+    a.W1 = p.W1; a.D = p.Dl; a.Dv = p.D; a.P1 = p.P1; a.P2 = p.P2; a.nrows = nrows; a.nb = nb; a.one = 1u;
     if (p.uniq < 100) {   // thr = ceil(minS * 100 / den) = floor((minS * 100 + den - 1) / den)
         const uint32_t den = (uint32_t)(100 - p.uniq);
         a.uniq_mul = 100u; a.uniq_add = den - 1u;
@@ -323,7 +323,7 @@ static int launch_hsweep2_t(ssm_ctx* c, int B, cudaStream_t s)
     } else {              // thr = minS ? 32768 : 0  ==  min(floor(minS * 32768 / 1), 32768) with the division by 1 as umulhi(n << ..)
         a.uniq_mul = 65536u; a.uniq_add = 0u; a.uniq_magic = 0x80000000u;   // umulhi(minS << 16, 2^31) = minS << 15 >= 32768 for minS >= 1
     }
-    const size_t smem = (size_t)wpb * 2 * kBlk * p.D * 2 + wpb * 8;
+    const size_t smem = (size_t)wpb * 2 * kBlk * p.Dl * 2 + wpb * 8;
     if (p.D == 64 * NR) {
         SSM_CUDA(cudaFuncSetAttribute(k_hrev<NR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_hrev<NR, true><<<grid, wpb * 32, smem, s>>>(a);
@@ -337,7 +337,7 @@ static int launch_hsweep2_t(ssm_ctx* c, int B, cudaStream_t s)
 
 int launch_hsweep2(ssm_ctx* c, int B, cudaStream_t s)
 {
-    return c->dp.D <= 64 ? launch_hsweep2_t<1>(c, B, s) : launch_hsweep2_t<2>(c, B, s);
+    return c->dp.Dl <= 64 ? launch_hsweep2_t<1>(c, B, s) : launch_hsweep2_t<2>(c, B, s);
 }
 
 int launch_wta_finalize2(ssm_ctx* c, int B, cudaStream_t s)
@@ -346,7 +346,7 @@ int launch_wta_finalize2(ssm_ctx* c, int B, cudaStream_t s)
     const size_t total = (size_t)B * p.H * p.W1;
     const unsigned grid = (unsigned)((total + 255) / 256);
     const uint4* rec = reinterpret_cast<const uint4*>(c->d_wta_rec);
-    if (p.D <= 64) k_wta_finalize2<1><<<grid, 256, 0, s>>>(rec, c->d_disp_raw, c->d_disp2key, p.W, p.D, total);
+    if (p.Dl <= 64) k_wta_finalize2<1><<<grid, 256, 0, s>>>(rec, c->d_disp_raw, c->d_disp2key, p.W, p.D, total);
     else k_wta_finalize2<2><<<grid, 256, 0, s>>>(rec, c->d_disp_raw, c->d_disp2key, p.W, p.D, total);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;

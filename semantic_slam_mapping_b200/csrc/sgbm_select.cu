@@ -494,7 +494,7 @@ static int select_fused_rows(const ssm_ctx* c, size_t* smem_out)
     // index / d as one multiply-high needs d >= 2 and index * d < 2^32 for every index formed (at most (R + 2) * W + 2 * 512)
     if (c->force_legacy_select || !hsweep2_supported(c) || p.W1 < 2 || p.W > 8192) return 0;
     const int WS = (p.W + 4 + 1) & ~1;
-    const int first = c->tune[2] > 0 ? c->tune[2] : 8;
+    const int first = c->select_rows > 0 ? c->select_rows : 8;
     for (int R = first; R >= 1; R >>= 1) {
         const size_t smem = (size_t)(R + 2) * p.W * 4 + (size_t)(R + 2) * WS * 2 + (size_t)R * p.W * 2 + 16;
         if ((size_t)R * p.W < 65535 && smem <= (R > 1 ? 110u : 220u) * 1024u) {
@@ -530,7 +530,7 @@ int launch_select(ssm_ctx* c, int B, cudaStream_t s)
     const size_t npix = (size_t)B * p.H * p.W;
     size_t smem = 0;
     if (const int R = select_fused_rows(c, &smem))   // records -> L-R checked, median-filtered disparity + band-local speckle labels
-        return p.D <= 64 ? launch_select_fused_t<1>(c, B, R, smem, s) : launch_select_fused_t<2>(c, B, R, smem, s);
+        return p.Dl <= 64 ? launch_select_fused_t<1>(c, B, R, smem, s) : launch_select_fused_t<2>(c, B, R, smem, s);
     SSM_CUDA(cudaMemsetAsync(c->d_disp2key, 0xff, npix * sizeof(uint32_t), s));
     int rc = hsweep2_supported(c) ? launch_wta_finalize2(c, B, s) : launch_wta_finalize(c, B, s);
     if (rc) return rc;

@@ -76,7 +76,8 @@ __device__ __forceinline__ void st_async_word(uint32_t remote_addr, uint32_t v, 
 
 template <int NR, int NWARPS, bool FULL /* D == 2 * NR * LANES: every lane owns disparities */, int LANES = 32 /* lanes per column */>
 __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __restrict__ C, uint16_t* __restrict__ S, int W1, int H,
-                                                             int D, int P1, int P2, int T, uint32_t one, int pf_rows)
+                                                             int D /* disparities per column in the layout */, int P1, int P2, int T,
+                                                             uint32_t one, int pf_rows, int Dv /* valid disparities <= D */)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __r
     cluster.sync();
 
     const int d0 = lane * 2 * NR;
-    const bool active = FULL || d0 < D;
+    const bool active = FULL || d0 < Dv;
     const uint32_t P1w = (uint32_t)P1 * 0x10001u, P2w = (uint32_t)P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)P2) * 0x10001u;
     const PathLane pl = make_path_lane<LANES>((int)(threadIdx.x & 31), one, (uint32_t)P1);
@@ -302,7 +303,7 @@ static int launch_vertical_t(ssm_ctx* c, int B, const VerticalPlan& plan, cudaSt
         cudaGetLastError();      // this cluster shape cannot be co-scheduled on this device: fall back
         return SSM_OK;
     }
-    SSM_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int16_t*)c->d_C, c->d_S, p.W1, p.H, p.D, p.P1, p.P2, plan.T, 1u, c->tune[0]));
+    SSM_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int16_t*)c->d_C, c->d_S, p.W1, p.H, p.Dl, p.P1, p.P2, plan.T, 1u, c->tune[0], p.D));
     SSM_LAUNCH_CHECK(c);
     *done = true;
     return SSM_OK;
@@ -319,7 +320,7 @@ static size_t vertical_smem(int NR, int T)
 static bool plan_vertical(const ssm_ctx* c, VerticalPlan& plan)
 {
     const DevParams& p = c->dp;
-    const int NR = p.D <= 64 ? 1 : (p.D <= 128 ? 2 : (p.D <= 256 ? 4 : 8));
+    const int NR = p.Dl <= 64 ? 1 : (p.Dl <= 128 ? 2 : (p.Dl <= 256 ? 4 : 8));
     const size_t limit = 225 * 1024;
     for (int cs : {1, 2, 4, 8, 16}) {
         if (cs > c->max_cluster) break;
@@ -340,13 +341,14 @@ int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done)
     if (c->force_legacy_vertical) return SSM_OK;
     VerticalPlan plan;
     if (!plan_vertical(c, plan)) return SSM_OK;
-    const int D = c->dp.D;
-    const bool full = D == 64 || D == 128 || D == 256 || D == 512;
+    const int D = c->dp.Dl;                       // the layout picks the kernel; lanes at d >= dp.D are inactive (FULL = false)
+    const bool full = c->dp.D == D && (D == 64 || D == 128 || D == 256 || D == 512);
     if (D <= 64) return full ? launch_vertical_t<1, 32, true>(c, B, plan, s, done) : launch_vertical_t<1, 32, false>(c, B, plan, s, done);
     if (D <= 128) {
         // D == 128: two columns per warp (16 lanes x 4 words each) halve the per-column overhead of the recurrence
-        if (D == 128 && c->tune[2] == 0) return launch_vertical_t<4, 16, true, 16>(c, B, plan, s, done);
-        if (D == 128 && c->tune[2] == 2) return launch_vertical_t<4, 24, true, 16>(c, B, plan, s, done);
+        if (D == 128 && c->tune[2] == 0)
+            return full ? launch_vertical_t<4, 16, true, 16>(c, B, plan, s, done) : launch_vertical_t<4, 16, false, 16>(c, B, plan, s, done);
+        if (D == 128 && full && c->tune[2] == 2) return launch_vertical_t<4, 24, true, 16>(c, B, plan, s, done);
         if (full && c->tune[2] == 1) return launch_vertical_t<2, 24, true>(c, B, plan, s, done);
         return full ? launch_vertical_t<2, 32, true>(c, B, plan, s, done) : launch_vertical_t<2, 32, false>(c, B, plan, s, done);
     }

@@ -67,6 +67,8 @@ __host__ __device__ inline int voxel_owner(int i, int j, int k, int nranks)
 // device-side constants of one context
 struct DevParams {
     int W, H, D, W1;
+    int Dl;                                 // disparities per column in the C / S_v layout: D, or D padded to 64 / 128 so that the
+                                            // full-width kernels apply (lanes at d >= D are inactive; their cells are never read)
     int bs, P1, P2, uniq, d12, ftzero, speckle_win, speckle_diff;
     double cx, cy, fx, fy, baseline, scale, roix, roiy, roiz, max_depth_units;
     float inv_leaf;
@@ -100,6 +102,8 @@ struct ssm_ctx {
     bool force_legacy_hsweep = false;     // SSM_LEGACY_HSWEEP=1: one-kernel horizontal sweep (S_f through HBM) instead of checkpointed recomputation
     bool force_legacy_cost = false;       // SSM_LEGACY_COST=1: k_pix_hsum + k_vsum instead of the fused cost kernel
     bool force_legacy_vertical = false;   // SSM_LEGACY_VERTICAL=1: per-direction kernels instead of the cluster kernel
+    bool no_pad = false;                  // SSM_NO_PAD=1: keep the cost-volume layout at exactly D disparities per column
+    int select_rows = 0;                  // SSM_SELECT_ROWS: rows per band of the fused selection kernel (0 = 8)
     bool force_legacy_select = false;     // SSM_LEGACY_SELECT=1: finalize / L-R check / median / speckle as separate kernels instead of the fused band kernel
     cudaStream_t stream = nullptr;
     // sub-batch streams of the split pipeline (SSM_TUNE3 = number of concurrent sub-batches): kernels bound by different

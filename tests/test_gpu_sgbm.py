@@ -216,7 +216,7 @@ def test_cityscapes_width_256_disparities_band():
 def test_fused_selection_band_heights(monkeypatch, rows, H, W, D, seed):
     """Fused selection kernel (records -> L-R check -> median -> band-local speckle components) for several band
     heights: odd widths, bands that do not divide H, components that cross several band borders."""
-    monkeypatch.setenv("SSM_TUNE2", str(rows))
+    monkeypatch.setenv("SSM_SELECT_ROWS", str(rows))
     L, R, _ = synth.stereo_pair(H, W, D, seed)
     rng = np.random.default_rng(seed)
     R = np.clip(R.astype(int) + rng.integers(-10, 11, R.shape), 0, 255).astype(np.uint8)   # speckles and rejected pixels
@@ -247,3 +247,33 @@ def test_legacy_separate_selection_kernels_still_exact(monkeypatch):
     p = _params(128, 300, 64)
     with Context(p) as ctx:
         assert int((ctx.sgbm(L, R) != oracle.sgbm(L, R, _oparams(p))).sum()) == 0
+
+
+@pytest.mark.parametrize("no_pad", [False, True])
+@pytest.mark.parametrize("H,W,D,seed", [(60, 330, 80, 131), (45, 260, 96, 132), (38, 300, 112, 133), (52, 180, 48, 134)])
+def test_padded_disparity_layouts(monkeypatch, no_pad, H, W, D, seed):
+    """D = 80 (the reference's src/stereo.cpp:18), 96, 112 run on the 128-disparity kernels and D = 48 on the 64-disparity
+    ones (lanes at d >= D switched off); SSM_NO_PAD=1 keeps the exact-D layout.  Both bit-exact, volumes included."""
+    if no_pad:
+        monkeypatch.setenv("SSM_NO_PAD", "1")
+    L, R, _ = synth.stereo_pair(H, W, D, seed)
+    p = _params(D, W, H)
+    want, vols = oracle.sgbm(L, R, _oparams(p), want_volumes=True)
+    with Context(p) as ctx:
+        got = ctx.sgbm(L, R)
+        C = ctx.debug_volume("C", W, H)
+        Sv = ctx.debug_volume("S", W, H)
+    assert int((C != vols["C"]).sum()) == 0, "matching cost"
+    assert int((Sv != vols["Sv"]).sum()) == 0 or int((Sv != vols["Sf"]).sum()) == 0, "aggregated cost"
+    assert int((got != want).sum()) == 0
+
+
+def test_padded_layout_batched_frames():
+    """Batched frames through the whole pipeline at the reference's D = 80 (padded layout, sub-batch offsets in layout cells)."""
+    H, W, D, B = 40, 210, 80, 3
+    seq = synth.sequence(B, H, W, D, 12, seed=141)
+    p = _params(D, W, H, max_batch=B, map_capacity=1 << 16)
+    with Context(p) as ctx:
+        _, got = ctx.pipeline_batch_host(seq["left"], seq["right"], seq["semantic"], seq["rgb"], seq["pose"], want_disp=True)
+    for i in range(B):
+        assert int((got[i] != oracle.sgbm(seq["left"][i], seq["right"][i], _oparams(p))).sum()) == 0
