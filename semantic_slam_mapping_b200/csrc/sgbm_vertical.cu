@@ -343,7 +343,13 @@ int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done)
     if (!plan_vertical(c, plan)) return SSM_OK;
     const int D = c->dp.Dl;                       // the layout picks the kernel; lanes at d >= dp.D are inactive (FULL = false)
     const bool full = c->dp.D == D && (D == 64 || D == 128 || D == 256 || D == 512);
-    if (D <= 64) return full ? launch_vertical_t<1, 32, true>(c, B, plan, s, done) : launch_vertical_t<1, 32, false>(c, B, plan, s, done);
+    if (D <= 64) {
+        // D == 64 / 32: two columns per warp as well (16 lanes x 2 words / x 1 word); SSM_TUNE2=3 keeps one column per warp
+        if (D == 64 && c->tune[2] != 3)
+            return full ? launch_vertical_t<2, 16, true, 16>(c, B, plan, s, done) : launch_vertical_t<2, 16, false, 16>(c, B, plan, s, done);
+        if (D == 32 && c->tune[2] != 3) return launch_vertical_t<1, 16, true, 16>(c, B, plan, s, done);
+        return full ? launch_vertical_t<1, 32, true>(c, B, plan, s, done) : launch_vertical_t<1, 32, false>(c, B, plan, s, done);
+    }
     if (D <= 128) {
         // D == 128: two columns per warp (16 lanes x 4 words each) halve the per-column overhead of the recurrence
         if (D == 128 && c->tune[2] == 0)
