@@ -133,8 +133,8 @@ struct HrevArgs {
     uint32_t uniq_mul, uniq_add, uniq_magic;
 };
 
-template <int NR, bool FULL>
-__global__ void __launch_bounds__(128) k_hrev(const HrevArgs a)
+template <int NR, bool FULL, int MINB = 5 /* CTAs per SM the register budget is cut for: 5 -> 96 registers, 6 -> 80 (no spills) */>
+__global__ void __launch_bounds__(128, MINB) k_hrev(const HrevArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -324,13 +324,15 @@ static int launch_hsweep2_t(ssm_ctx* c, int B, cudaStream_t s)
         a.uniq_mul = 65536u; a.uniq_add = 0u; a.uniq_magic = 0x80000000u;   // umulhi(minS << 16, 2^31) = minS << 15 >= 32768 for minS >= 1
     }
     const size_t smem = (size_t)wpb * 2 * kBlk * p.Dl * 2 + wpb * 8;
-    if (p.D == 64 * NR) {
-        SSM_CUDA(cudaFuncSetAttribute(k_hrev<NR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hrev<NR, true><<<grid, wpb * 32, smem, s>>>(a);
-    } else {
-        SSM_CUDA(cudaFuncSetAttribute(k_hrev<NR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hrev<NR, false><<<grid, wpb * 32, smem, s>>>(a);
-    }
+    auto go = [&](auto kern) -> int {
+        SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, wpb * 32, smem, s>>>(a);
+        return SSM_OK;
+    };
+    int rc;
+    if (p.D == 64 * NR) rc = c->tune[1] == 5 ? go(k_hrev<NR, true, 5>) : go(k_hrev<NR, true, 6>);   // 80 registers: six CTAs per SM (SSM_TUNE1=5: 96 registers, five)
+    else rc = go(k_hrev<NR, false>);
+    if (rc) return rc;
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }
