@@ -209,9 +209,19 @@ __global__ void __launch_bounds__(256) k_vsum(const uint16_t* __restrict__ hs, i
 // values fit a byte: Sobel channel in [0, 126], raw channel in [0, 255]).  One thread makes 4 consecutive pixels
 // from one 8 x 3 pixel neighbourhood; both images in one launch.
 // ------------------------------------------------------------------------------------------------
+// 8 consecutive bytes starting at byte address `a` of a 4-byte aligned array, from three aligned 32-bit loads
+__device__ __forceinline__ uint2 load8_unaligned(const uint8_t* __restrict__ base, size_t a)
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (a >> 2);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    const uint32_t sh = (uint32_t)(a & 3) * 8u;
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+__device__ __forceinline__ int byte_of(const uint2& v, int i) { return (int)(((i < 4 ? v.x : v.y) >> (8 * (i & 3))) & 0xffu); }
+
 __global__ void __launch_bounds__(256) k_prefilter8(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right,
                                                     uint2* __restrict__ recL, uint2* __restrict__ recR, int W, int H, int ftzero,
-                                                    int quads_per_row, size_t total_quads)
+                                                    int quads_per_row, size_t total_quads, int aligned4 /* both images 4-byte aligned */)
 {
     const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= total_quads) return;
@@ -221,10 +231,36 @@ __global__ void __launch_bounds__(256) k_prefilter8(const uint8_t* __restrict__ 
     const int x0 = (int)(q % quads_per_row) * 4;
     const size_t row = q / quads_per_row;            // frame * H + y
     const int y = (int)(row % H);
-    const uint8_t* cur = img_all + row * (size_t)W;
-    const uint8_t* up = y > 0 ? cur - W : cur;
-    const uint8_t* dn = y < H - 1 ? cur + W : cur;
-    // columns x0 - 2 .. x0 + 5 of the three rows (clamped loads; out-of-range values are never used unclamped)
+    const size_t cur_o = row * (size_t)W;
+    const size_t up_o = y > 0 ? cur_o - W : cur_o, dn_o = y < H - 1 ? cur_o + W : cur_o;
+    int g[6], r[6];
+    // columns x0 - 2 .. x0 + 5 of the three rows
+    if (aligned4 && x0 >= 8 && x0 + 10 <= W) {
+        // interior quad: every byte (and the aligned words around them) lies inside the frame -- three aligned 32-bit loads and
+        // two funnel shifts per row instead of eight byte loads; no border column among x0 - 1 .. x0 + 4
+        const uint2 a = load8_unaligned(img_all, up_o + x0 - 2), b = load8_unaligned(img_all, cur_o + x0 - 2),
+                    c = load8_unaligned(img_all, dn_o + x0 - 2);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int sx = (byte_of(b, i + 2) - byte_of(b, i)) * 2 + (byte_of(a, i + 2) - byte_of(a, i)) + (byte_of(c, i + 2) - byte_of(c, i));
+            g[i] = max(-ftzero, min(ftzero, sx)) + ftzero;
+            r[i] = byte_of(b, i + 1);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ga = (g[i + 1] + g[i]) >> 1, gb = (g[i + 1] + g[i + 2]) >> 1;
+            const int ra = (r[i + 1] + r[i]) >> 1, rb = (r[i + 1] + r[i + 2]) >> 1;
+            const int glo = min(min(ga, gb), g[i + 1]), ghi = max(max(ga, gb), g[i + 1]);
+            const int rlo = min(min(ra, rb), r[i + 1]), rhi = max(max(ra, rb), r[i + 1]);
+            rec[cur_o + x0 + i] = make_uint2((uint32_t)g[i + 1] | ((uint32_t)glo << 8) | ((uint32_t)ghi << 16) | ((uint32_t)r[i + 1] << 24),
+                                             (uint32_t)rlo | ((uint32_t)rhi << 8));
+        }
+        return;
+    }
+    const uint8_t* cur = img_all + cur_o;
+    const uint8_t* up = img_all + up_o;
+    const uint8_t* dn = img_all + dn_o;
+    // border quads: clamped byte loads; out-of-range values are never used unclamped
     int a[8], b[8], c[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -232,7 +268,6 @@ __global__ void __launch_bounds__(256) k_prefilter8(const uint8_t* __restrict__ 
         a[i] = up[x]; b[i] = cur[x]; c[i] = dn[x];
     }
     // g[i], r[i] for columns x0 - 1 .. x0 + 4
-    int g[6], r[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         const int x = x0 - 1 + i;
@@ -544,7 +579,8 @@ int launch_prefilter(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, cu
         const size_t total_quads = (size_t)B * p.H * quads_per_row;
         dim3 grid((unsigned)((total_quads + 255) / 256), 2);
         k_prefilter8<<<grid, 256, 0, s>>>(dL, dR, reinterpret_cast<uint2*>(c->d_recL), reinterpret_cast<uint2*>(c->d_recR), p.W, p.H,
-                                          p.ftzero, quads_per_row, total_quads);
+                                          p.ftzero, quads_per_row, total_quads,
+                                          (int)(((reinterpret_cast<uintptr_t>(dL) | reinterpret_cast<uintptr_t>(dR)) & 3) == 0));
         SSM_LAUNCH_CHECK(c);
         return SSM_OK;
     }
