@@ -1,10 +1,13 @@
 // sgbm_select.cu -- disparity selection and post-filters, sm_100a.
 //
-// Replaces the tail of cv::StereoSGBM (called from /root/reference src/stereo.cpp:30):
-//   (winner-take-all itself is fused into the horizontal sweep, sgbm_hsweep.cu)
-//   k_lrcheck     left-right consistency (A-6); also writes the always-invalid columns [0, D)
-//   k_median3     cv::medianBlur(disp, 3) on int16 with replicate border
-//   k_cc_*        cv::filterSpeckles == connected components under |a-b| <= maxDiff; union-find with atomicMin
+// Replaces the tail of cv::StereoSGBM (called from /root/reference src/stereo.cpp:30); winner-take-all itself is fused
+// into the horizontal sweep (sgbm_hsweep2.cu / sgbm_hsweep.cu), which leaves one record per pixel.
+//   k_select_fused      records -> sub-pixel disparity + disp2 -> L-R check (A-6) -> cv::medianBlur(3) -> speckle components
+//                       inside a band of rows, all in shared memory (checkpointed-sweep record format, D <= 128)
+//   k_cc_merge_bands, k_cc_count_roots, k_cc_apply_bands
+//                       the rest of cv::filterSpeckles: join components across bands, total their sizes, filter
+//   k_lrcheck, k_median3, k_cc_init / merge / count / apply
+//                       the same steps as separate kernels through HBM (D > 128, SSM_LEGACY_SELECT=1); union-find with atomicMin
 #include "sgbm_wta.cuh"
 
 namespace ssm {
