@@ -223,15 +223,21 @@ __global__ void __launch_bounds__(256) k_moving_mask(const uint32_t* __restrict_
 // ------------------------------------------------------------------------------------------------
 // per-pixel point generation (mapper.cpp:22-86 + rgbdframe.h:63-75 + transformPointCloud)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool make_point_from(const DevParams& p, size_t idx, int d, int mask_v, int l, const uint8_t* __restrict__ sem,
+                                                const uint8_t* __restrict__ rgb, const double* __restrict__ pose, Point& out);
 __device__ __forceinline__ bool make_point(const DevParams& p, size_t idx, const uint16_t* __restrict__ depth, const uint8_t* __restrict__ label,
                                            const uint8_t* __restrict__ mask, const uint8_t* __restrict__ sem,
                                            const uint8_t* __restrict__ rgb, const double* __restrict__ pose, Point& out)
 {
-    const int d = depth[idx];
+    return make_point_from(p, idx, depth[idx], mask[idx], label[idx], sem, rgb, pose, out);
+}
+// the same with the pixel's depth / mask / label already in registers (callers that keep several pixels' loads in flight)
+__device__ __forceinline__ bool make_point_from(const DevParams& p, size_t idx, int d, int mask_v, int l, const uint8_t* __restrict__ sem,
+                                                const uint8_t* __restrict__ rgb, const double* __restrict__ pose, Point& out)
+{
     if (d == 0) return false;                                  // mapper.cpp:28
     if ((double)d > p.max_depth_units) return false;           // :30  d > max_distance * camera.scale
-    if (mask[idx] == 255) return false;                        // :32
-    const int l = label[idx];
+    if (mask_v == 255) return false;                           // :32
     if (l != SSM_LABEL_UNKNOWN && ((p.drop_mask >> l) & 1u)) return false;   // :41-55
     const int u = (int)(idx % p.W);
     const size_t r = idx / p.W;
@@ -259,58 +265,133 @@ __device__ __forceinline__ bool make_point(const DevParams& p, size_t idx, const
 }
 
 // ---- voxel hash insert -------------------------------------------------------------------------
-__device__ __forceinline__ void fuse_point(const DevParams& p, Voxel* __restrict__ table, uint64_t mask, const Point& pt, uint32_t* counters)
+// Warp-collective insert (every lane of a converged warp calls it; `ok` says whether the lane has a point).  Adjacent lanes
+// are adjacent pixels, and at map resolution several of them fall into the same voxel: lanes are grouped into runs of equal
+// keys, the run's sums are formed with segmented shuffles, and only the run's first lane probes the table and issues the
+// atomics -- the kernel is bound by the L2 atomic units, not by issue slots.  All accumulators are integers, so the table is
+// bit-identical to the point-by-point insert.
+__device__ __forceinline__ void fuse_point_warp(const DevParams& p, Voxel* __restrict__ table, uint64_t mask, const Point& pt, bool ok,
+                                                uint32_t* counters)
 {
-    if (!isfinite(pt.x) || !isfinite(pt.y) || !isfinite(pt.z)) return;   // cloud.is_dense == false (mapper.cpp:92)
-    // pcl::VoxelGrid: ijk = floor(coord * inverse_leaf_size) in fp32
-    const int i = (int)floorf(__fmul_rn(pt.x, p.inv_leaf));
-    const int j = (int)floorf(__fmul_rn(pt.y, p.inv_leaf));
-    const int k = (int)floorf(__fmul_rn(pt.z, p.inv_leaf));
-    if (i < -(1 << 20) || i >= (1 << 20) || j < -(1 << 20) || j >= (1 << 20) || k < -(1 << 20) || k >= (1 << 20)) {
-        atomicOr(&counters[2], 2u);   // coordinate outside the 21-bit key range
-        return;
+    const uint32_t full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned long long key = kEmptyKey;
+    unsigned long long fx = 0ull, fy = 0ull, fz = 0ull, col = 0ull;
+    if (ok && !(isfinite(pt.x) && isfinite(pt.y) && isfinite(pt.z))) ok = false;   // cloud.is_dense == false (mapper.cpp:92)
+    if (ok) {
+        // pcl::VoxelGrid: ijk = floor(coord * inverse_leaf_size) in fp32
+        const int i = (int)floorf(__fmul_rn(pt.x, p.inv_leaf));
+        const int j = (int)floorf(__fmul_rn(pt.y, p.inv_leaf));
+        const int k = (int)floorf(__fmul_rn(pt.z, p.inv_leaf));
+        if (i < -(1 << 20) || i >= (1 << 20) || j < -(1 << 20) || j >= (1 << 20) || k < -(1 << 20) || k >= (1 << 20)) {
+            atomicOr(&counters[2], 2u);   // coordinate outside the 21-bit key range
+            ok = false;
+        } else {
+            key = pack_key(i, j, k);
+            fx = (unsigned long long)__double2ll_rn(__dmul_rn((double)pt.x, kFixScale));
+            fy = (unsigned long long)__double2ll_rn(__dmul_rn((double)pt.y, kFixScale));
+            fz = (unsigned long long)__double2ll_rn(__dmul_rn((double)pt.z, kFixScale));
+            col = (unsigned long long)((pt.rgba >> 16) & 255u) | ((unsigned long long)((pt.rgba >> 8) & 255u) << 20) |
+                  ((unsigned long long)(pt.rgba & 255u) << 40);   // r, g, b in 20-bit fields: 32 lanes x 255 fits
+        }
     }
-    const unsigned long long key = pack_key(i, j, k);
-    uint64_t slot = mix64(key) & mask;
-    for (uint64_t probe = 0; probe <= mask; ++probe, slot = (slot + 1) & mask) {
-        Voxel* v = table + slot;
-        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&v->key);
-        if (cur == kEmptyKey) {
-            cur = atomicCAS(&v->key, kEmptyKey, key);
+    const uint32_t label = ok && pt.label < (uint32_t)p.num_labels ? pt.label : 0xffffffffu;
+    // segment starts: a lane without a point is a segment of its own, so runs never reach across it
+    const unsigned long long kprev = __shfl_up_sync(full, key, 1);
+    const uint32_t lprev = __shfl_up_sync(full, label, 1);
+    const bool head = ok && (lane == 0 || kprev != key);
+    const bool vhead = ok && (head || lprev != label);               // start of a run of equal (voxel, label)
+    const uint32_t bounds = __ballot_sync(full, head || !ok);
+    const uint32_t vbounds = __ballot_sync(full, vhead || !ok);
+    const uint32_t after = lane == 31 ? 0u : (bounds >> (lane + 1));
+    const int run_to = after ? lane + __ffs(after) - 1 : 31;          // last lane of my run
+    const uint32_t vafter = lane == 31 ? 0u : (vbounds >> (lane + 1));
+    const uint32_t vcount = (uint32_t)(vafter ? __ffs(vafter) : 32 - lane);
+    const int head_lane = 31 - __clz(bounds & (0xffffffffu >> (31 - lane)));   // first lane of my run (bit `lane` or below is set)
+    // segmented suffix sums by doubling; as many rounds as the longest run needs
+    const int longest = (int)__reduce_max_sync(full, head ? (uint32_t)(run_to - lane + 1) : 0u);
+    for (int s = 1; s < longest; s <<= 1) {
+        const unsigned long long ox = __shfl_down_sync(full, fx, s), oy = __shfl_down_sync(full, fy, s),
+                                 oz = __shfl_down_sync(full, fz, s), oc = __shfl_down_sync(full, col, s);
+        if (lane + s <= run_to) { fx += ox; fy += oy; fz += oz; col += oc; }
+    }
+    // the run's first lane finds (or claims) the voxel's slot
+    uint32_t slot32 = 0xffffffffu;
+    if (head) {
+        uint64_t slot = mix64(key) & mask;
+        for (uint64_t probe = 0; probe <= mask; ++probe, slot = (slot + 1) & mask) {
+            Voxel* v = table + slot;
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&v->key);
             if (cur == kEmptyKey) {
-                atomicAdd(&counters[1], 1u);
-                cur = key;
+                cur = atomicCAS(&v->key, kEmptyKey, key);
+                if (cur == kEmptyKey) {
+                    atomicAdd(&counters[1], 1u);
+                    cur = key;
+                }
+            }
+            if (cur == key) {
+                const unsigned long long n = (unsigned long long)(run_to - lane + 1);
+                atomicAdd(&v->sx, fx);
+                atomicAdd(&v->sy, fy);
+                atomicAdd(&v->sz, fz);
+                // (n, sr) and (sg, sb) are adjacent 32-bit fields on 8-byte boundaries: one 64-bit add each (no field can carry
+                // into its neighbour before 2^32 points / 2^24 points of full intensity)
+                atomicAdd(reinterpret_cast<unsigned long long*>(&v->n), n | ((col & 0xfffffull) << 32));
+                atomicAdd(reinterpret_cast<unsigned long long*>(&v->sg), ((col >> 20) & 0xfffffull) | (((col >> 40) & 0xfffffull) << 32));
+                slot32 = (uint32_t)slot;
+                break;
             }
         }
-        if (cur == key) {
-            atomicAdd(&v->sx, (unsigned long long)__double2ll_rn(__dmul_rn((double)pt.x, kFixScale)));
-            atomicAdd(&v->sy, (unsigned long long)__double2ll_rn(__dmul_rn((double)pt.y, kFixScale)));
-            atomicAdd(&v->sz, (unsigned long long)__double2ll_rn(__dmul_rn((double)pt.z, kFixScale)));
-            // (n, sr) and (sg, sb) are adjacent 32-bit fields on 8-byte boundaries: one 64-bit add each (no field can carry
-            // into its neighbour before 2^32 points / 2^24 points of full intensity)
-            atomicAdd(reinterpret_cast<unsigned long long*>(&v->n), 1ull | ((unsigned long long)((pt.rgba >> 16) & 255u) << 32));
-            atomicAdd(reinterpret_cast<unsigned long long*>(&v->sg), (unsigned long long)((pt.rgba >> 8) & 255u) | ((unsigned long long)(pt.rgba & 255u) << 32));
-            if (pt.label < (uint32_t)p.num_labels) atomicAdd(&v->votes[pt.label], 1u);
-            return;
-        }
+        if (slot32 == 0xffffffffu) atomicOr(&counters[2], 1u);   // table full
     }
-    atomicOr(&counters[2], 1u);   // table full
+    __syncwarp();
+    slot32 = __shfl_sync(full, slot32, head_lane);
+    if (vhead && label != 0xffffffffu && slot32 != 0xffffffffu) atomicAdd(&table[slot32].votes[label], vcount);
 }
 
-// FUSE mode: straight from pixels into the hash (single-GPU pipeline)
+// FUSE mode: straight from pixels into the hash (single-GPU pipeline).  The kernel waits on memory (the voxel records live
+// in a multi-GB table: every probe is a DRAM access), so a thread takes kPixPerThread pixels -- lane l of a warp takes pixels
+// l, l + 32, ... of the warp's span, so that adjacent lanes stay adjacent pixels -- with all their input loads, and then all
+// their table-line prefetches, in flight together before the first insert.
+constexpr int kPixPerThread = 4;
 __global__ void __launch_bounds__(256) k_points_fuse(const uint16_t* __restrict__ depth, const uint8_t* __restrict__ label,
                                                      const uint8_t* __restrict__ mask, const uint8_t* __restrict__ sem,
                                                      const uint8_t* __restrict__ rgb, const double* __restrict__ pose,
                                                      Voxel* __restrict__ table, uint64_t slot_mask, uint32_t* counters,
                                                      size_t total, SSM_DP)
 {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    Point pt;
-    const bool ok = idx < total && make_point(p, idx, depth, label, mask, sem, rgb, pose, pt);
-    if (ok) fuse_point(p, table, slot_mask, pt, counters);
+    const int lane = threadIdx.x & 31;
+    const size_t span = ((size_t)blockIdx.x * blockDim.x + (threadIdx.x - lane)) * kPixPerThread;   // first pixel of my warp
+    int d[kPixPerThread], m[kPixPerThread], l[kPixPerThread];
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) {
+        const size_t idx = span + k * 32 + lane;
+        const bool in = idx < total;
+        d[k] = in ? (int)depth[idx] : 0;
+        m[k] = in ? (int)mask[idx] : 0;
+        l[k] = in ? (int)label[idx] : 0;
+    }
+    Point pt[kPixPerThread];
+    bool ok[kPixPerThread];
+    uint32_t made = 0;
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) {
+        const size_t idx = span + k * 32 + lane;
+        ok[k] = idx < total && make_point_from(p, idx, d[k], m[k], l[k], sem, rgb, pose, pt[k]);
+        if (ok[k]) {
+            // warm the record's line (same slot computation as the insert; a prefetch of a wrong or unused line is harmless)
+            const int i = (int)floorf(__fmul_rn(pt[k].x, p.inv_leaf)), j = (int)floorf(__fmul_rn(pt[k].y, p.inv_leaf)),
+                      kk = (int)floorf(__fmul_rn(pt[k].z, p.inv_leaf));
+            const Voxel* v = table + (mix64(pack_key(i, j, kk)) & slot_mask);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(v));
+            ++made;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) fuse_point_warp(p, table, slot_mask, pt[k], ok[k], counters);
     // points of this call: one atomic per warp instead of one per point
-    const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
-    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&counters[0], (uint32_t)__popc(ballot));
+    made = __reduce_add_sync(0xffffffffu, made);
+    if (lane == 0 && made) atomicAdd(&counters[0], made);
 }
 
 // P2P mode (multi-GPU): straight from pixels; locally owned points go into this rank's hash, the others are appended
@@ -334,7 +415,7 @@ __global__ void __launch_bounds__(256) k_points_p2p(const uint16_t* __restrict__
         owner = voxel_owner(i, j, k, nranks);
         atomicAdd(&counters[0], 1u);
     }
-    if (owner == rank) fuse_point(p, table, slot_mask, pt, counters);
+    fuse_point_warp(p, table, slot_mask, pt, owner == rank, counters);
     // remote points: group the warp's lanes by owner
     uint32_t pending = __ballot_sync(0xffffffffu, owner >= 0 && owner != rank);
     while (pending) {
@@ -444,8 +525,13 @@ __global__ void __launch_bounds__(256) k_fuse_list(const Point* __restrict__ pts
                                                    uint32_t* counters, SSM_DP)
 {
     const uint32_t n = count ? min(*count, max_count) : max_count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        fuse_point(p, table, slot_mask, pts[i], counters);
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += gridDim.x * blockDim.x) {   // warp-uniform trips
+        const uint32_t i = base + lane;
+        Point pt = {};
+        if (i < n) pt = pts[i];
+        fuse_point_warp(p, table, slot_mask, pt, i < n, counters);
+    }
 }
 
 // Cached keyframe clouds (mapper.cpp:17-20 keeps frame->pointcloud in camera coordinates; :90-91 re-transforms it by
@@ -454,8 +540,11 @@ struct Pose12 { double m[12]; };
 __global__ void __launch_bounds__(256) k_transform_fuse(const Point* __restrict__ pts, uint32_t n, Pose12 T, Voxel* __restrict__ table,
                                                         uint64_t slot_mask, uint32_t* counters, SSM_DP)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Point pt = pts[i];
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += gridDim.x * blockDim.x) {   // warp-uniform trips
+        const uint32_t i = base + lane;
+        Point pt = {};
+        if (i < n) pt = pts[i];
         float w[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -466,7 +555,7 @@ __global__ void __launch_bounds__(256) k_transform_fuse(const Point* __restrict_
             w[k] = (float)acc;
         }
         pt.x = w[0]; pt.y = w[1]; pt.z = w[2];
-        fuse_point(p, table, slot_mask, pt, counters);
+        fuse_point_warp(p, table, slot_mask, pt, i < n, counters);
     }
 }
 
@@ -534,7 +623,7 @@ int launch_points(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t* d_s
     const size_t total = (size_t)p.W * p.H * B;
     SSM_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t), s));   // counters[0] = points of this call
     if (fuse_into_map) {
-        k_points_fuse<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_depth, c->d_label, c->d_mask, d_sem, d_rgb, d_pose,
+        k_points_fuse<<<(unsigned)((total + 256 * kPixPerThread - 1) / (256 * kPixPerThread)), 256, 0, s>>>(d_depth, c->d_label, c->d_mask, d_sem, d_rgb, d_pose,
                                                                       c->d_table, c->table_slots - 1, c->d_counters, total, p);
         SSM_LAUNCH_CHECK(c);
         return SSM_OK;
