@@ -349,6 +349,13 @@ __device__ __forceinline__ void fuse_point_warp(const DevParams& p, Voxel* __res
     if (vhead && label != 0xffffffffu && slot32 != 0xffffffffu) atomicAdd(&table[slot32].votes[label], vcount);
 }
 
+// L2 prefetch of the record a point's first probe will touch
+__device__ __forceinline__ void prefetch_voxel_line(const Voxel* __restrict__ table, uint64_t slot_mask, const Point& pt, float inv_leaf)
+{
+    const int i = (int)floorf(__fmul_rn(pt.x, inv_leaf)), j = (int)floorf(__fmul_rn(pt.y, inv_leaf)), k = (int)floorf(__fmul_rn(pt.z, inv_leaf));
+    const Voxel* v = table + (mix64(pack_key(i, j, k)) & slot_mask);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(v));
+}
 // FUSE mode: straight from pixels into the hash (single-GPU pipeline).  The kernel waits on memory (the voxel records live
 // in a multi-GB table: every probe is a DRAM access), so a thread takes kPixPerThread pixels -- lane l of a warp takes pixels
 // l, l + 32, ... of the warp's span, so that adjacent lanes stay adjacent pixels -- with all their input loads, and then all
@@ -379,11 +386,7 @@ __global__ void __launch_bounds__(256) k_points_fuse(const uint16_t* __restrict_
         const size_t idx = span + k * 32 + lane;
         ok[k] = idx < total && make_point_from(p, idx, d[k], m[k], l[k], sem, rgb, pose, pt[k]);
         if (ok[k]) {
-            // warm the record's line (same slot computation as the insert; a prefetch of a wrong or unused line is harmless)
-            const int i = (int)floorf(__fmul_rn(pt[k].x, p.inv_leaf)), j = (int)floorf(__fmul_rn(pt[k].y, p.inv_leaf)),
-                      kk = (int)floorf(__fmul_rn(pt[k].z, p.inv_leaf));
-            const Voxel* v = table + (mix64(pack_key(i, j, kk)) & slot_mask);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(v));
+            prefetch_voxel_line(table, slot_mask, pt[k], p.inv_leaf);   // same slot as the insert's first probe; a stray prefetch is harmless
             ++made;
         }
     }
@@ -395,8 +398,11 @@ __global__ void __launch_bounds__(256) k_points_fuse(const uint16_t* __restrict_
 }
 
 // P2P mode (multi-GPU): straight from pixels; locally owned points go into this rank's hash, the others are appended
-// to their owner's inbox through the peer mapping (NVLink stores; slots are reserved with one system-scope atomic per
-// (warp, owner) group).  The compute step (back-projection, transform) and the dispatch all-to-all are one kernel.
+// to their owner's inbox through the peer mapping (NVLink stores).  The compute step (back-projection, transform) and the
+// dispatch all-to-all are one kernel.  Inbox slots are reserved in two levels: the lanes of a warp that share an owner
+// take consecutive places in the CTA's block for that owner (shared-memory atomic, one per (warp, owner) group), and one
+// system-scope atomic per (CTA, owner) -- issued by nranks threads in parallel -- places the block in the peer's inbox:
+// one NVLink round trip per CTA instead of one per group in every warp.
 __global__ void __launch_bounds__(256) k_points_p2p(const uint16_t* __restrict__ depth, const uint8_t* __restrict__ label,
                                                     const uint8_t* __restrict__ mask, const uint8_t* __restrict__ sem,
                                                     const uint8_t* __restrict__ rgb, const double* __restrict__ pose,
@@ -404,39 +410,72 @@ __global__ void __launch_bounds__(256) k_points_p2p(const uint16_t* __restrict__
                                                     void* const* __restrict__ peer_base, int rank, int nranks, int parity,
                                                     uint32_t inbox_cap, size_t total, SSM_DP)
 {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t s_cnt[ssm_ctx::kMaxPeers], s_base[ssm_ctx::kMaxPeers];
     const int lane = threadIdx.x & 31;
-    Point pt;
-    int owner = -1;
-    if (idx < total && make_point(p, idx, depth, label, mask, sem, rgb, pose, pt) && isfinite(pt.x) && isfinite(pt.y) && isfinite(pt.z)) {
-        const int i = (int)floorf(__fmul_rn(pt.x, p.inv_leaf));
-        const int j = (int)floorf(__fmul_rn(pt.y, p.inv_leaf));
-        const int k = (int)floorf(__fmul_rn(pt.z, p.inv_leaf));
-        owner = voxel_owner(i, j, k, nranks);
-        atomicAdd(&counters[0], 1u);
+    if ((int)threadIdx.x < nranks) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    const size_t span = ((size_t)blockIdx.x * blockDim.x + (threadIdx.x - lane)) * kPixPerThread;   // first pixel of my warp
+    int d[kPixPerThread], m[kPixPerThread], l[kPixPerThread];
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) {
+        const size_t idx = span + k * 32 + lane;
+        const bool in = idx < total;
+        d[k] = in ? (int)depth[idx] : 0;
+        m[k] = in ? (int)mask[idx] : 0;
+        l[k] = in ? (int)label[idx] : 0;
     }
-    fuse_point_warp(p, table, slot_mask, pt, owner == rank, counters);
-    // remote points: group the warp's lanes by owner
-    uint32_t pending = __ballot_sync(0xffffffffu, owner >= 0 && owner != rank);
-    while (pending) {
-        const int leader = __ffs(pending) - 1;
-        const int o = __shfl_sync(0xffffffffu, owner, leader);
-        const uint32_t group = __ballot_sync(0xffffffffu, owner == o) & pending;
-        char* base = static_cast<char*>(peer_base[o]);
-        uint32_t slot0 = 0;
-        if (lane == leader) slot0 = atomicAdd_system(reinterpret_cast<uint32_t*>(base) + parity, (uint32_t)__popc(group));
-        slot0 = __shfl_sync(0xffffffffu, slot0, leader);
-        if ((group >> lane) & 1u) {
-            const uint32_t slot = slot0 + __popc(group & ((1u << lane) - 1u));
+    Point pt[kPixPerThread];
+    int owner[kPixPerThread];
+    uint32_t pos[kPixPerThread];
+    uint32_t made = 0;
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) {
+        const size_t idx = span + k * 32 + lane;
+        owner[k] = -1;
+        pos[k] = 0u;
+        if (idx < total && make_point_from(p, idx, d[k], m[k], l[k], sem, rgb, pose, pt[k]) && isfinite(pt[k].x) && isfinite(pt[k].y) &&
+            isfinite(pt[k].z)) {
+            const int i = (int)floorf(__fmul_rn(pt[k].x, p.inv_leaf));
+            const int j = (int)floorf(__fmul_rn(pt[k].y, p.inv_leaf));
+            const int kk = (int)floorf(__fmul_rn(pt[k].z, p.inv_leaf));
+            owner[k] = voxel_owner(i, j, kk, nranks);
+            ++made;
+            if (owner[k] == rank) prefetch_voxel_line(table, slot_mask, pt[k], p.inv_leaf);
+        }
+        // remote points: the warp's lanes with the same owner take consecutive places in the CTA's block for that owner
+        uint32_t pending = __ballot_sync(0xffffffffu, owner[k] >= 0 && owner[k] != rank);
+        while (pending) {
+            const int leader = __ffs(pending) - 1;
+            const int o = __shfl_sync(0xffffffffu, owner[k], leader);
+            const uint32_t group = __ballot_sync(0xffffffffu, owner[k] == o) & pending;
+            uint32_t p0 = 0u;
+            if (lane == leader) p0 = atomicAdd(&s_cnt[o], (uint32_t)__popc(group));
+            p0 = __shfl_sync(0xffffffffu, p0, leader);
+            if ((group >> lane) & 1u) pos[k] = p0 + __popc(group & ((1u << lane) - 1u));
+            pending &= ~group;
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nranks && (int)threadIdx.x != rank && s_cnt[threadIdx.x] != 0u)
+        s_base[threadIdx.x] = atomicAdd_system(reinterpret_cast<uint32_t*>(peer_base[threadIdx.x]) + parity, s_cnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) {
+        if (owner[k] >= 0 && owner[k] != rank) {
+            char* base = static_cast<char*>(peer_base[owner[k]]);
+            const uint32_t slot = s_base[owner[k]] + pos[k];
             if (slot < inbox_cap) {
                 Point* dst = reinterpret_cast<Point*>(base + kInboxHeader) + (size_t)parity * inbox_cap + slot;
-                *dst = pt;
+                *dst = pt[k];
             } else {
                 atomicOr_system(reinterpret_cast<uint32_t*>(base) + 2, 1u);
             }
         }
-        pending &= ~group;
     }
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) fuse_point_warp(p, table, slot_mask, pt[k], owner[k] == rank, counters);
+    made = __reduce_add_sync(0xffffffffu, made);
+    if (lane == 0 && made) atomicAdd(&counters[0], made);
 }
 
 // COMPACT mode (ordered, row-major like the reference's push_back loop): count per block, scan, scatter
@@ -526,11 +565,23 @@ __global__ void __launch_bounds__(256) k_fuse_list(const Point* __restrict__ pts
 {
     const uint32_t n = count ? min(*count, max_count) : max_count;
     const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += gridDim.x * blockDim.x) {   // warp-uniform trips
-        const uint32_t i = base + lane;
-        Point pt = {};
-        if (i < n) pt = pts[i];
-        fuse_point_warp(p, table, slot_mask, pt, i < n, counters);
+    // a warp takes 32 * kPixPerThread consecutive points per trip (warp-uniform trip count): loads, then table-line prefetches, then inserts
+    for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane)) * kPixPerThread; base < n;
+         base += (uint64_t)gridDim.x * blockDim.x * kPixPerThread) {
+        Point pt[kPixPerThread];
+        bool ok[kPixPerThread];
+#pragma unroll
+        for (int k = 0; k < kPixPerThread; ++k) {
+            const uint64_t i = base + k * 32 + lane;
+            ok[k] = i < n;
+            pt[k] = Point{};
+            if (ok[k]) pt[k] = pts[i];
+        }
+#pragma unroll
+        for (int k = 0; k < kPixPerThread; ++k)
+            if (ok[k]) prefetch_voxel_line(table, slot_mask, pt[k], p.inv_leaf);
+#pragma unroll
+        for (int k = 0; k < kPixPerThread; ++k) fuse_point_warp(p, table, slot_mask, pt[k], ok[k], counters);
     }
 }
 
@@ -645,7 +696,7 @@ int launch_points_p2p(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t*
     const DevParams& p = c->dp;
     const size_t total = (size_t)p.W * p.H * B;
     SSM_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t), s));
-    k_points_p2p<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_depth, c->d_label, c->d_mask, d_sem, d_rgb, d_pose, c->d_table,
+    k_points_p2p<<<(unsigned)((total + 256 * kPixPerThread - 1) / (256 * kPixPerThread)), 256, 0, s>>>(d_depth, c->d_label, c->d_mask, d_sem, d_rgb, d_pose, c->d_table,
                                                                  c->table_slots - 1, c->d_counters, d_peer_base, c->rank, c->nranks, parity,
                                                                  (uint32_t)c->inbox_cap, total, p);
     SSM_LAUNCH_CHECK(c);
