@@ -49,6 +49,7 @@ static int validate(const ssm_params& p)
 static int layout_disparities(const ssm_ctx* c, int D)
 {
     if (c->no_pad || c->force_legacy_cost || c->force_legacy_hsweep || c->force_legacy_vertical) return D;
+    if (D > 128 && D < 256) return 256;
     if (D > 64 && D < 128) return 128;
     if (D > 32 && D < 64) return 64;
     return D;
@@ -194,7 +195,7 @@ static void offset_buffers(ssm_ctx* c, ptrdiff_t frames)
     c->d_recL += npix; c->d_recR += npix;
     c->d_C += cells; c->d_S += cells; c->d_hs += cells;
     c->d_disp_raw += npix; c->d_disp_lr += npix; c->d_disp_med += npix; c->d_disp += npix;
-    c->d_disp2key += npix; c->d_wta_rec += 2 * npix; c->d_cc_label += npix;
+    c->d_disp2key += npix; c->d_wta_rec += (c->dp.Dl > 128 ? 4 : 2) * npix; c->d_cc_label += npix;
     if (c->d_ck) c->d_ck += (ptrdiff_t)hsweep2_ck_words(c->dp.W1, c->dp.Dl, c->dp.H, 1) * frames; c->d_cc_size += npix;
     c->d_depth += npix; c->d_label += npix; c->d_mask += npix;
     c->d_min_disp += frames;
@@ -425,8 +426,8 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
     A(dalloc(&c->d_C, ncell)); A(dalloc(&c->d_S, ncell));
     c->d_hs = c->d_S;   // horizontal sums are dead once C exists; S is written afterwards
     A(dalloc(&c->d_disp_raw, npix)); A(dalloc(&c->d_disp_lr, npix)); A(dalloc(&c->d_disp_med, npix)); A(dalloc(&c->d_disp, npix));
-    A(dalloc(&c->d_disp2key, npix)); A(dalloc(&c->d_wta_rec, npix * 2));
-    if (p->num_disparities <= 128)
+    A(dalloc(&c->d_disp2key, npix)); A(dalloc(&c->d_wta_rec, npix * (layout_disparities(c, p->num_disparities) > 128 ? 4 : 2)));   // 16-byte records, 32-byte ones for 256-disparity layouts
+    if (p->num_disparities <= 256)
         A(dalloc(&c->d_ck, hsweep2_ck_words(c->cap_w - p->num_disparities, layout_disparities(c, p->num_disparities), c->cap_h, c->cap_b))); A(dalloc(&c->d_uniq_thr, (size_t)32768)); A(dalloc(&c->d_cc_label, npix)); A(dalloc(&c->d_cc_size, npix));
     A(dalloc(&c->d_depth, npix)); A(dalloc(&c->d_label, npix)); A(dalloc(&c->d_mask, npix)); A(dalloc(&c->d_label_lut, (size_t)1 << 24));
     A(dalloc(&c->d_sem, npix * 3)); A(dalloc(&c->d_rgb, npix * 3));

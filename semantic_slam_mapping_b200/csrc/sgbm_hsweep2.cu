@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(128, MINB) k_hrev(const HrevArgs a)
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
-    constexpr int LOG_DPL = NR == 1 ? 1 : 2;     // log2(disparities per lane)
+    constexpr int LOG_DPL = NR == 1 ? 1 : (NR == 2 ? 2 : 3);     // log2(disparities per lane)
     const int D = a.D, W1 = a.W1;
     const uint32_t colbytes = (uint32_t)D * 2;   // one column of C / S_v
     const uint32_t blkbytes = colbytes * kBlk;
@@ -158,11 +158,11 @@ __global__ void __launch_bounds__(128, MINB) k_hrev(const HrevArgs a)
     const PathLane pl = make_path_lane(lane, a.one, (uint32_t)a.P1);
     const uint32_t P1w = (uint32_t)a.P1 * 0x10001u, P2w = (uint32_t)a.P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)a.P2) * 0x10001u;
-    const uint32_t lanemask = active ? (NR == 2 ? 0x80808080u : 0x00008080u) : 0u;
+    const uint32_t lanemask = active ? (NR >= 2 ? 0x80808080u : 0x00008080u) : 0u;   // per flag word (4 disparities)
     const uint8_t* Cg = reinterpret_cast<const uint8_t*>(a.C) + (size_t)row * W1 * colbytes;
     const uint8_t* Sg = reinterpret_cast<const uint8_t*>(a.Sv) + (size_t)row * W1 * colbytes;
     const uint32_t* ckrow = a.ck + (size_t)row * a.nb * (LW + 32);
-    uint4* rrow = a.rec + (size_t)row * W1;
+    uint4* rrow = a.rec + (size_t)row * W1 * WtaRec<NR>::kQuads;
     const uint32_t loff = (uint32_t)lane * NR * 4;   // this lane's words inside a column
     uint32_t cA = smem_addr(myC) + loff, sA = smem_addr(myS) + loff;   // shared-window addresses of this lane's words
     keep(cA); keep(sA);
@@ -242,20 +242,33 @@ __global__ void __launch_bounds__(128, MINB) k_hrev(const HrevArgs a)
             // flag byte per disparity: bit 7 set <=> S < thr.  (S + 0x8000 - thr never leaves its 16-bit half.)
             const uint32_t kt = 0x80008000u - thr * 0x10001u;
             uint32_t flags;
-            if constexpr (NR == 2) flags = __byte_perm(Sw[0] * pl.one + kt, Sw[1] * pl.one + kt, 0x7531);
+            if constexpr (NR >= 2) flags = __byte_perm(Sw[0] * pl.one + kt, Sw[1] * pl.one + kt, 0x7531);
             else flags = __byte_perm(Sw[0] * pl.one + kt, 0u, 0x4431);
             const uint32_t below = ~flags & lanemask;
             // bytes of [best - 1, best + 1] inside this lane: 0x808080 shifted by whole bytes (64-bit shift clamps to zero)
             const uint32_t k8 = (uint32_t)((int)d0 + 4 - (int)best) * 8u;  // 8 * (4 - rel), rel = best - d0; wraps huge when negative
             unsigned long long win;
             asm("shr.u64 %0, %1, %2;" : "=l"(win) : "l"(0x0000808080000000ull), "r"(k8));
-            const uint32_t outside = below & ~(uint32_t)win;
+            uint32_t outside = below & ~(uint32_t)win;
+            if constexpr (NR == 4) {   // the lane's second group of four disparities, d0 + 4 .. d0 + 7
+                const uint32_t flags1 = __byte_perm(Sw[2] * pl.one + kt, Sw[3] * pl.one + kt, 0x7531);
+                const uint32_t k81 = (uint32_t)((int)d0 + 8 - (int)best) * 8u;
+                unsigned long long win1;
+                asm("shr.u64 %0, %1, %2;" : "=l"(win1) : "l"(0x0000808080000000ull), "r"(k81));
+                outside |= ~flags1 & lanemask & ~(uint32_t)win1;
+            }
             const uint32_t reject = __any_sync(0xffffffffu, outside != 0u) ? 1u : 0u;
             // values across the lane borders, for the sub-pixel fit when the winner sits at a lane edge
             const uint32_t upv = __shfl_up_sync(0xffffffffu, Sw[NR - 1] >> 16, 1);
             const uint32_t dnv = __shfl_down_sync(0xffffffffu, Sw[0] & 0xffffu, 1);
-            if (lane == (int)(best >> LOG_DPL))
-                rrow[xs + i] = make_uint4(minS | (best << 16) | (reject << 31), Sw[0], NR == 2 ? Sw[NR - 1] : 0u, (upv & 0xffffu) | (dnv << 16));
+            if (lane == (int)(best >> LOG_DPL)) {
+                if constexpr (NR == 4) {
+                    rrow[2 * (xs + i)] = make_uint4(minS | (best << 16) | (reject << 31), Sw[0], Sw[1], Sw[2]);
+                    rrow[2 * (xs + i) + 1] = make_uint4(Sw[3], (upv & 0xffffu) | (dnv << 16), 0u, 0u);
+                } else {
+                    rrow[xs + i] = make_uint4(minS | (best << 16) | (reject << 31), Sw[0], NR == 2 ? Sw[NR - 1] : 0u, (upv & 0xffffu) | (dnv << 16));
+                }
+            }
         }
         };
         if (n == kBlk) walk(std::integral_constant<int, kBlk>{});
@@ -274,11 +287,12 @@ __global__ void __launch_bounds__(256) k_wta_finalize2(const uint4* __restrict__
     const int W1 = W - D;
     const int xp = (int)(idx % W1);
     const size_t row = idx / W1;
-    const uint4 r = rec[idx];
+    const uint4 r = rec[idx * WtaRec<NR>::kQuads];
+    const uint4 r2 = NR == 4 ? rec[idx * 2 + 1] : r;
     const int x = xp + D;
     int minS, best;
     bool valid;
-    const int out = wta2_decode<NR>(r, D, minS, best, valid);
+    const int out = wta2_decode<NR>(r, r2, D, minS, best, valid);
     if (valid) atomicMin(&disp2key[row * W + (x - best)], ((uint32_t)minS << 16) | (uint32_t)(0xffff - x));
     disp_raw[row * W + x] = (int16_t)out;
 }
@@ -286,12 +300,12 @@ __global__ void __launch_bounds__(256) k_wta_finalize2(const uint4* __restrict__
 // ------------------------------------------------------------------------------------------------
 size_t hsweep2_ck_words(int W1, int D, int H, int B)
 {
-    const int NR = D <= 64 ? 1 : 2;
+    const int NR = D <= 64 ? 1 : (D <= 128 ? 2 : 4);
     const int nb = (W1 + kBlk - 1) / kBlk;
     return (size_t)B * H * nb * (32 * NR + 32);
 }
 
-bool hsweep2_supported(const ssm_ctx* c) { return c->dp.Dl <= 128 && !c->force_legacy_hsweep && c->d_ck != nullptr; }
+bool hsweep2_supported(const ssm_ctx* c) { return c->dp.Dl <= 256 && !c->force_legacy_hsweep && c->d_ck != nullptr; }
 
 template <int NR>
 static int launch_hsweep2_t(ssm_ctx* c, int B, cudaStream_t s)
@@ -330,7 +344,8 @@ static int launch_hsweep2_t(ssm_ctx* c, int B, cudaStream_t s)
         return SSM_OK;
     };
     int rc;
-    if (p.D == 64 * NR) rc = c->tune[1] == 5 ? go(k_hrev<NR, true, 5>) : go(k_hrev<NR, true, 6>);   // 80 registers: six CTAs per SM (SSM_TUNE1=5: 96 registers, five)
+    if constexpr (NR == 4) rc = p.D == 64 * NR ? go(k_hrev<NR, true, 3>) : go(k_hrev<NR, false, 3>);   // 64 KB of staging per CTA: three per SM
+    else if (p.D == 64 * NR) rc = c->tune[1] == 5 ? go(k_hrev<NR, true, 5>) : go(k_hrev<NR, true, 6>);   // 80 registers: six CTAs per SM (SSM_TUNE1=5: 96 registers, five)
     else rc = go(k_hrev<NR, false>);
     if (rc) return rc;
     SSM_LAUNCH_CHECK(c);
@@ -339,7 +354,7 @@ static int launch_hsweep2_t(ssm_ctx* c, int B, cudaStream_t s)
 
 int launch_hsweep2(ssm_ctx* c, int B, cudaStream_t s)
 {
-    return c->dp.Dl <= 64 ? launch_hsweep2_t<1>(c, B, s) : launch_hsweep2_t<2>(c, B, s);
+    return c->dp.Dl <= 64 ? launch_hsweep2_t<1>(c, B, s) : (c->dp.Dl <= 128 ? launch_hsweep2_t<2>(c, B, s) : launch_hsweep2_t<4>(c, B, s));
 }
 
 int launch_wta_finalize2(ssm_ctx* c, int B, cudaStream_t s)
@@ -349,7 +364,8 @@ int launch_wta_finalize2(ssm_ctx* c, int B, cudaStream_t s)
     const unsigned grid = (unsigned)((total + 255) / 256);
     const uint4* rec = reinterpret_cast<const uint4*>(c->d_wta_rec);
     if (p.Dl <= 64) k_wta_finalize2<1><<<grid, 256, 0, s>>>(rec, c->d_disp_raw, c->d_disp2key, p.W, p.D, total);
-    else k_wta_finalize2<2><<<grid, 256, 0, s>>>(rec, c->d_disp_raw, c->d_disp2key, p.W, p.D, total);
+    else if (p.Dl <= 128) k_wta_finalize2<2><<<grid, 256, 0, s>>>(rec, c->d_disp_raw, c->d_disp2key, p.W, p.D, total);
+    else k_wta_finalize2<4><<<grid, 256, 0, s>>>(rec, c->d_disp_raw, c->d_disp2key, p.W, p.D, total);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }

@@ -247,12 +247,13 @@ __global__ void __launch_bounds__(512) k_select_fused(SelArgs a)
     __syncthreads();
     // ---- records -> raw disparity, disp2 candidates; two records in flight per thread
     {
-        const uint4* recf = a.rec + frame_row0 * W1;
+        constexpr int RQ = WtaRec<NR>::kQuads;
+        const uint4* recf = a.rec + frame_row0 * W1 * RQ;
         const int n1 = ns * W1;
-        auto item = [&](const uint4& r, int j, int xp) {
+        auto item = [&](const uint4& r, const uint4& rb, int j, int xp) {
             int minS, best;
             bool valid;
-            const int out = wta2_decode<NR>(r, D, minS, best, valid);
+            const int out = wta2_decode<NR>(r, rb, D, minS, best, valid);
             const int x = xp + D;
             if (valid) atomicMin(&keys[j * W + (x - best)], ((uint32_t)minS << 16) | (uint32_t)(0xffff - x));
             dsp[j * WS + x + 2] = (int16_t)out;
@@ -263,10 +264,11 @@ __global__ void __launch_bounds__(512) k_select_fused(SelArgs a)
             int j, xp, j2, xp2;
             divmod_magic(i, a.mW1, W1, j, xp);
             divmod_magic(two ? i2 : i, a.mW1, W1, j2, xp2);
-            const uint4 r = recf[min(max(y0 - 1 + j, 0), H - 1) * W1 + xp];
-            const uint4 r2 = recf[min(max(y0 - 1 + j2, 0), H - 1) * W1 + xp2];
-            item(r, j, xp);
-            if (two) item(r2, j2, xp2);
+            const int ia = (min(max(y0 - 1 + j, 0), H - 1) * W1 + xp) * RQ, ib = (min(max(y0 - 1 + j2, 0), H - 1) * W1 + xp2) * RQ;
+            const uint4 r = recf[ia], r2 = recf[ib];
+            const uint4 rb = NR == 4 ? recf[ia + 1] : r, r2b = NR == 4 ? recf[ib + 1] : r2;
+            item(r, rb, j, xp);
+            if (two) item(r2, r2b, j2, xp2);
         }
     }
     __syncthreads();
@@ -533,7 +535,8 @@ int launch_select(ssm_ctx* c, int B, cudaStream_t s)
     const size_t npix = (size_t)B * p.H * p.W;
     size_t smem = 0;
     if (const int R = select_fused_rows(c, &smem))   // records -> L-R checked, median-filtered disparity + band-local speckle labels
-        return p.Dl <= 64 ? launch_select_fused_t<1>(c, B, R, smem, s) : launch_select_fused_t<2>(c, B, R, smem, s);
+        return p.Dl <= 64 ? launch_select_fused_t<1>(c, B, R, smem, s)
+                          : (p.Dl <= 128 ? launch_select_fused_t<2>(c, B, R, smem, s) : launch_select_fused_t<4>(c, B, R, smem, s));
     SSM_CUDA(cudaMemsetAsync(c->d_disp2key, 0xff, npix * sizeof(uint32_t), s));
     int rc = hsweep2_supported(c) ? launch_wta_finalize2(c, B, s) : launch_wta_finalize(c, B, s);
     if (rc) return rc;

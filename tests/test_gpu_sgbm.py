@@ -250,10 +250,11 @@ def test_legacy_separate_selection_kernels_still_exact(monkeypatch):
 
 
 @pytest.mark.parametrize("no_pad", [False, True])
-@pytest.mark.parametrize("H,W,D,seed", [(60, 330, 80, 131), (45, 260, 96, 132), (38, 300, 112, 133), (52, 180, 48, 134)])
+@pytest.mark.parametrize("H,W,D,seed", [(60, 330, 80, 131), (45, 260, 96, 132), (38, 300, 112, 133), (52, 180, 48, 134), (30, 420, 192, 135)])
 def test_padded_disparity_layouts(monkeypatch, no_pad, H, W, D, seed):
-    """D = 80 (the reference's src/stereo.cpp:18), 96, 112 run on the 128-disparity kernels and D = 48 on the 64-disparity
-    ones (lanes at d >= D switched off); SSM_NO_PAD=1 keeps the exact-D layout.  Both bit-exact, volumes included."""
+    """D = 80 (the reference's src/stereo.cpp:18), 96, 112 run on the 128-disparity kernels, D = 48 on the 64-disparity ones and
+    D = 192 on the 256-disparity ones (lanes at d >= D switched off); SSM_NO_PAD=1 keeps the exact-D layout.  Both bit-exact,
+    volumes included."""
     if no_pad:
         monkeypatch.setenv("SSM_NO_PAD", "1")
     L, R, _ = synth.stereo_pair(H, W, D, seed)
@@ -277,3 +278,32 @@ def test_padded_layout_batched_frames():
         _, got = ctx.pipeline_batch_host(seq["left"], seq["right"], seq["semantic"], seq["rgb"], seq["pose"], want_disp=True)
     for i in range(B):
         assert int((got[i] != oracle.sgbm(seq["left"][i], seq["right"][i], _oparams(p))).sum()) == 0
+
+
+@pytest.mark.parametrize("uniq", [0, 10, 99])
+@pytest.mark.parametrize("rows", [2, 8])
+def test_256_disparities_checkpointed_sweep_and_fused_selection(monkeypatch, uniq, rows):
+    """BASELINE configs[3] disparity count on the checkpointed horizontal sweep (8 disparities per lane, 32-byte winner
+    records) and the fused selection kernel: ambiguous matches, winners at lane borders, several uniqueness ratios."""
+    monkeypatch.setenv("SSM_SELECT_ROWS", str(rows))
+    H, W, D = 36, 400, 256
+    L, R, _ = synth.stereo_pair(H, W, D, 151 + uniq)
+    rng = np.random.default_rng(uniq)
+    R = np.clip(R.astype(int) + rng.integers(-12, 13, R.shape), 0, 255).astype(np.uint8)
+    p = _params(D, W, H, uniqueness_ratio=uniq)
+    want, vols = oracle.sgbm(L, R, _oparams(p), want_volumes=True)
+    with Context(p) as ctx:
+        got = ctx.sgbm(L, R)
+        Sv = ctx.debug_volume("S", W, H)
+        raw = ctx.debug_volume("disp_raw", W, H)
+    assert int((Sv != vols["Sv"]).sum()) == 0, "S_v (the checkpointed sweep keeps the three top-down paths' sum)"
+    assert int((raw != vols["disp_raw"]).sum()) == 0, "WTA / uniqueness / sub-pixel / L-R check"
+    assert int((got != want).sum()) == 0
+
+
+def test_legacy_one_kernel_sweep_256_disparities(monkeypatch):
+    monkeypatch.setenv("SSM_LEGACY_HSWEEP", "1")
+    L, R, _ = synth.stereo_pair(30, 380, 256, 161)
+    p = _params(256, 380, 30)
+    with Context(p) as ctx:
+        assert int((ctx.sgbm(L, R) != oracle.sgbm(L, R, _oparams(p))).sum()) == 0
