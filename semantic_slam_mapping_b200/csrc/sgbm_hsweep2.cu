@@ -1,5 +1,5 @@
 // sgbm_hsweep2.cu -- the two horizontal SGM paths + winner-take-all with checkpointed recomputation (SURVEY.md
-// App. A-4, A-5), sm_100a.  Used for D <= 128 (NR <= 2 words per lane); sgbm_hsweep.cu remains the generic path.
+// App. A-4, A-5), sm_100a.  Used for layouts of up to 256 disparities (NR = 1, 2, 4 words per lane); sgbm_hsweep.cu remains the generic path.
 //
 // The one-kernel sweep (sgbm_hsweep.cu) writes S_f = S_v + L(->) for the whole row and reads it back on the way
 // home: 10N bytes of HBM traffic for 4N algorithmic bytes, at 5.2 TB/s -- it is HBM-bound.  Here the left-to-right
