@@ -315,32 +315,32 @@ static size_t vertical_smem(int NR, int T)
     return sizeof(uint32_t) * ((size_t)(3 * T + 4) * LW + ((3 * (T + 2) + 1) & ~1) + 4);
 }
 
-// Smallest cluster whose per-CTA strip fits shared memory.  Returns false when none does (caller falls back to the
-// per-direction kernels).
-static bool plan_vertical(const ssm_ctx* c, VerticalPlan& plan)
+// Smallest cluster whose per-CTA strip fits shared memory -- or, for the few-frame calls of the drop-in API (one frame per
+// calDisparity_SGBM call), a larger one: a frame is walked row by row, so its latency is rows x trips per row, and a cluster of
+// 16 narrow strips makes three trips per row where a cluster of 4 makes nine.  Larger clusters are only taken while all of
+// them are co-resident (at most 64 CTAs: four 16-CTA or eight 8-CTA clusters fit the GPCs).  Returns false when no cluster
+// shape fits (caller falls back to the per-direction kernels).
+static bool plan_vertical(const ssm_ctx* c, int B, VerticalPlan& plan)
 {
     const DevParams& p = c->dp;
     const int NR = p.Dl <= 64 ? 1 : (p.Dl <= 128 ? 2 : (p.Dl <= 256 ? 4 : 8));
     const size_t limit = 225 * 1024;
+    bool found = false;
     for (int cs : {1, 2, 4, 8, 16}) {
         if (cs > c->max_cluster) break;
         if (cs < c->min_cluster) continue;
         const int T = (p.W1 + cs - 1) / cs;
         const size_t need = vertical_smem(NR, T);
-        if (need <= limit) {
-            plan.cluster = cs; plan.T = T; plan.smem = need;
-            return true;
-        }
+        if (need > limit) continue;
+        if (found && (B * cs > 64 || T < 32)) break;     // a larger cluster than needed: only for small batches and strips of a full trip
+        plan.cluster = cs; plan.T = T; plan.smem = need;
+        found = true;
     }
-    return false;
+    return found;
 }
 
-int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done)
+static int launch_vertical_plan(ssm_ctx* c, int B, const VerticalPlan& plan, cudaStream_t s, bool* done)
 {
-    *done = false;
-    if (c->force_legacy_vertical) return SSM_OK;
-    VerticalPlan plan;
-    if (!plan_vertical(c, plan)) return SSM_OK;
     const int D = c->dp.Dl;                       // the layout picks the kernel; lanes at d >= dp.D are inactive (FULL = false)
     const bool full = c->dp.D == D && (D == 64 || D == 128 || D == 256 || D == 512);
     if (D <= 64) {
@@ -360,6 +360,19 @@ int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done)
     }
     if (D <= 256) return full ? launch_vertical_t<4, 16, true>(c, B, plan, s, done) : launch_vertical_t<4, 16, false>(c, B, plan, s, done);
     return full ? launch_vertical_t<8, 16, true>(c, B, plan, s, done) : launch_vertical_t<8, 16, false>(c, B, plan, s, done);
+}
+
+int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done)
+{
+    *done = false;
+    if (c->force_legacy_vertical) return SSM_OK;
+    VerticalPlan plan, smallest;
+    if (!plan_vertical(c, B, plan)) return SSM_OK;
+    int rc = launch_vertical_plan(c, B, plan, s, done);
+    if (rc || *done) return rc;
+    // the latency-oriented cluster shape cannot be co-scheduled here: the smallest shape that fits shared memory
+    if (plan_vertical(c, 1 << 20, smallest) && smallest.cluster != plan.cluster) return launch_vertical_plan(c, B, smallest, s, done);
+    return SSM_OK;
 }
 
 }  // namespace ssm
