@@ -103,7 +103,7 @@ def test_two_rank_gloo_routing_equals_single_map():
 
 
 # ---- GPU: NCCL all-to-all inside libssm.so --------------------------------------------------------------------
-def _nccl_worker(rank, world, port, q, p2p, split=0):
+def _nccl_worker(rank, world, port, q, p2p, split=0, n=6):
     if split:
         os.environ["SSM_TUNE3"] = str(split)     # sub-batch streams: SGBM per sub-batch, one routing exchange per batch
     import torch
@@ -114,7 +114,7 @@ def _nccl_worker(rank, world, port, q, p2p, split=0):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        H, W, Dd, n = 96, 320, 64, 6
+        H, W, Dd = 96, 320, 64
         p = Params(num_disparities=Dd, max_width=W, max_height=H, max_batch=3, resolution=0.05, map_capacity=1 << 18)
         seq = synth.sequence(n, H, W, Dd, 12, seed=9)
         with Context(p, device=rank) as ctx:
@@ -140,24 +140,19 @@ def _nccl_worker(rank, world, port, q, p2p, split=0):
         dist.destroy_process_group()
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("p2p,split", [(True, 0), (False, 0), (True, 2), (False, 3)])
-def test_two_gpu_map_equals_oracle_map(p2p, split):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+def _run_ranks_and_compare(world, p2p, split, n):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q, p2p, split)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q, p2p, split, n)) for r in range(world)]
     for p in procs:
         p.start()
     merged = q.get(timeout=300)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    H, W, Dd, n = 96, 320, 64, 6
+    H, W, Dd = 96, 320, 64
     seq = synth.sequence(n, H, W, Dd, 12, seed=9)
     mp_ = oracle.MapParams()
     vm = oracle.VoxelMap(0.05, 12)
@@ -170,3 +165,23 @@ def test_two_gpu_map_equals_oracle_map(p2p, split):
     assert (merged["votes"] == want["votes"]).all() and (merged["label"] == want["label"]).all()
     ref = want["centroid_d"]
     assert (np.abs(merged["xyz"] - ref) <= 1e-5 * np.maximum(np.abs(ref), 1.0)).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p2p,split", [(True, 0), (False, 0), (True, 2), (False, 3)])
+def test_two_gpu_map_equals_oracle_map(p2p, split):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    _run_ranks_and_compare(2, p2p, split, 6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,p2p", [(4, True), (4, False), (8, True)])
+def test_many_gpu_map_equals_oracle_map(world, p2p):
+    """The spatially owned map over 4 / 8 ranks (every rank routes to every other one: one system-scope reservation per
+    (CTA, owner), the NCCL all-to-all fallback) is the oracle's single map, vote for vote."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (run under gpurun --gpus {world})")
+    _run_ranks_and_compare(world, p2p, 0, 8 if world == 4 else 16)
