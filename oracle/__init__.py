@@ -366,7 +366,8 @@ def build_ref() -> str | None:
     the prebuilt file that travels with the snapshot).  Returns the path, or None when neither source nor binary exists."""
     src = os.path.join(_REFERENCE_ROOT, "src", "stereo.cpp")
     if os.path.exists(src):
-        deps = [src, os.path.join(_HERE, "ref_stereo_wrap.cpp"), os.path.join(_HERE, "cvstub", "cvstub.hpp")]
+        deps = [src, os.path.join(_REFERENCE_ROOT, "src", "uvdisparity.cpp"), os.path.join(_HERE, "ref_stereo_wrap.cpp"),
+                os.path.join(_HERE, "ref_uv_wrap.cpp"), os.path.join(_HERE, "cvstub", "cvstub.hpp"), os.path.join(_HERE, "cvstub", "cvstub_more.hpp")]
         if (not os.path.exists(_REF_PATH)) or any(os.path.getmtime(f) > os.path.getmtime(_REF_PATH) for f in deps):
             subprocess.check_call(["make", "-C", _HERE, "-B", "_ref/libref_stereo.so", f"REF={_REFERENCE_ROOT}"], stdout=subprocess.DEVNULL)
     return _REF_PATH if os.path.exists(_REF_PATH) else None
@@ -402,6 +403,10 @@ def ref():
         R.ref_triangulate10D.argtypes = [vp, vp, C.c_int, C.c_int, d, d, d, d, d, d, d, vp]
         R.ref_correct3DPoints.argtypes = [vp, C.c_int, C.c_int, d, d, d, d, d]
         R.ref_setImageROI.argtypes = [vp, C.c_int, C.c_int, vp]
+        R.ref_calVDisparity.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int]
+        R.ref_calVDisparity.restype = C.c_int
+        R.ref_calUDisparity.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int]
+        R.ref_calUDisparity.restype = C.c_int
         R.ref_set_sgbm(_sgbm_cb)
         _ref = R
     return _ref
@@ -485,3 +490,31 @@ def labels_from_indices(index_img: np.ndarray, dw: int, dh: int, lut_bgr: np.nda
     raw = resize_linear_u8(index_img, dw, dh)
     lut = np.ascontiguousarray(lut_bgr, np.uint8).reshape(256, 3)
     return lut[raw], raw
+
+
+def ref_v_disparity(disp, xyz, cap_cols=1024):
+    """The reference's own UVDisparity::calVDisparity (src/uvdisparity.cpp:277-366); same returns as v_disparity()."""
+    disp = np.ascontiguousarray(disp, np.int16)
+    out = np.ascontiguousarray(xyz, np.float32).copy()
+    H, W = disp.shape
+    vi = np.zeros(H * cap_cols, np.int32)
+    v8 = np.zeros(H * cap_cols, np.uint8)
+    vc = ref().ref_calVDisparity(_p(disp), W, H, _p(out), _p(vi), _p(v8), cap_cols)
+    if vc < 0:
+        raise ValueError("v-disparity wider than cap_cols")
+    return out, vi[: H * vc].reshape(H, vc).copy(), v8[: H * vc].reshape(H, vc).copy()
+
+
+def ref_u_disparity(disp, xyz, roi_mask, ground_mask, cap_rows=1025):
+    """The reference's own UVDisparity::calUDisparity (src/uvdisparity.cpp:195-274); same returns as u_disparity()."""
+    disp = np.ascontiguousarray(disp, np.int16)
+    out = np.ascontiguousarray(xyz, np.float32).copy()
+    roi_mask = np.ascontiguousarray(roi_mask, np.uint8)
+    ground_mask = np.ascontiguousarray(ground_mask, np.uint8)
+    H, W = disp.shape
+    ui = np.zeros(cap_rows * W, np.int32)
+    u8 = np.zeros(cap_rows * W, np.uint8)
+    ur = ref().ref_calUDisparity(_p(disp), W, H, _p(out), _p(roi_mask), _p(ground_mask), _p(ui), _p(u8), cap_rows)
+    if ur < 0:
+        raise ValueError("u-disparity taller than cap_rows")
+    return out, ui[: ur * W].reshape(ur, W).copy(), u8[: ur * W].reshape(ur, W).copy()

@@ -55,6 +55,10 @@ struct Size {
     Size(int w, int h) : width(w), height(h) {}
 };
 
+struct Scalar;
+struct Range;
+struct Rect;
+
 class Mat {
 public:
     int rows, cols;
@@ -83,14 +87,35 @@ public:
         if (data && r == rows && c == cols && t == type_) return;
         rows = r; cols = c; type_ = t;
         step = (size_t)cols * elemSize();
-        own_.reset(new std::vector<uchar>(step * (size_t)rows + 64, 0));
-        data = own_->data();
+        // Zeroed slack before and after the pixels.  The reference indexes a little outside its matrices in
+        // UVDisparity::calVDisparity / calUDisparity (row -1 of the 8-bit U map, int reads from the 8-bit V map, histogram
+        // bin v_cols); with the slack those accesses have the meaning DESIGN.md section 2 gives them (reads see zeros,
+        // writes past the last row are dropped) instead of touching foreign memory.
+        const size_t lead = step + 64, trail = 4 * step + 64;
+        own_.reset(new std::vector<uchar>(lead + step * (size_t)rows + trail, 0));
+        data = own_->data() + lead;
     }
     void create(Size s, int t) { create(s.height, s.width, t); }
     template <typename T> T* ptr(int i = 0) { return (T*)(data + step * (size_t)i); }
     template <typename T> const T* ptr(int i = 0) const { return (const T*)(data + step * (size_t)i); }
-    template <typename T> T& at(int i, int j) { return ((T*)(data + step * (size_t)i))[j]; }
-    template <typename T> const T& at(int i, int j) const { return ((const T*)(data + step * (size_t)i))[j]; }
+    template <typename T> T& at(int i, int j) { return ((T*)(data + (ptrdiff_t)step * i))[j]; }
+    template <typename T> const T& at(int i, int j) const { return ((const T*)(data + (ptrdiff_t)step * i))[j]; }
+    template <typename T> T& at(int i) { return rows == 1 ? ((T*)data)[i] : *(T*)(data + (ptrdiff_t)step * i); }
+    template <typename T> const T& at(int i) const { return rows == 1 ? ((const T*)data)[i] : *(const T*)(data + (ptrdiff_t)step * i); }
+    static Mat zeros(int r, int c, int t) { return Mat(r, c, t); }   // create() zero-fills
+    static Mat zeros(Size s, int t) { return Mat(s.height, s.width, t); }
+    Mat clone() const
+    {
+        Mat m(rows, cols, type_);
+        for (int i = 0; i < rows; ++i) std::memcpy(m.data + m.step * (size_t)i, data + step * (size_t)i, (size_t)cols * elemSize());
+        return m;
+    }
+    void copyTo(Mat& m) const { m = clone(); }
+    // declared for compilation only (cvstub_more.hpp): sub-matrix views, masked copy, fill
+    Mat operator()(const Range& rows, const Range& cols) const;
+    Mat operator()(const Rect& roi) const;
+    void copyTo(Mat& m, const Mat& mask) const;
+    Mat& operator=(const Scalar& s);
 
 private:
     int type_;
@@ -183,4 +208,5 @@ public:
 };
 
 }  // namespace cv
+#include "cvstub_more.hpp"
 #endif

@@ -21,13 +21,13 @@
  *   (label production, experiment/segnet.cpp:121-135, is restated in numpy in oracle/__init__.py)
  *
  * Parity pinning: the SGBM chain is pinned against cv2 4.13 (tests/test_oracle_golden.py and
- * the committed vectors in tests/golden/); triangulate10D / correct3DPoints / setImageROI and
- * calDisparity_SGBM's parameter block against the reference's OWN src/stereo.cpp, compiled by
- * oracle/Makefile against oracle/cvstub into oracle/_ref/libref_stereo.so
- * (tests/test_oracle_cues.py, tests/golden/cues_ref.npz); cv::resize + cv::LUT against cv2 4.13.
- * The reference itself ships no tests or golden vectors for this path; PCL and
- * src/uvdisparity.cpp cannot be compiled or executed here, so the voxel-fusion part and the
- * U/V-disparity histograms are "parity unpinned" beyond their written definition.
+ * the committed vectors in tests/golden/); triangulate10D / correct3DPoints / setImageROI,
+ * calDisparity_SGBM's parameter block and the U/V-disparity histograms against the reference's
+ * OWN src/stereo.cpp and src/uvdisparity.cpp, compiled by oracle/Makefile against oracle/cvstub
+ * into oracle/_ref/libref_stereo.so (tests/test_oracle_cues.py, tests/golden/cues_ref.npz);
+ * cv::resize + cv::LUT against cv2 4.13.  The reference itself ships no tests or golden vectors
+ * for this path; PCL cannot be compiled or executed here, so the voxel-fusion part is
+ * "parity unpinned" beyond its written definition.
  */
 #ifndef SSM_ORACLE_H
 #define SSM_ORACLE_H

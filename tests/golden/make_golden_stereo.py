@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Regenerates tests/golden/cues_ref.npz by RUNNING THE REFERENCE'S OWN src/stereo.cpp (compiled where it lies by
-oracle/Makefile against oracle/cvstub into oracle/_ref/libref_stereo.so): calDisparity_SGBM's parameter set,
-triangulate10D, correct3DPoints and setImageROI outputs on small seeded inputs.  /root/reference only exists in the
+"""Regenerates tests/golden/cues_ref.npz by RUNNING THE REFERENCE'S OWN src/stereo.cpp and src/uvdisparity.cpp (compiled
+where they lie by oracle/Makefile against oracle/cvstub into oracle/_ref/libref_stereo.so): calDisparity_SGBM's parameter
+set, triangulate10D, correct3DPoints, setImageROI and UVDisparity::calVDisparity / calUDisparity outputs on small seeded
+inputs.  /root/reference only exists in the
 build container, so the vectors are committed; tests/test_oracle_cues.py checks the C oracle against them everywhere
 and against the live reference build where oracle/_ref is present.
 
@@ -42,6 +43,21 @@ def main():
     cor = oracle.ref_correct_3d_points(xyz, tuple(roi), pitch[0], pitch[1])
     mask = oracle.ref_set_image_roi(cor)
     out.update(left=L, disp=disp, cam=cam, roi=roi, pitch=pitch, xyz=xyz, corrected=cor, roi_mask=mask)
+    # U/V-disparity histograms (src/uvdisparity.cpp:277-366, 195-274) in the order UVDisparity::Process runs them: V on the
+    # triangulated records, U on the corrected ones.  The map's maximum is 90.5625 px: v_cols = 91 and round() = 91, so that
+    # pixel's bin index equals v_cols (spills into the next row; past the matrix on the last row); 20.5 rounds to 20.
+    duv = disp.copy()
+    duv[7, 9] = 16 * 90 + 9
+    duv[H - 1, 4] = 16 * 90 + 9
+    duv[2, 11] = 16 * 20 + 8
+    xyz_uv = oracle.ref_triangulate10d(L, duv, *cam, roi=tuple(roi))
+    v_xyz, v_int, v_u8 = oracle.ref_v_disparity(duv, xyz_uv)
+    cor_uv = oracle.ref_correct_3d_points(v_xyz, tuple(roi), pitch[0], pitch[1])
+    mask_uv = oracle.ref_set_image_roi(cor_uv)
+    ground = (np.random.default_rng(6).random((H, W)) < 0.7).astype(np.uint8) * 255
+    u_xyz, u_int, u_u8 = oracle.ref_u_disparity(duv, cor_uv, mask_uv, ground)
+    out.update(uv_disp=duv, uv_xyz=xyz_uv, v_xyz=v_xyz, v_int=v_int, v_u8=v_u8, uv_corrected=cor_uv, uv_roi_mask=mask_uv,
+               uv_ground=ground, u_xyz=u_xyz, u_int=u_int, u_u8=u_u8)
     np.savez_compressed(os.path.join(OUT, "cues_ref.npz"), **out)
     print("wrote cues_ref.npz:", {k: v.shape for k, v in out.items()})
 

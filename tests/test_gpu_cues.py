@@ -1,5 +1,5 @@
 """-m gpu parity tests of the dense motion cues through the C ABI vs the CPU oracle, which is itself
-pinned to the reference's own src/stereo.cpp (tests/test_oracle_cues.py).  Everything is compared bit for bit (fp32
+pinned to the reference's own src/stereo.cpp and src/uvdisparity.cpp (tests/test_oracle_cues.py).  Everything is compared bit for bit (fp32
 words, infinities and NaNs included)."""
 import os
 
@@ -40,6 +40,11 @@ def test_golden_vectors_from_reference_source(ctx, golden_dir):
     cor = ctx.correct_3d_points(g["xyz"], tuple(g["roi"]), g["pitch"][0], g["pitch"][1])
     assert _eq(cor, g["corrected"])
     assert _eq(ctx.set_image_roi(g["corrected"]), g["roi_mask"])
+    # U/V-disparity histograms: vectors produced by the reference's own UVDisparity::calVDisparity / calUDisparity
+    got, vint, v8 = ctx.v_disparity(g["uv_disp"], g["uv_xyz"])
+    assert _eq(vint, g["v_int"]) and _eq(v8, g["v_u8"]) and _eq(got, g["v_xyz"])
+    got, uint_, u8 = ctx.u_disparity(g["uv_disp"], g["uv_corrected"], g["uv_roi_mask"], g["uv_ground"])
+    assert _eq(uint_, g["u_int"]) and _eq(u8, g["u_u8"]) and _eq(got, g["u_xyz"])
 
 
 @pytest.mark.parametrize("H,W,D,seed", [(56, 200, 64, 1), (37, 131, 32, 2), (120, 400, 128, 3)])

@@ -1,6 +1,7 @@
 """CPU tests of the dense-motion-cue oracle: the C restatement against vectors produced by the
-reference's own src/stereo.cpp (tests/golden/cues_ref.npz, generator make_golden_stereo.py), against the live reference
-build where oracle/_ref/libref_stereo.so exists, and numpy restatements of the U/V-disparity histograms."""
+reference's own src/stereo.cpp and src/uvdisparity.cpp (tests/golden/cues_ref.npz, generator make_golden_stereo.py),
+against the live reference build where oracle/_ref/libref_stereo.so exists, and numpy restatements of the
+U/V-disparity histograms."""
 import os
 
 import numpy as np
@@ -56,6 +57,35 @@ def test_oracle_equals_live_reference(seed):
     assert _eq(oracle.set_image_roi(cor), oracle.ref_set_image_roi(cor))
     # calDisparity_SGBM itself: the reference's parameter block over the oracle's SGBM == oracle defaults
     assert _eq(oracle.ref_cal_disparity_sgbm(L, R), oracle.sgbm(L, R, oracle.SgbmParams()))
+
+
+def test_uv_disparity_match_reference_vectors(gold):
+    """The U/V-disparity restatement against what the reference's own UVDisparity::calVDisparity / calUDisparity
+    (src/uvdisparity.cpp, compiled against oracle/cvstub) produced: histograms, 8-bit maps, record channels 8 and 7."""
+    out, vint, v8 = oracle.v_disparity(gold["uv_disp"], gold["uv_xyz"])
+    assert _eq(vint, gold["v_int"]) and _eq(v8, gold["v_u8"]) and _eq(out, gold["v_xyz"])
+    assert vint.shape[1] == 91 and vint[8, 0] >= 1            # the bin == v_cols spill of row 7 landed on row 8, bin 0
+    assert vint.sum() == (gold["uv_disp"] > 0).sum() - 1      # the last row's spill is past the matrix
+    out, uint_, u8 = oracle.u_disparity(gold["uv_disp"], gold["uv_corrected"], gold["uv_roi_mask"], gold["uv_ground"])
+    assert _eq(uint_, gold["u_int"]) and _eq(u8, gold["u_u8"]) and _eq(out, gold["u_xyz"])
+    assert uint_.sum() > 100 and (gold["u_xyz"][..., 7] > 0).any()
+
+
+@pytest.mark.skipif(oracle.ref() is None, reason="oracle/_ref/libref_stereo.so not built (no /root/reference on this machine)")
+@pytest.mark.parametrize("H,W,D,seed", [(56, 200, 64, 1), (37, 131, 32, 2), (120, 400, 128, 3), (90, 310, 80, 4)])
+def test_uv_disparity_equals_live_reference(H, W, D, seed):
+    L, R, _ = synth.stereo_pair(H, W, D, seed)
+    disp = oracle.sgbm(L, R, oracle.SgbmParams(num_disparities=D))
+    disp[1, D + 3] = 16 * (D - 2) + 9                         # a new maximum with fraction .5625: bin index == v_cols
+    disp[H - 1, D + 5] = 16 * (D - 2) + 9
+    xyz = oracle.ref_triangulate10d(L, disp, 718.856, W / 2.0, H / 2.0, 0.54)
+    got, want = oracle.v_disparity(disp, xyz), oracle.ref_v_disparity(disp, xyz)
+    assert all(_eq(a, b) for a, b in zip(got, want))
+    cor = oracle.ref_correct_3d_points(want[0], (30000.0, -1000.0, 30000.0), 0.02)
+    roi = oracle.ref_set_image_roi(cor)
+    ground = (np.random.default_rng(seed).integers(0, 3, (H, W)) > 0).astype(np.uint8) * 255
+    got, want = oracle.u_disparity(disp, cor, roi, ground), oracle.ref_u_disparity(disp, cor, roi, ground)
+    assert all(_eq(a, b) for a, b in zip(got, want))
 
 
 def _np_v_disparity(disp, W):
