@@ -48,7 +48,7 @@ static int validate(const ssm_params& p)
 // kernels and D = 48 on the D = 64 ones: the lanes above D are switched off, their cells are computed but never read.
 static int layout_disparities(const ssm_ctx* c, int D)
 {
-    if (c->no_pad || c->force_legacy_cost || c->force_legacy_hsweep || c->force_legacy_vertical) return D;
+    if (c->no_pad || c->force_legacy_cost || c->force_legacy_hsweep || c->force_legacy_vertical || c->p.block_size != 11) return D;
     if (D > 128 && D < 256) return 256;
     if (D > 64 && D < 128) return 128;
     if (D > 32 && D < 64) return 64;

@@ -330,11 +330,13 @@ struct CostGeom {
     static constexpr size_t smem_words(int bs) { return (size_t)12 * TW + NE * 8 + (size_t)NE * PS + (size_t)bs * TX * WPP; }
 };
 
-template <int TX, int RAD /* block_size / 2, or -1: run-time radius (slow generic window sums) */>
+template <int TX, int RAD /* block_size / 2, or -1: run-time radius (slow generic window sums) */,
+          bool PAD = false /* padded layout: cells at d >= Dv are written as `padw`, the aggregation kernels' "+inf" cost */>
 __global__ void __launch_bounds__(256, 2) k_cost_fused(const uint2* __restrict__ recL, const uint2* __restrict__ recR,
                                                        int16_t* __restrict__ C, int W, int H, int Dv /* valid disparities <= D: the image geometry */,
                                                        int radius, int band_rows,
-                                                       uint32_t mone /* 0xffffffff, opaque: x * mone + K is one IMAD */)
+                                                       uint32_t mone /* 0xffffffff, opaque: x * mone + K is one IMAD */,
+                                                       uint32_t padw = 0u)
 {
     using G = CostGeom<TX>;
     constexpr int D = G::D, WPP = G::WPP, TW = G::TW, PS = G::PS, LPP = G::LPP, WPL = G::WPL;
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(256, 2) k_cost_fused(const uint2* __restrict__
                 const uint32_t old = rg[c * WPP];
                 rg[c * WPP] = hs[c];
                 crun[c] = crun[c] + hs[c] - old;
-                if (yout >= y0 && c0 + c < W1) *reinterpret_cast<uint32_t*>(dst + (size_t)c * D) = crun[c];
+                if (yout >= y0 && c0 + c < W1) *reinterpret_cast<uint32_t*>(dst + (size_t)c * D) = (PAD && 2 * w2 >= Dv) ? padw : crun[c];
             }
         }
         slot = slot + 1 == bs ? 0 : slot + 1;
@@ -591,20 +593,21 @@ int launch_prefilter(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, cu
     return SSM_OK;
 }
 
-template <int TX, int RAD>
+template <int TX, int RAD, bool PAD = false>
 static int launch_cost_fused_t(ssm_ctx* c, int B, cudaStream_t s)
 {
     const DevParams& p = c->dp;
     const int radius = p.bs / 2;
     const size_t smem = sizeof(uint32_t) * CostGeom<TX>::smem_words(p.bs);
-    SSM_CUDA(cudaFuncSetAttribute(k_cost_fused<TX, RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSM_CUDA(cudaFuncSetAttribute(k_cost_fused<TX, RAD, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // bands: enough CTAs to fill the machine a few times over, but tall enough to amortise the 2*radius halo rows
     const int tiles = (p.W1 + TX - 1) / TX;
     int bands = std::max(1, std::min(p.H / 32, (c->sm_count * 8 + tiles * B - 1) / (tiles * B)));
     const int band_rows = (p.H + bands - 1) / bands;
     bands = (p.H + band_rows - 1) / band_rows;
     dim3 grid(tiles, bands, B);
-    k_cost_fused<TX, RAD><<<grid, 256, smem, s>>>(reinterpret_cast<const uint2*>(c->d_recL), reinterpret_cast<const uint2*>(c->d_recR), c->d_C, p.W, p.H, p.D, radius, band_rows, 0xffffffffu);
+    k_cost_fused<TX, RAD, PAD><<<grid, 256, smem, s>>>(reinterpret_cast<const uint2*>(c->d_recL), reinterpret_cast<const uint2*>(c->d_recR), c->d_C, p.W, p.H, p.D, radius, band_rows, 0xffffffffu,
+                                                       (kBig - (uint32_t)p.P2) * 0x10001u);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }
@@ -615,6 +618,14 @@ int launch_cost_volume(ssm_ctx* c, int B, cudaStream_t s)
     if (use_fused_cost(c)) {
         // TX * D/2 = 2048 words per CTA row
         const bool r5 = p.bs == 11;   // the reference's block size gets the compile-time window; others the generic one
+        if (p.Dl != p.D) {            // padded layouts (only formed for block size 11, api.cu: layout_disparities)
+            switch (p.Dl) {
+                case 64: return launch_cost_fused_t<64, 5, true>(c, B, s);
+                case 128: return launch_cost_fused_t<32, 5, true>(c, B, s);
+                case 256: return launch_cost_fused_t<16, 5, true>(c, B, s);
+                default: break;
+            }
+        }
         switch (p.Dl) {
             case 16: return r5 ? launch_cost_fused_t<256, 5>(c, B, s) : launch_cost_fused_t<256, -1>(c, B, s);
             case 32: return r5 ? launch_cost_fused_t<128, 5>(c, B, s) : launch_cost_fused_t<128, -1>(c, B, s);

@@ -133,7 +133,8 @@ struct HrevArgs {
     uint32_t uniq_mul, uniq_add, uniq_magic;
 };
 
-template <int NR, bool FULL, int MINB = 5 /* CTAs per SM the register budget is cut for: 5 -> 96 registers, 6 -> 80 (no spills) */>
+template <int NR, bool FULL, int MINB = 5 /* CTAs per SM the register budget is cut for: 5 -> 96 registers, 6 -> 80 (no spills) */,
+          bool PADDED = false /* padded layout (with FULL): all lanes load, the lanes at d >= Dv are kept out of the winner-take-all */>
 __global__ void __launch_bounds__(128, MINB) k_hrev(const HrevArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -158,7 +159,8 @@ __global__ void __launch_bounds__(128, MINB) k_hrev(const HrevArgs a)
     const PathLane pl = make_path_lane(lane, a.one, (uint32_t)a.P1);
     const uint32_t P1w = (uint32_t)a.P1 * 0x10001u, P2w = (uint32_t)a.P2 * 0x10001u;
     const uint32_t padC = (kBig - (uint32_t)a.P2) * 0x10001u;
-    const uint32_t lanemask = active ? (NR >= 2 ? 0x80808080u : 0x00008080u) : 0u;   // per flag word (4 disparities)
+    const bool valid = PADDED ? d0 < a.Dv : active;   // lanes that hold disparities of the image
+    const uint32_t lanemask = valid ? (NR >= 2 ? 0x80808080u : 0x00008080u) : 0u;   // per flag word (4 disparities)
     const uint8_t* Cg = reinterpret_cast<const uint8_t*>(a.C) + (size_t)row * W1 * colbytes;
     const uint8_t* Sg = reinterpret_cast<const uint8_t*>(a.Sv) + (size_t)row * W1 * colbytes;
     const uint32_t* ckrow = a.ck + (size_t)row * a.nb * (LW + 32);
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(128, MINB) k_hrev(const HrevArgs a)
             uint32_t kmin = 0xffffffffu;
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
-                Sw[r] = active ? __viaddmin_u16x2(tw[r], Lr[r], kSatW) : 0xffffffffu;
+                Sw[r] = valid ? __viaddmin_u16x2(tw[r], Lr[r], kSatW) : 0xffffffffu;
                 const uint32_t klo = Sw[r] * pl.sh16 + (uint32_t)(d0 + 2 * r);
                 const uint32_t khi = (Sw[r] & 0xffff0000u) | (uint32_t)(d0 + 2 * r + 1);
                 kmin = __vimin3_u32(kmin, klo, khi);                       // smaller d wins ties: first minimum
@@ -317,7 +319,7 @@ static int launch_hsweep2_t(ssm_ctx* c, int B, cudaStream_t s)
     const unsigned grid = (unsigned)((nrows + wpb - 1) / wpb);
     if (nb > 1) {
         const size_t smem_f = (size_t)wpb * 2 * kBlk * p.Dl * 2 + wpb * 16;
-        if (p.D == 64 * NR) {
+        if (p.D == 64 * NR || p.Dl != p.D) {   // full-width layout, or a padded one (its cells at d >= D hold the "+inf" cost)
             SSM_CUDA(cudaFuncSetAttribute(k_hfwd<NR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
             k_hfwd<NR, true><<<grid, wpb * 32, smem_f, s>>>(c->d_C, c->d_ck, p.W1, p.Dl, p.P1, p.P2, nrows, nb, 1u, p.D);
         } else {
@@ -344,9 +346,10 @@ static int launch_hsweep2_t(ssm_ctx* c, int B, cudaStream_t s)
         return SSM_OK;
     };
     int rc;
-    if constexpr (NR == 4) rc = p.D == 64 * NR ? go(k_hrev<NR, true, 3>) : go(k_hrev<NR, false, 3>);   // 64 KB of staging per CTA: three per SM
+    if (p.Dl != p.D) rc = NR == 4 ? go(k_hrev<NR, true, 3, true>) : go(k_hrev<NR, true, 6, true>);   // padded layout
+    else if constexpr (NR == 4) rc = p.D == 64 * NR ? go(k_hrev<NR, true, 3>) : go(k_hrev<NR, false, 3>);   // 64 KB of staging per CTA: three per SM
     else if (p.D == 64 * NR) rc = c->tune[1] == 5 ? go(k_hrev<NR, true, 5>) : go(k_hrev<NR, true, 6>);   // 80 registers: six CTAs per SM (SSM_TUNE1=5: 96 registers, five)
-    else rc = go(k_hrev<NR, false>);
+    else rc = go(k_hrev<NR, false, 6>);
     if (rc) return rc;
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;

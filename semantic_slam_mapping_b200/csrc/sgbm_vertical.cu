@@ -342,7 +342,8 @@ static bool plan_vertical(const ssm_ctx* c, int B, VerticalPlan& plan)
 static int launch_vertical_plan(ssm_ctx* c, int B, const VerticalPlan& plan, cudaStream_t s, bool* done)
 {
     const int D = c->dp.Dl;                       // the layout picks the kernel; lanes at d >= dp.D are inactive (FULL = false)
-    const bool full = c->dp.D == D && (D == 64 || D == 128 || D == 256 || D == 512);
+    // padded layouts: the cost kernel wrote the "+inf" cost into the cells at d >= dp.D, so every lane runs the same code
+    const bool full = c->dp.D != D || (D == 64 || D == 128 || D == 256 || D == 512);
     if (D <= 64) {
         // D == 64 / 32: two columns per warp as well (16 lanes x 2 words / x 1 word); SSM_TUNE2=3 keeps one column per warp
         if (D == 64 && c->tune[2] != 3)
@@ -352,8 +353,13 @@ static int launch_vertical_plan(ssm_ctx* c, int B, const VerticalPlan& plan, cud
     }
     if (D <= 128) {
         // D == 128: two columns per warp (16 lanes x 4 words each) halve the per-column overhead of the recurrence
-        if (D == 128 && c->tune[2] == 0)
+        if (D == 128 && c->tune[2] == 0) {
+            // 17 warps walk 34 columns per trip: taken when that saves a trip per row (strips of 289..306 columns, e.g. the
+            // 291 of a 1241-pixel frame at the reference's 80 disparities: nine trips instead of ten)
+            if ((plan.T + 33) / 34 < (plan.T + 31) / 32)
+                return full ? launch_vertical_t<4, 17, true, 16>(c, B, plan, s, done) : launch_vertical_t<4, 17, false, 16>(c, B, plan, s, done);
             return full ? launch_vertical_t<4, 16, true, 16>(c, B, plan, s, done) : launch_vertical_t<4, 16, false, 16>(c, B, plan, s, done);
+        }
         if (D == 128 && full && c->tune[2] == 2) return launch_vertical_t<4, 24, true, 16>(c, B, plan, s, done);
         if (full && c->tune[2] == 1) return launch_vertical_t<2, 24, true>(c, B, plan, s, done);
         return full ? launch_vertical_t<2, 32, true>(c, B, plan, s, done) : launch_vertical_t<2, 32, false>(c, B, plan, s, done);
