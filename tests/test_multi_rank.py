@@ -79,9 +79,12 @@ def _gloo_worker(rank, world, port, leaf, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_gloo_routing_equals_single_map():
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_routing_equals_single_map(world):
+    """Host-side routing logic (frame split, ownership, bucketing, all-to-all, map merge) over 2 and 3 gloo ranks: the
+    merged map is the single-process map, vote for vote (3 ranks: uneven frame shards, a non-power-of-two owner hash)."""
     import torch.multiprocessing as mp
-    leaf, world = 0.1, 2
+    leaf = 0.1
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
