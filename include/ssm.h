@@ -205,6 +205,20 @@ int ssm_labels_from_indices(ssm_ctx* ctx, const uint8_t* index, size_t index_str
 int ssm_labels_from_indices_batch_device(ssm_ctx* ctx, int batch, const uint8_t* d_index, int sw, int sh, int dw, int dh,
                                          const uint8_t* lut_bgr, uint8_t* d_semantic_bgr, uint8_t* d_raw, void* stream);
 
+/* ---- PNG ingest in front of the path (FrameReader::next, src/rgbdframe.cpp:45-78, 138-180) ----- */
+/* The reference reads every image with cv::imread: the grey stereo pair with flag 0, the colour and label images with
+ * the default flag.  ssm_png_decode_batch_device decodes `batch` PNG files held in host memory into device images of
+ * the layout the pipeline entry points take: mode 0 -> [batch][h][w] u8 (== imread(path, 0)), mode 1 -> [batch][h][w][3]
+ * u8 BGR (== imread(path)).  The zlib streams are inflated on `host_threads` host threads (0 = all cores); PNG
+ * un-filtering, palette expansion, alpha stripping, channel reordering and the colour -> grey conversion run on the GPU
+ * on `stream` (NULL = the context's stream).  Every file must be w x h, 8 bits per sample, non-interlaced (grey,
+ * grey + alpha, RGB, RGBA or palette).  Bit-exact with cv2 4.13.  The host returns when the batch is queued. */
+int ssm_png_info(const uint8_t* png, size_t png_bytes, int* w, int* h, int* channels /* 1 or 3, may be NULL */);
+int ssm_png_decode_batch_device(ssm_ctx* ctx, int batch, const uint8_t* const* png, const size_t* png_bytes, int w, int h,
+                                int mode, uint8_t* d_out, int host_threads, void* stream);
+/* one file, host buffer out (blocking): == cv::imread(path, mode ? 1 : 0) */
+int ssm_png_decode(ssm_ctx* ctx, const uint8_t* png, size_t png_bytes, int mode, uint8_t* out, size_t out_bytes, int* w, int* h);
+
 /* ---- the whole path, batched (north_star: stereo pair + labels + pose -> map) ----------------- */
 /* Device-resident inputs: [batch][h][w] u8 left/right, [batch][h][w][3] u8 semantic/rgb BGR,
  * [batch][16] double poses.  d_disp_out (optional, may be NULL) receives [batch][h][w] int16. */

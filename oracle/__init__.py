@@ -518,3 +518,117 @@ def ref_u_disparity(disp, xyz, roi_mask, ground_mask, cap_rows=1025):
     if ur < 0:
         raise ValueError("u-disparity taller than cap_rows")
     return out, ui[: ur * W].reshape(ur, W).copy(), u8[: ur * W].reshape(ur, W).copy()
+
+
+# ---- PNG ingest: restatement of what cv::imread does with an 8-bit non-interlaced PNG --------------
+def png_decode(png: bytes, colour: bool) -> np.ndarray:
+    """cv2.imdecode(png, IMREAD_COLOR / IMREAD_GRAYSCALE) for 8-bit, non-interlaced PNG files (grey, grey + alpha, RGB,
+    RGBA, palette): chunk parsing, inflate, the five scanline filters of the PNG specification, palette expansion, alpha
+    stripping, BGR order; grey from colour as libpng's rgb_to_gray with OpenCV's coefficients,
+    (9797 R + 19234 G + 3737 B) >> 15.  Pinned against cv2 4.13 in tests/test_oracle_png.py."""
+    import struct
+    import zlib
+    assert png[:8] == b"\x89PNG\r\n\x1a\n", "not a PNG file"
+    pos, idat, pal, ihdr = 8, [], None, None
+    while pos + 12 <= len(png):
+        (n,), typ = struct.unpack(">I", png[pos:pos + 4]), png[pos + 4:pos + 8]
+        data = png[pos + 8:pos + 8 + n]
+        if typ == b"IHDR":
+            ihdr = struct.unpack(">IIBBBBB", data)
+        elif typ == b"PLTE":
+            pal = np.frombuffer(data, np.uint8).reshape(-1, 3)
+        elif typ == b"IDAT":
+            idat.append(data)
+        elif typ == b"IEND":
+            break
+        pos += 12 + n
+    W, H, depth, ctype, _, _, interlace = ihdr
+    if depth != 8 or interlace != 0:
+        raise ValueError("only 8-bit non-interlaced PNG files")
+    bpp = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype]
+    raw = np.frombuffer(zlib.decompress(b"".join(idat)), np.uint8).reshape(H, W * bpp + 1)
+    img = np.zeros((H, W * bpp), np.int64)
+    prev = np.zeros(W * bpp, np.int64)
+    for y in range(H):
+        ft, line = int(raw[y, 0]), raw[y, 1:].astype(np.int64)
+        if ft == 0:
+            cur = line
+        elif ft == 2:
+            cur = (line + prev) & 255
+        elif ft == 1:
+            cur = line.copy()
+            for c in range(bpp):
+                cur[c::bpp] = np.cumsum(line[c::bpp]) & 255
+        else:
+            cur = np.zeros(W * bpp, np.int64)
+            for i in range(W * bpp):
+                a = cur[i - bpp] if i >= bpp else 0
+                b = prev[i]
+                c = prev[i - bpp] if i >= bpp else 0
+                if ft == 3:
+                    pred = (a + b) >> 1
+                else:
+                    p = a + b - c
+                    pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
+                    pred = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+                cur[i] = (line[i] + pred) & 255
+        img[y] = cur
+        prev = cur
+    px = img.reshape(H, W, bpp)
+    if ctype in (2, 6):
+        r, g, b = px[..., 0], px[..., 1], px[..., 2]
+    elif ctype == 3:
+        table = np.zeros((256, 3), np.int64)
+        table[: len(pal)] = pal
+        rgb = table[px[..., 0]]
+        r, g, b = rgb[..., 0], rgb[..., 1], rgb[..., 2]
+    else:
+        r = g = b = px[..., 0]
+    if colour:
+        return np.stack([b, g, r], axis=-1).astype(np.uint8)
+    return ((9797 * r + 19234 * g + 3737 * b) >> 15).astype(np.uint8)
+
+
+def png_encode(img: np.ndarray, colour_type: int, filters=None, palette=None, level: int = 6, idat_split: int = 0) -> bytes:
+    """Test helper: an 8-bit non-interlaced PNG of `img` ([H][W] samples for types 0 / 3, [H][W][2|3|4] for 4 / 2 / 6) with a
+    chosen filter type per row (list or None = cycle through all five), so that every un-filter path is exercised."""
+    import struct
+    import zlib
+    img = np.ascontiguousarray(img, np.uint8)
+    H, W = img.shape[:2]
+    bpp = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[colour_type]
+    rows = img.reshape(H, W * bpp).astype(np.int64)
+    out = bytearray()
+    prev = np.zeros(W * bpp, np.int64)
+    for y in range(H):
+        ft = filters[y % len(filters)] if filters is not None else y % 5
+        cur = rows[y]
+        left = np.concatenate([np.zeros(bpp, np.int64), cur[:-bpp]])
+        upleft = np.concatenate([np.zeros(bpp, np.int64), prev[:-bpp]])
+        if ft == 0:
+            f = cur
+        elif ft == 1:
+            f = cur - left
+        elif ft == 2:
+            f = cur - prev
+        elif ft == 3:
+            f = cur - ((left + prev) >> 1)
+        else:
+            p = left + prev - upleft
+            pa, pb, pc = np.abs(p - left), np.abs(p - prev), np.abs(p - upleft)
+            pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, prev, upleft))
+            f = cur - pred
+        out.append(ft)
+        out += bytes((f & 255).astype(np.uint8))
+        prev = cur
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+    z = zlib.compress(bytes(out), level)
+    parts = [z] if idat_split <= 0 else [z[i:i + idat_split] for i in range(0, len(z), idat_split)]
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, 8, colour_type, 0, 0, 0))
+    if colour_type == 3:
+        png += chunk(b"PLTE", bytes(np.ascontiguousarray(palette, np.uint8).reshape(-1)))
+    for p in parts:
+        png += chunk(b"IDAT", p)
+    return png + chunk(b"IEND", b"")

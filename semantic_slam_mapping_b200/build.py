@@ -9,7 +9,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libssm.so")
-SOURCES = ["api.cu", "sgbm_cost.cu", "sgbm_aggregate.cu", "sgbm_vertical.cu", "sgbm_hsweep.cu", "sgbm_hsweep2.cu", "sgbm_select.cu", "mapper.cu", "comm.cu", "cues.cu", "labels.cu"]
+SOURCES = ["api.cu", "sgbm_cost.cu", "sgbm_aggregate.cu", "sgbm_vertical.cu", "sgbm_hsweep.cu", "sgbm_hsweep2.cu", "sgbm_select.cu", "mapper.cu", "comm.cu", "cues.cu", "labels.cu",
+           "ingest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-Wall", "--fmad=false"]
 
@@ -43,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=6) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"], capture_output=True, text=True)
+    r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-lcudart", "-ldl", "-lz"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB

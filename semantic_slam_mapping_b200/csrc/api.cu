@@ -485,6 +485,7 @@ void ssm_destroy(ssm_ctx* c)
     ssm_comm_destroy(c);
     cues_free(c);
     labels_free(c);
+    ingest_free(c);
     keyframes_free(c);
     free_all(c);
     delete c;

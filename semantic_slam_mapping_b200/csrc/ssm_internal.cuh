@@ -176,6 +176,7 @@ struct ssm_ctx {
     void* keyframes = nullptr;                       // cached camera-space keyframe clouds (api.cu: ssm_keyframe_*)
     void* labels_ws = nullptr;                       // label production workspace (labels.cu)
     void* cues_ws = nullptr;                         // dense motion cues workspace (cues.cu), allocated on first use
+    void* ingest_ws = nullptr;                       // PNG ingest staging (ingest.cu), allocated on first use
 };
 
 namespace ssm {
@@ -183,6 +184,7 @@ namespace ssm {
 void set_error(const std::string& s);
 void cues_free(ssm_ctx* c);   // cues.cu
 void labels_free(ssm_ctx* c); // labels.cu
+void ingest_free(ssm_ctx* c); // ingest.cu
 int cuda_fail(cudaError_t e, const char* what);
 
 #define SSM_CUDA(expr)                                                      \

@@ -27,6 +27,7 @@ SYMBOLS = [
     "ssm_map_integrate_keyframes",
     "ssm_labels_from_indices", "ssm_labels_from_indices_batch_device",
     "ssm_motion_cues_stage1_device", "ssm_motion_cues_stage2_device", "ssm_motion_cues_overflow",
+    "ssm_png_info", "ssm_png_decode_batch_device", "ssm_png_decode",
 ]
 
 
@@ -65,6 +66,9 @@ def load() -> C.CDLL:
     L.ssm_set_stage_timing.argtypes = [vp, i]
     L.ssm_stage_time_ms.argtypes = [vp, i, C.POINTER(C.c_float)]
     L.ssm_sgbm.argtypes = [vp, vp, vp, i, i, sz, vp, sz]
+    L.ssm_png_info.argtypes = [vp, sz, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
+    L.ssm_png_decode_batch_device.argtypes = [vp, i, C.POINTER(vp), C.POINTER(sz), i, i, i, vp, i, vp]
+    L.ssm_png_decode.argtypes = [vp, vp, sz, i, vp, sz, C.POINTER(i), C.POINTER(i)]
     L.ssm_sgbm_batch_device.argtypes = [vp, i, vp, vp, i, i, vp, vp]
     L.ssm_debug_copy_volume.argtypes = [vp, i, i, vp, sz]
     L.ssm_disparity_to_depth.argtypes = [vp, vp, i, i, sz, vp, sz]
@@ -276,6 +280,30 @@ class Context:
 
     def map_save_pcd(self, path: str):
         self._check(self._L.ssm_map_save_pcd(self._h, path.encode()))
+
+    # -- PNG ingest (FrameReader::next's cv::imread calls, src/rgbdframe.cpp:45-78, 138-180) ------------------------------
+    def png_info(self, png: bytes):
+        w, h, ch = C.c_int(), C.c_int(), C.c_int()
+        buf = np.frombuffer(png, np.uint8)
+        self._check(self._L.ssm_png_info(_ptr(buf), buf.size, C.byref(w), C.byref(h), C.byref(ch)))
+        return w.value, h.value, ch.value
+
+    def png_decode(self, png: bytes, colour: bool) -> np.ndarray:
+        """== cv2.imdecode(png, IMREAD_COLOR if colour else IMREAD_GRAYSCALE): inflate on the host, the rest on the GPU."""
+        w, h, _ = self.png_info(png)
+        buf = np.frombuffer(png, np.uint8)
+        out = np.empty((h, w, 3) if colour else (h, w), np.uint8)
+        self._check(self._L.ssm_png_decode(self._h, _ptr(buf), buf.size, 1 if colour else 0, _ptr(out), out.nbytes, None, None))
+        return out
+
+    def png_decode_batch_device(self, pngs, w: int, h: int, colour: bool, d_out, host_threads: int = 0, stream=None):
+        """`pngs`: list of bytes objects; d_out: device buffer [len(pngs)][h][w]([3]) u8."""
+        bufs = [np.frombuffer(p, np.uint8) for p in pngs]
+        n = len(bufs)
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = (C.c_size_t * n)(*[b.size for b in bufs])
+        self._check(self._L.ssm_png_decode_batch_device(self._h, n, ptrs, sizes, w, h, 1 if colour else 0, _ptr(d_out), host_threads,
+                                                        C.c_void_p(stream) if stream else None))
 
     # -- label production (experiment/segnet.cpp:121-135) ---------------------------------------------------------------
     def labels_from_indices(self, index_img, dw: int, dh: int, lut_bgr, want_raw: bool = True):
