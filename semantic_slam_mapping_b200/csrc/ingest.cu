@@ -62,7 +62,9 @@ static const char* png_inflate(const uint8_t* png, size_t n, PngInfo& info, uint
             if (err) break;
             have_ihdr = true;
             if (header_only) return nullptr;
-            if ((size_t)info.h * ((size_t)info.w * info.bpp + 1) > out_cap) { err = "PNG larger than the context's frame capacity"; break; }
+            if (info.w < 1 || info.h < 1 || info.w > (1 << 20) || info.h > (1 << 20)) { err = "PNG dimensions out of range"; break; }
+            if ((size_t)info.h * ((size_t)info.w * info.bpp + 1) > out_cap) { err = "PNG larger than the batch's frame size"; break; }
+            if ((size_t)info.h * ((size_t)info.w * info.bpp + 1) > 0x7fffffffull) { err = "PNG too large"; break; }
             if (inflateInit(&zs) != Z_OK) { err = "zlib inflateInit failed"; break; }
             stream_open = true;
             zs.next_out = out;
