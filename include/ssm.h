@@ -38,7 +38,7 @@ typedef enum {
     SSM_ERR_INVALID_ARGUMENT = -1, /* bad shape / parameter (the reference would throw cv::Exception) */
     SSM_ERR_CUDA = -2,             /* CUDA runtime error; text in ssm_last_error */
     SSM_ERR_NO_DEVICE = -3,        /* no sm_100 GPU: there is no CPU fallback */
-    SSM_ERR_CAPACITY = -4,         /* frame larger than ctx limits, or voxel hash table full */
+    SSM_ERR_CAPACITY = -4,         /* frame larger than ctx limits, or voxel hash full with no memory left to grow */
     SSM_ERR_COMM = -5,             /* NCCL error / communicator not initialised */
     SSM_ERR_UNSUPPORTED = -6       /* parameter combination outside the 16-bit cost range */
 } ssm_status;
@@ -70,7 +70,7 @@ typedef struct ssm_params {
     int colour_source;       /* 0: left rgb image (mapper.cpp:72-84); 1: semantic colour (mapper.cpp~:60) */
     /* capacities (allocation limits of the context) */
     int max_width, max_height, max_batch;
-    uint64_t map_capacity;   /* voxel hash slots (rounded up to a power of two) */
+    uint64_t map_capacity;   /* initial voxel hash slots (rounded up to a power of two); the table doubles when half full */
 } ssm_params;
 
 typedef struct ssm_ctx ssm_ctx;
@@ -148,8 +148,29 @@ int ssm_map_integrate_keyframes(ssm_ctx* ctx, const int* ids, int n);
 int ssm_map_clear(ssm_ctx* ctx);                      /* globalMap->clear(), mapper.cpp:125 */
 int ssm_map_size(ssm_ctx* ctx, uint64_t* n_voxels);   /* "points in global map", mapper.cpp:161 */
 /* Export up to max_voxels voxels of THIS rank's table; sorted != 0 orders them by (k,j,i)
- * (pcl::VoxelGrid output order).  *n_out receives the number written. */
+ * (pcl::VoxelGrid output order).  *n_out receives the number of voxels in the map.  Everything runs on the device -- K9
+ * voxel_finalize (centroid division, truncated mean colour, majority label) and a radix sort into PCL's order -- followed
+ * by one D2H copy per requested array (pinned destinations make those asynchronous DMA). */
 int ssm_map_export(ssm_ctx* ctx, const ssm_voxel_export* out, uint64_t max_voxels, int sorted, uint64_t* n_out);
+/* Device time (ms) of the kernels of the latest ssm_map_export* call on this context: K9 voxel_finalize + the radix sort. */
+int ssm_map_export_device_ms(ssm_ctx* ctx, float* ms);
+/* Multi-GPU export (SURVEY 8e "Export"): collective over the communicator -- every rank calls it with the same `sorted`;
+ * the ranks' tables (disjoint by ownership) travel to rank 0 over NCCL, which finalizes and orders the union and fills
+ * `out` (other ranks may pass out == NULL and receive *n_out = 0).  Without a communicator == ssm_map_export. */
+int ssm_map_export_gathered(ssm_ctx* ctx, const ssm_voxel_export* out, uint64_t max_voxels, int sorted, uint64_t* n_out);
+/* The voxel hash grows by itself (doubling, stream-ordered, no host stall; DESIGN.md "growth"); ssm_map_reserve grows it
+ * ahead of time to at least `slots` slots.  ssm_map_stats reports its state (blocking). */
+typedef struct ssm_map_statistics {
+    uint64_t slots;        /* table size */
+    uint64_t voxels;       /* occupied slots */
+    double load_factor;    /* voxels / slots */
+    double mean_probe;     /* mean displacement of a record from its home slot (linear probing) */
+    uint64_t max_probe;    /* longest displacement */
+    uint64_t grow_steps;   /* growth steps since ssm_create */
+    uint64_t table_bytes;  /* 128 bytes per slot */
+} ssm_map_statistics;
+int ssm_map_reserve(ssm_ctx* ctx, uint64_t slots);
+int ssm_map_stats(ssm_ctx* ctx, ssm_map_statistics* out);
 /* Write the fused map as a binary PCD with fields x y z rgba (pcl::PCDWriter, mapper.cpp:165-170). */
 int ssm_map_save_pcd(ssm_ctx* ctx, const char* path);
 

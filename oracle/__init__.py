@@ -525,14 +525,23 @@ def png_decode(png: bytes, colour: bool) -> np.ndarray:
     """cv2.imdecode(png, IMREAD_COLOR / IMREAD_GRAYSCALE) for 8-bit, non-interlaced PNG files (grey, grey + alpha, RGB,
     RGBA, palette): chunk parsing, inflate, the five scanline filters of the PNG specification, palette expansion, alpha
     stripping, BGR order; grey from colour as libpng's rgb_to_gray with OpenCV's coefficients,
-    (9797 R + 19234 G + 3737 B) >> 15.  Pinned against cv2 4.13 in tests/test_oracle_png.py."""
+    (9797 R + 19234 G + 3737 B) >> 15 -- in linear light through libpng's gamma_to_1 / gamma_from_1 tables when the file
+    carries a gAMA chunk outside 1 +- 0.05 or an sRGB chunk.  A CRC mismatch in a critical chunk or a scanline filter type
+    above 4 raises ValueError (cv2 returns None for such files).  Pinned against cv2 4.13 in tests/test_oracle_png.py."""
+    import math
     import struct
     import zlib
     assert png[:8] == b"\x89PNG\r\n\x1a\n", "not a PNG file"
-    pos, idat, pal, ihdr = 8, [], None, None
+    pos, idat, pal, ihdr, gama, srgb = 8, [], None, None, 0, False
     while pos + 12 <= len(png):
         (n,), typ = struct.unpack(">I", png[pos:pos + 4]), png[pos + 4:pos + 8]
         data = png[pos + 8:pos + 8 + n]
+        if not (typ[0] & 0x20) and struct.unpack(">I", png[pos + 8 + n:pos + 12 + n])[0] != (zlib.crc32(typ + data) & 0xffffffff):
+            raise ValueError("PNG chunk CRC mismatch")
+        if typ == b"gAMA" and not idat and n == 4 and 16 <= struct.unpack(">I", data)[0] <= 625000000:
+            gama = struct.unpack(">I", data)[0]
+        elif typ == b"sRGB" and not idat:
+            srgb = True
         if typ == b"IHDR":
             ihdr = struct.unpack(">IIBBBBB", data)
         elif typ == b"PLTE":
@@ -547,6 +556,8 @@ def png_decode(png: bytes, colour: bool) -> np.ndarray:
         raise ValueError("only 8-bit non-interlaced PNG files")
     bpp = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype]
     raw = np.frombuffer(zlib.decompress(b"".join(idat)), np.uint8).reshape(H, W * bpp + 1)
+    if (raw[:, 0] > 4).any():
+        raise ValueError("bad PNG scanline filter type")
     img = np.zeros((H, W * bpp), np.int64)
     prev = np.zeros(W * bpp, np.int64)
     for y in range(H):
@@ -586,10 +597,27 @@ def png_decode(png: bytes, colour: bool) -> np.ndarray:
         r = g = b = px[..., 0]
     if colour:
         return np.stack([b, g, r], axis=-1).astype(np.uint8)
-    return ((9797 * r + 19234 * g + 3737 * b) >> 15).astype(np.uint8)
+    plain = (9797 * r + 19234 * g + 3737 * b) >> 15
+    file_gamma = 45455 if srgb else gama
+    if ctype in (2, 3, 6) and file_gamma and not 95000 <= file_gamma <= 105000:
+        # libpng 1.6 png_build_gamma_table + png_do_rgb_to_gray (screen gamma defaults to the reciprocal of the file gamma)
+        def recip(a):
+            return int(math.floor(1e10 / a + .5))
+
+        def table(gm):
+            t = np.arange(256, dtype=np.int64)
+            if gm < 95000 or gm > 105000:
+                for i in range(1, 255):
+                    t[i] = int(math.floor(255 * math.pow(i / 255., gm * .00001) + .5))
+            return t
+        to1, from1 = table(recip(file_gamma)), table(recip(recip(file_gamma)))
+        lin = from1[(9797 * to1[r] + 19234 * to1[g] + 3737 * to1[b] + 16384) >> 15]
+        plain = np.where((r == g) & (r == b), plain, lin)
+    return plain.astype(np.uint8)
 
 
-def png_encode(img: np.ndarray, colour_type: int, filters=None, palette=None, level: int = 6, idat_split: int = 0) -> bytes:
+def png_encode(img: np.ndarray, colour_type: int, filters=None, palette=None, level: int = 6, idat_split: int = 0,
+               extra_chunks=()) -> bytes:
     """Test helper: an 8-bit non-interlaced PNG of `img` ([H][W] samples for types 0 / 3, [H][W][2|3|4] for 4 / 2 / 6) with a
     chosen filter type per row (list or None = cycle through all five), so that every un-filter path is exercised."""
     import struct
@@ -627,6 +655,8 @@ def png_encode(img: np.ndarray, colour_type: int, filters=None, palette=None, le
     z = zlib.compress(bytes(out), level)
     parts = [z] if idat_split <= 0 else [z[i:i + idat_split] for i in range(0, len(z), idat_split)]
     png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, 8, colour_type, 0, 0, 0))
+    for t, d in extra_chunks:      # ancillary chunks in front of PLTE / IDAT, e.g. (b"gAMA", struct.pack(">I", 45455))
+        png += chunk(t, d)
     if colour_type == 3:
         png += chunk(b"PLTE", bytes(np.ascontiguousarray(palette, np.uint8).reshape(-1)))
     for p in parts:

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libssm.so")
-SOURCES = ["api.cu", "sgbm_cost.cu", "sgbm_aggregate.cu", "sgbm_vertical.cu", "sgbm_hsweep.cu", "sgbm_hsweep2.cu", "sgbm_select.cu", "mapper.cu", "comm.cu", "cues.cu", "labels.cu",
+SOURCES = ["api.cu", "sgbm_cost.cu", "sgbm_aggregate.cu", "sgbm_vertical.cu", "sgbm_hsweep.cu", "sgbm_hsweep2.cu", "sgbm_select.cu", "mapper.cu", "voxel_table.cu", "comm.cu", "cues.cu", "labels.cu",
            "ingest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-Wall", "--fmad=false"]

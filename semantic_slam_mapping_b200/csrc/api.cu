@@ -41,6 +41,10 @@ static int validate(const ssm_params& p)
     if (p.uniqueness_ratio > 100) return fail(SSM_ERR_INVALID_ARGUMENT, "uniqueness_ratio must be <= 100");
     if (p.dilate_iterations < 0 || p.dilate_iterations > 8) return fail(SSM_ERR_INVALID_ARGUMENT, "dilate_iterations in [0, 8]");
     if (p.map_capacity < 1024) return fail(SSM_ERR_INVALID_ARGUMENT, "map_capacity must be >= 1024 slots");
+    // rgbdframe.cpp:112-113 stores ushort(pz * scale) for pz < roiz: the product has to fit 16 bits, or depths would wrap (and a
+    // wrapped value of 0 reads as "no depth")
+    if (!(p.roix > 0) || !(p.roiy > 0) || !(p.roiz > 0)) return fail(SSM_ERR_INVALID_ARGUMENT, "roix, roiy, roiz must be positive");
+    if (!(p.roiz * p.scale < 65536.0)) return fail(SSM_ERR_INVALID_ARGUMENT, "roiz * scale must stay below 65536 (16-bit depth image)");
     return SSM_OK;
 }
 
@@ -103,6 +107,10 @@ static void free_all(ssm_ctx* c)
                     c->d_recv, c->d_send_counts};
     for (void* q : ptrs)
         if (q) cudaFree(q);
+    for (auto& q : c->d_spill)
+        if (q) cudaFree(q);
+    if (c->h_mirror) cudaFreeHost(c->h_mirror);
+    if (c->export_ws) cudaFree(c->export_ws);
     for (auto& set : c->ev)
         for (auto& e : set)
             if (e) cudaEventDestroy(e);
@@ -202,6 +210,51 @@ static void offset_buffers(ssm_ctx* c, ptrdiff_t frames)
 }
 
 static int run_map(ssm_ctx* c, int B, const int16_t* d_disp, const uint8_t* d_sem, const uint8_t* d_rgb, const double* d_pose, cudaStream_t s);
+static int sync_route(ssm_ctx* c);
+
+// Growth policy of the streaming path.  The host never waits for the device here: it looks at the pinned mirror of the device
+// counters (refreshed behind every pipeline call, so stale by the one or two batches still in flight) and keeps the table
+// below half full with room for three more batches of the largest increase seen so far.  Whatever still does not fit lands in
+// the spill list and is re-inserted by the growth step this triggers.
+static int maybe_grow(ssm_ctx* c, cudaStream_t s)
+{
+    if (!c->auto_grow || !c->h_mirror) return SSM_OK;
+    // until one batch's voxel count has been seen there is no growth rate to plan with: the second and third call wait for
+    // the batch before them (once per map; the streaming overlap starts right after)
+    const uint64_t calls = c->pipeline_calls++;
+    if (c->mirror_dmax == 0 && calls >= 1 && calls <= 2) {
+        int rr = sync_route(c);
+        if (rr) return rr;
+        SSM_CUDA(cudaStreamSynchronize(s));
+    }
+    const volatile uint32_t* m = c->h_mirror;
+    const uint64_t nvox = m[1], parked = m[4];
+    if (nvox >= c->mirror_prev) c->mirror_dmax = std::max(c->mirror_dmax, nvox - c->mirror_prev);
+    c->mirror_prev = nvox;
+    const uint64_t need = nvox + 3 * c->mirror_dmax;
+    if (parked == 0 && 2 * need <= c->table_slots) return SSM_OK;
+    if (c->route_pending) {   // the exchange stream inserts into the table as well
+        SSM_CUDA(cudaStreamWaitEvent(s, c->ev_route_done, 0));
+        c->route_pending = false;
+    }
+    uint64_t want = c->table_slots;
+    while (want < 2 * need) want <<= 1;
+    if (want == c->table_slots) want <<= 1;
+    int rc = table_grow(c, want, s);
+    if (rc == SSM_ERR_CAPACITY) {   // no room for a bigger table: keep going on the old one; a full table surfaces at the next blocking call
+        c->auto_grow = false;
+        return SSM_OK;
+    }
+    if (rc) return rc;
+    // the mirror still shows the parked points until the next refresh: do not grow again for them
+    c->h_mirror[4] = 0;
+    return SSM_OK;
+}
+static int refresh_mirror(ssm_ctx* c, cudaStream_t s)
+{
+    if (c->h_mirror) SSM_CUDA(cudaMemcpyAsync(c->h_mirror, c->d_counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    return SSM_OK;
+}
 
 // The whole path on device buffers.  On a single GPU a batch of 64 frames or more (or SSM_TUNE3 = n > 1) is cut into
 // sub-batches that run on their own streams and meet again on `s`.
@@ -209,6 +262,7 @@ static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR,
                         const double* d_pose, int16_t* d_disp, cudaStream_t s)
 {
     int rc;
+    if ((rc = maybe_grow(c, s))) return rc;
     // sub-batches of at least ~one full wave of the vertical cluster kernel each (33 KITTI frames on a B200): kernels of
     // different sub-batches are bound by different units (shared memory, issue slots, HBM) and fill each other's tails
     const int want = c->tune[3] >= 0 ? c->tune[3] : (B >= 96 ? 3 : (B >= 64 ? 2 : 1));
@@ -219,7 +273,8 @@ static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR,
             c->route_pending = false;
         }
         if ((rc = run_sgbm(c, B, dL, dR, d_disp, s))) return rc;
-        return run_map(c, B, d_disp, d_sem, d_rgb, d_pose, s);
+        if ((rc = run_map(c, B, d_disp, d_sem, d_rgb, d_pose, s))) return rc;
+        return refresh_mirror(c, s);
     }
     const size_t npix = (size_t)c->dp.W * c->dp.H;
     if (!c->sub_fork) {
@@ -245,18 +300,20 @@ static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR,
     SSM_CUDA(cudaEventRecord(c->sub_fork, s));
     int first = 0;
     rc = SSM_OK;
+    auto cuda_rc = [](cudaError_t e, const char* what) { return e == cudaSuccess ? (int)SSM_OK : cuda_fail(e, what); };
     for (int i = 0; i < nsplit && rc == SSM_OK; ++i) {
         const int n = B / nsplit + (i < B % nsplit ? 1 : 0);
         cudaStream_t ss = c->sub_stream[i];
         SSM_CUDA(cudaStreamWaitEvent(ss, c->sub_fork, 0));
+        // no early return between the two offset_buffers calls: the work pointers must always be shifted back
         offset_buffers(c, first);
         rc = run_sgbm(c, n, dL + first * npix, dR + first * npix, d_disp + first * npix, ss);
         if (rc == SSM_OK) {
             // one GPU: the sub-batch fuses its own points; several ranks: routing is one exchange per batch (below)
             if (c->nranks > 1) {
                 // the previous batch's exchange may still be reading the depth / label / mask buffers
-                if (c->route_pending) SSM_CUDA(cudaStreamWaitEvent(ss, c->ev_route_done, 0));
-                rc = run_map_prepare(c, n, d_disp + first * npix, d_sem + first * npix * 3, ss);
+                if (c->route_pending) rc = cuda_rc(cudaStreamWaitEvent(ss, c->ev_route_done, 0), "cudaStreamWaitEvent(route)");
+                if (rc == SSM_OK) rc = run_map_prepare(c, n, d_disp + first * npix, d_sem + first * npix * 3, ss);
             }
             else rc = run_map(c, n, d_disp + first * npix, d_sem + first * npix * 3, d_rgb + first * npix * 3, d_pose + (size_t)first * 16, ss);
         }
@@ -278,6 +335,9 @@ static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR,
             SSM_CUDA(cudaEventRecord(c->ev_route_done, rs));
             c->route_pending = true;
         }
+        if (rc == SSM_OK) rc = refresh_mirror(c, rs);
+    } else if (rc == SSM_OK) {
+        rc = refresh_mirror(c, s);
     }
     return rc;
 }
@@ -309,19 +369,33 @@ static int sync_route(ssm_ctx* c)
     return SSM_OK;
 }
 
+// Blocking checkpoint of the voxel hash: waits for the work in flight, grows the table while points are parked in the spill
+// list (or the table is more than half full), reports sticky errors and the voxel count.
 static int check_overflow(ssm_ctx* c, cudaStream_t s, uint64_t* n_voxels)
 {
     int rr = sync_route(c);
     if (rr) return rr;
-    uint32_t h[4];
-    SSM_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
-    SSM_CUDA(cudaStreamSynchronize(s));
+    if (c->user_stream && c->user_stream != s) SSM_CUDA(cudaStreamSynchronize(c->user_stream));
+    uint32_t h[8];
+    for (int round = 0;; ++round) {
+        SSM_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+        SSM_CUDA(cudaStreamSynchronize(s));
+        if (h[2] & 1u) break;
+        const bool crowded = 2ull * h[1] > c->table_slots;
+        if (!c->auto_grow || (h[4] == 0 && !crowded) || round >= 8) break;
+        int rc = table_grow(c, 4ull * ((uint64_t)h[1] + h[4]), s);
+        if (rc == SSM_ERR_CAPACITY && h[4] == 0) { c->auto_grow = false; break; }   // crowded but complete: carry on
+        if (rc) return rc;
+    }
+    if (c->h_mirror) memcpy(c->h_mirror, h, sizeof(h));
     if (c->p2p && c->ipc_base) {
         uint32_t flag = 0;
         SSM_CUDA(cudaMemcpy(&flag, static_cast<char*>(c->ipc_base) + 8, sizeof(flag), cudaMemcpyDeviceToHost));
         if (flag) return fail(SSM_ERR_CAPACITY, "peer inbox overflow: more routed points than 2x a local batch (raise max_batch)");
     }
-    if (h[2] & 1u) return fail(SSM_ERR_CAPACITY, "voxel hash table is full (raise ssm_params.map_capacity)");
+    if ((h[2] & 1u) || h[4] != 0)
+        return fail(SSM_ERR_CAPACITY, c->auto_grow ? "voxel hash table and its spill list are full (raise ssm_params.map_capacity)"
+                                                   : "voxel hash table is full and cannot grow (device memory, or SSM_NO_GROW)");
     if (h[2] & 2u) return fail(SSM_ERR_CAPACITY, "point outside the 21-bit voxel coordinate range");
     if (n_voxels) *n_voxels = h[1];
     return SSM_OK;
@@ -405,6 +479,8 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
         c->no_pad = np && np[0] == '1';
         const char* sr = getenv("SSM_SELECT_ROWS");
         if (sr && atoi(sr) > 0) c->select_rows = atoi(sr);
+        const char* ng = getenv("SSM_NO_GROW");
+        c->auto_grow = !(ng && ng[0] == '1');
         const char* m = getenv("SSM_MAX_CLUSTER");
         if (m && atoi(m) > 0) c->max_cluster = atoi(m);
         const char* n = getenv("SSM_MIN_CLUSTER");
@@ -432,8 +508,13 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
     A(dalloc(&c->d_depth, npix)); A(dalloc(&c->d_label, npix)); A(dalloc(&c->d_mask, npix)); A(dalloc(&c->d_label_lut, (size_t)1 << 24));
     A(dalloc(&c->d_sem, npix * 3)); A(dalloc(&c->d_rgb, npix * 3));
     A(dalloc(&c->d_pose, (size_t)16 * c->cap_b)); A(dalloc(&c->d_min_disp, (size_t)c->cap_b));
-    A(dalloc(&c->d_points, npix)); A(dalloc(&c->d_blk_count, npix / 1024 + 2)); A(dalloc(&c->d_counters, 8));
-    A(dalloc(&c->d_table, slots));
+    A(dalloc(&c->d_points, npix)); A(dalloc(&c->d_blk_count, npix / 1024 + 2)); A(dalloc(&c->d_counters, 16));
+    // the table comes from the stream-ordered allocator, so that a growth step can release it without stalling the host
+    A(cudaMallocAsync(reinterpret_cast<void**>(&c->d_table), sizeof(Voxel) * slots, c->stream));
+    c->spill_cap = std::min<size_t>(std::max<size_t>(npix, (size_t)1 << 16), (size_t)1 << 22);
+    A(dalloc(&c->d_spill[0], c->spill_cap)); A(dalloc(&c->d_spill[1], c->spill_cap));
+    A(cudaHostAlloc(reinterpret_cast<void**>(&c->h_mirror), 8 * sizeof(uint32_t), cudaHostAllocDefault));
+    if (c->h_mirror) memset(c->h_mirror, 0, 8 * sizeof(uint32_t));
     if (e != cudaSuccess) {
         free_all(c);
         delete c;
@@ -494,6 +575,7 @@ void ssm_destroy(ssm_ctx* c)
 int ssm_set_stage_timing(ssm_ctx* c, int enabled)
 {
     if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
+    SSM_ENTER(c);
     c->timing = enabled != 0;
     c->ev_used = 0;
     c->ev_set = 0;
@@ -502,6 +584,7 @@ int ssm_set_stage_timing(ssm_ctx* c, int enabled)
 int ssm_stage_time_ms(ssm_ctx* c, int stage, float* ms)
 {
     if (!c || !ms || stage < 0 || stage >= SSM_STAGE_COUNT) return fail(SSM_ERR_INVALID_ARGUMENT, "bad stage");
+    SSM_ENTER(c);
     if (!c->timing || c->ev_used == 0) return fail(SSM_ERR_INVALID_ARGUMENT, "stage timing is off or no pipeline call was timed");
     int rc = finish_timing(c);   // waits for the last timed pipeline call
     if (rc) return rc;
@@ -511,6 +594,7 @@ int ssm_stage_time_ms(ssm_ctx* c, int stage, float* ms)
 int ssm_synchronize(ssm_ctx* c)
 {
     if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
+    SSM_ENTER(c);
     SSM_CUDA(cudaStreamSynchronize(c->stream));
     return sync_route(c);
 }
@@ -518,6 +602,7 @@ int ssm_synchronize(ssm_ctx* c)
 int ssm_set_route_overlap(ssm_ctx* c, int enabled)
 {
     if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
+    SSM_ENTER(c);
     int rc = sync_route(c);
     if (rc) return rc;
     c->route_overlap = enabled != 0;
@@ -528,6 +613,7 @@ int ssm_set_route_overlap(ssm_ctx* c, int enabled)
 int ssm_sgbm_batch_device(ssm_ctx* c, int batch, const uint8_t* dL, const uint8_t* dR, int w, int h, int16_t* d_disp, void* stream)
 {
     if (!c || !dL || !dR || !d_disp) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
     int rc = set_shape(c, w, h, batch);
     if (rc) return rc;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
@@ -537,6 +623,7 @@ int ssm_sgbm_batch_device(ssm_ctx* c, int batch, const uint8_t* dL, const uint8_
 int ssm_sgbm(ssm_ctx* c, const uint8_t* left, const uint8_t* right, int w, int h, size_t stride, int16_t* disp, size_t disp_stride)
 {
     if (!c || !left || !right || !disp) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
     if (stride < (size_t)w || disp_stride < (size_t)w * 2) return fail(SSM_ERR_INVALID_ARGUMENT, "stride smaller than a row");
     int rc = set_shape(c, w, h, 1);
     if (rc) return rc;
@@ -553,6 +640,7 @@ int ssm_sgbm(ssm_ctx* c, const uint8_t* left, const uint8_t* right, int w, int h
 int ssm_debug_copy_volume(ssm_ctx* c, int which, int bi, void* dst, size_t bytes)
 {
     if (!c || !dst || bi < 0 || bi >= c->cap_b) return fail(SSM_ERR_INVALID_ARGUMENT, "bad argument");
+    SSM_ENTER(c);
     const DevParams& p = c->dp;
     const size_t cells = (size_t)p.H * p.W1 * p.D, lcells = (size_t)p.H * p.W1 * p.Dl, npix = (size_t)p.H * p.W;
     const void* src = nullptr;
@@ -577,6 +665,7 @@ int ssm_debug_copy_volume(ssm_ctx* c, int which, int bi, void* dst, size_t bytes
 int ssm_disparity_to_depth(ssm_ctx* c, const int16_t* disp, int w, int h, size_t disp_stride, uint16_t* depth, size_t depth_stride)
 {
     if (!c || !disp || !depth) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
     int rc = set_shape(c, w, h, 1);
     if (rc) return rc;
     cudaStream_t s = c->stream;
@@ -591,6 +680,7 @@ int ssm_disparity_to_depth(ssm_ctx* c, const int16_t* disp, int w, int h, size_t
 int ssm_semantic_motion_fuse(ssm_ctx* c, const uint8_t* sem, int w, int h, size_t stride, uint8_t* mask, size_t mask_stride)
 {
     if (!c || !sem || !mask) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
     int rc = set_shape(c, w, h, 1);
     if (rc) return rc;
     cudaStream_t s = c->stream;
@@ -616,6 +706,7 @@ int ssm_generate_point_cloud(ssm_ctx* c, const uint16_t* depth, const uint8_t* s
                              const double* T, float* xyz, uint32_t* rgba, uint8_t* label, int max_points, int* n_points)
 {
     if (!c || !depth || !sem || !rgb || !T || !n_points) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
     int rc = set_shape(c, w, h, 1);
     if (rc) return rc;
     cudaStream_t s = c->stream;
@@ -642,6 +733,7 @@ int ssm_generate_point_cloud(ssm_ctx* c, const uint16_t* depth, const uint8_t* s
 int ssm_map_integrate_frame(ssm_ctx* c, const uint16_t* depth, const uint8_t* sem, const uint8_t* rgb, int w, int h, const double* T)
 {
     if (!c || !depth || !sem || !rgb || !T) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
     int rc = set_shape(c, w, h, 1);
     if (rc) return rc;
     cudaStream_t s = c->stream;
@@ -687,6 +779,7 @@ static void keyframes_free(ssm_ctx* c)
 int ssm_keyframe_add(ssm_ctx* c, const uint16_t* depth, const uint8_t* sem, const uint8_t* rgb, int w, int h, const double* T, int* id_out)
 {
     if (!c || !depth || !sem || !rgb || !T || !id_out) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
     if (c->nranks > 1) return fail(SSM_ERR_UNSUPPORTED, "the keyframe cache is per context; with a communicator use ssm_map_integrate_frame");
     int rc = set_shape(c, w, h, 1);
     if (rc) return rc;
@@ -723,6 +816,7 @@ static Keyframe* kf_get(ssm_ctx* c, int id)
 int ssm_keyframe_set_pose(ssm_ctx* c, int id, const double* T)
 {
     if (!c || !T) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
     Keyframe* k = kf_get(c, id);
     if (!k) return fail(SSM_ERR_INVALID_ARGUMENT, "unknown keyframe id");
     std::memcpy(k->T, T, sizeof(k->T));
@@ -732,6 +826,7 @@ int ssm_keyframe_set_pose(ssm_ctx* c, int id, const double* T)
 int ssm_keyframe_release(ssm_ctx* c, int id)
 {
     if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
+    SSM_ENTER(c);
     Keyframe* k = kf_get(c, id);
     if (!k) return fail(SSM_ERR_INVALID_ARGUMENT, "unknown keyframe id");
     SSM_CUDA(cudaStreamSynchronize(c->stream));
@@ -743,6 +838,7 @@ int ssm_keyframe_release(ssm_ctx* c, int id)
 int ssm_keyframe_count(ssm_ctx* c, int* n_live, uint64_t* n_points)
 {
     if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
+    SSM_ENTER(c);
     KeyframeStore* st = static_cast<KeyframeStore*>(c->keyframes);
     int live = 0;
     uint64_t pts = 0;
@@ -758,6 +854,7 @@ int ssm_keyframe_count(ssm_ctx* c, int* n_live, uint64_t* n_points)
 static int integrate_keyframes(ssm_ctx* c, const int* ids, int n, bool clear_first)
 {
     if (!c || n < 0) return fail(SSM_ERR_INVALID_ARGUMENT, "bad argument");
+    SSM_ENTER(c);
     KeyframeStore* st = static_cast<KeyframeStore*>(c->keyframes);
     cudaStream_t s = c->stream;
     int rc;
@@ -780,17 +877,29 @@ int ssm_map_integrate_keyframes(ssm_ctx* c, const int* ids, int n) { return inte
 int ssm_map_integrate_points(ssm_ctx* c, const float* xyz, const uint32_t* rgba, const uint8_t* label, int n)
 {
     if (!c || (n > 0 && (!xyz || !rgba || !label)) || n < 0) return fail(SSM_ERR_INVALID_ARGUMENT, "bad argument");
+    SSM_ENTER(c);
     const size_t cap = (size_t)c->cap_w * c->cap_h * c->cap_b;
     cudaStream_t s = c->stream;
     std::vector<Point> pts;
-    for (size_t base = 0; base < (size_t)n; base += cap) {
+    // With a communicator every round is collective (bucket, all-gather of the counts, grouped send / recv), so the ranks
+    // agree on the number of rounds first: the largest ceil(n / cap) of any rank, at least one; a rank without points left
+    // takes part with empty rounds.
+    size_t rounds = ((size_t)n + cap - 1) / cap;
+    if (c->nranks > 1) {
+        uint32_t r32 = (uint32_t)std::max<size_t>(rounds, 1);
+        int rc0 = comm_allreduce_max(c, &r32, s);
+        if (rc0) return rc0;
+        rounds = r32;
+    }
+    for (size_t round = 0; round < rounds; ++round) {
+        const size_t base = std::min(round * cap, (size_t)n);
         const size_t m = std::min(cap, (size_t)n - base);
         pts.resize(m);
         for (size_t i = 0; i < m; ++i) {
             const size_t q = base + i;
             pts[i] = Point{xyz[3 * q], xyz[3 * q + 1], xyz[3 * q + 2], rgba[q] & 0xffffffu, (uint32_t)label[q]};
         }
-        SSM_CUDA(cudaMemcpyAsync(c->d_points, pts.data(), sizeof(Point) * m, cudaMemcpyHostToDevice, s));
+        if (m) SSM_CUDA(cudaMemcpyAsync(c->d_points, pts.data(), sizeof(Point) * m, cudaMemcpyHostToDevice, s));
         int rc;
         if (c->nranks > 1) {
             const uint32_t mm = (uint32_t)m;
@@ -807,111 +916,120 @@ int ssm_map_integrate_points(ssm_ctx* c, const float* xyz, const uint32_t* rgba,
 int ssm_map_clear(ssm_ctx* c)
 {
     if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
+    SSM_ENTER(c);
     int rc = sync_route(c);
     if (rc) return rc;
+    if (c->user_stream) SSM_CUDA(cudaStreamSynchronize(c->user_stream));
     rc = launch_map_clear(c, c->stream);
     if (rc) return rc;
     SSM_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->h_mirror) memset(c->h_mirror, 0, 8 * sizeof(uint32_t));
+    c->mirror_prev = 0;
+    c->pipeline_calls = 0;
     return SSM_OK;
 }
 
 int ssm_map_size(ssm_ctx* c, uint64_t* n)
 {
     if (!c || !n) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
     return check_overflow(c, c->stream, n);
-}
-
-static int export_records(ssm_ctx* c, std::vector<Voxel>& recs, bool sorted)
-{
-    uint64_t n = 0;
-    int rc = check_overflow(c, c->stream, &n);
-    if (rc) return rc;
-    recs.resize(n);
-    if (n == 0) return SSM_OK;
-    Voxel* d_out = nullptr;
-    SSM_CUDA(cudaMalloc(&d_out, sizeof(Voxel) * n));
-    rc = launch_export(c, d_out, (uint32_t)n, c->stream);
-    if (rc == SSM_OK && cudaMemcpyAsync(recs.data(), d_out, sizeof(Voxel) * n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
-        rc = cuda_fail(cudaGetLastError(), "export copy");
-    if (rc == SSM_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "export sync");
-    cudaFree(d_out);
-    if (rc) return rc;
-    if (sorted) {
-        // pcl::VoxelGrid orders by idx = i + j*dx + k*dx*dy  <=>  lexicographic (k, j, i)
-        std::sort(recs.begin(), recs.end(), [](const Voxel& a, const Voxel& b) {
-            int ai, aj, ak, bi, bj, bk;
-            unpack_key(a.key, ai, aj, ak);
-            unpack_key(b.key, bi, bj, bk);
-            if (ak != bk) return ak < bk;
-            if (aj != bj) return aj < bj;
-            return ai < bi;
-        });
-    }
-    return SSM_OK;
-}
-
-static void finalize_voxel(const ssm_ctx* c, const Voxel& v, float xyz[3], uint32_t* rgba, uint8_t* label)
-{
-    const double n = (double)v.n;
-    xyz[0] = (float)((double)(long long)v.sx / kFixScale / n);
-    xyz[1] = (float)((double)(long long)v.sy / kFixScale / n);
-    xyz[2] = (float)((double)(long long)v.sz / kFixScale / n);
-    // PCL: centroid /= float(n); rgb = int(r)<<16 | int(g)<<8 | int(b)  (truncation, alpha 0)
-    const float fn = (float)v.n;
-    const float r = (float)v.sr / fn, g = (float)v.sg / fn, b = (float)v.sb / fn;
-    *rgba = ((uint32_t)(int)r << 16) | ((uint32_t)(int)g << 8) | (uint32_t)(int)b;
-    uint32_t bestv = 0;
-    int bestl = SSM_LABEL_UNKNOWN;
-    for (int l = 0; l < c->p.num_labels; ++l)
-        if (v.votes[l] > bestv) { bestv = v.votes[l]; bestl = l; }
-    *label = (uint8_t)bestl;
 }
 
 int ssm_map_export(ssm_ctx* c, const ssm_voxel_export* out, uint64_t max_voxels, int sorted, uint64_t* n_out)
 {
     if (!c || !out || !n_out) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
-    std::vector<Voxel> recs;
-    int rc = export_records(c, recs, sorted != 0);
+    SSM_ENTER(c);
+    uint64_t n = 0;
+    int rc = check_overflow(c, c->stream, &n);
     if (rc) return rc;
-    const uint64_t n = std::min<uint64_t>(recs.size(), max_voxels);
-    const int L = c->p.num_labels;
-    for (uint64_t q = 0; q < n; ++q) {
-        const Voxel& v = recs[q];
-        float xyz[3];
-        uint32_t rgba;
-        uint8_t label;
-        finalize_voxel(c, v, xyz, &rgba, &label);
-        if (out->ijk) { int i, j, k; unpack_key(v.key, i, j, k); out->ijk[3 * q] = i; out->ijk[3 * q + 1] = j; out->ijk[3 * q + 2] = k; }
-        if (out->xyz) { out->xyz[3 * q] = xyz[0]; out->xyz[3 * q + 1] = xyz[1]; out->xyz[3 * q + 2] = xyz[2]; }
-        if (out->rgba) out->rgba[q] = rgba;
-        if (out->label) out->label[q] = label;
-        if (out->count) out->count[q] = v.n;
-        if (out->votes) for (int l = 0; l < L; ++l) out->votes[q * L + l] = v.votes[l];
-    }
-    *n_out = recs.size();
+    // K9 on the device: index the occupied records, radix-sort them into pcl::VoxelGrid's output order, finalize, copy out
+    return export_records_device(c, c->d_table, c->table_slots, n, sorted != 0, out, max_voxels, n_out, c->stream, &c->last_export_ms);
+}
+
+int ssm_map_export_device_ms(ssm_ctx* c, float* ms)
+{
+    if (!c || !ms) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    *ms = c->last_export_ms;
     return SSM_OK;
+}
+
+// Every rank calls this; rank 0 receives the union of the ranks' tables (disjoint by ownership) in pcl::VoxelGrid order.
+int ssm_map_export_gathered(ssm_ctx* c, const ssm_voxel_export* out, uint64_t max_voxels, int sorted, uint64_t* n_out)
+{
+    if (!c || !n_out) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
+    if (c->nranks <= 1) return ssm_map_export(c, out, max_voxels, sorted, n_out);
+    uint64_t n = 0;
+    int rc = check_overflow(c, c->stream, &n);   // (an error here leaves the peers waiting in the collective: the caller tears down)
+    if (rc) return rc;
+    Voxel* d_all = nullptr;
+    uint64_t n_all = 0;
+    if ((rc = comm_gather_records(c, &d_all, &n_all, c->stream))) return rc;
+    *n_out = 0;
+    if (c->rank == 0) {
+        if (!out) rc = fail(SSM_ERR_INVALID_ARGUMENT, "rank 0 needs the output arrays");
+        else rc = export_records_device(c, d_all, n_all, n_all, sorted != 0, out, max_voxels, n_out, c->stream, &c->last_export_ms);
+    }
+    if (d_all) cudaFree(d_all);
+    return rc;
 }
 
 int ssm_map_save_pcd(ssm_ctx* c, const char* path)
 {
     if (!c || !path) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
-    std::vector<Voxel> recs;
-    int rc = export_records(c, recs, true);
+    SSM_ENTER(c);
+    uint64_t n = 0;
+    int rc = check_overflow(c, c->stream, &n);
     if (rc) return rc;
+    std::vector<float> xyz(3 * n);
+    std::vector<uint32_t> rgba(n);
+    ssm_voxel_export ex = {};
+    ex.xyz = xyz.data();
+    ex.rgba = rgba.data();
+    uint64_t got = 0;
+    if ((rc = export_records_device(c, c->d_table, c->table_slots, n, true, &ex, n, &got, c->stream, nullptr))) return rc;
     FILE* f = fopen(path, "wb");
     if (!f) return fail(SSM_ERR_INVALID_ARGUMENT, std::string("cannot open ") + path);
     // pcl::PCDWriter::write (ASCII header, binary body) for PointXYZRGBA: x y z rgba
     fprintf(f, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z rgba\nSIZE 4 4 4 4\nTYPE F F F U\n"
-               "COUNT 1 1 1 1\nWIDTH %zu\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %zu\nDATA binary\n", recs.size(), recs.size());
-    for (const Voxel& v : recs) {
-        float xyz[3];
-        uint32_t rgba;
-        uint8_t label;
-        finalize_voxel(c, v, xyz, &rgba, &label);
-        fwrite(xyz, sizeof(float), 3, f);
-        fwrite(&rgba, sizeof(uint32_t), 1, f);
+               "COUNT 1 1 1 1\nWIDTH %zu\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %zu\nDATA binary\n", (size_t)got, (size_t)got);
+    for (uint64_t q = 0; q < got; ++q) {
+        fwrite(&xyz[3 * q], sizeof(float), 3, f);
+        fwrite(&rgba[q], sizeof(uint32_t), 1, f);
     }
     fclose(f);
+    return SSM_OK;
+}
+
+int ssm_map_reserve(ssm_ctx* c, uint64_t slots)
+{
+    if (!c) return fail(SSM_ERR_INVALID_ARGUMENT, "null ctx");
+    SSM_ENTER(c);
+    int rc = check_overflow(c, c->stream, nullptr);
+    if (rc) return rc;
+    if (slots <= c->table_slots) return SSM_OK;
+    if ((rc = table_grow(c, slots, c->stream))) return rc;
+    SSM_CUDA(cudaStreamSynchronize(c->stream));
+    return SSM_OK;
+}
+
+int ssm_map_stats(ssm_ctx* c, ssm_map_statistics* st)
+{
+    if (!c || !st) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
+    uint64_t n = 0;
+    int rc = check_overflow(c, c->stream, &n);
+    if (rc) return rc;
+    unsigned long long t[3] = {0, 0, 0};
+    if ((rc = table_stats(c, c->stream, t))) return rc;
+    st->slots = c->table_slots;
+    st->voxels = t[0];
+    st->load_factor = (double)t[0] / (double)c->table_slots;
+    st->mean_probe = t[0] ? (double)t[1] / (double)t[0] : 0.0;
+    st->max_probe = t[2];
+    st->grow_steps = c->grows;
+    st->table_bytes = c->table_slots * sizeof(Voxel);
     return SSM_OK;
 }
 
@@ -920,9 +1038,11 @@ int ssm_pipeline_batch_device(ssm_ctx* c, int batch, const uint8_t* dL, const ui
                               const uint8_t* d_rgb, const double* d_poses, int w, int h, int16_t* d_disp_out, void* stream)
 {
     if (!c || !dL || !dR || !d_sem || !d_rgb || !d_poses) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
     int rc = set_shape(c, w, h, batch);
     if (rc) return rc;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    c->user_stream = stream ? (cudaStream_t)stream : nullptr;
     int16_t* d_disp = d_disp_out ? d_disp_out : c->d_disp;
     return run_pipeline(c, batch, dL, dR, d_sem, d_rgb, d_poses, d_disp, s);
 }
@@ -931,6 +1051,7 @@ int ssm_pipeline_batch_host_async(ssm_ctx* c, int batch, const uint8_t* left, co
                                   const uint8_t* rgb, const double* poses, int w, int h, uint32_t* n_voxels_pinned)
 {
     if (!c || !left || !right || !sem || !rgb || !poses) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
     int rc = set_shape(c, w, h, batch);
     if (rc) return rc;
     SSM_CUDA(cudaSetDevice(c->device));
@@ -973,6 +1094,7 @@ int ssm_pipeline_batch_host(ssm_ctx* c, int batch, const uint8_t* left, const ui
                             const uint8_t* rgb, const double* poses, int w, int h, int16_t* disp_out, uint64_t* n_voxels_out)
 {
     if (!c || !left || !right || !sem || !rgb || !poses) return fail(SSM_ERR_INVALID_ARGUMENT, "null argument");
+    SSM_ENTER(c);
     int rc = set_shape(c, w, h, batch);
     if (rc) return rc;
     cudaStream_t s = c->stream;

@@ -186,6 +186,69 @@ int comm_barrier(ssm_ctx* c, cudaStream_t s)
     return SSM_OK;
 }
 
+// blocking: *value = max over the ranks (used to agree on collective round counts)
+int comm_allreduce_max(ssm_ctx* c, uint32_t* value, cudaStream_t s)
+{
+    if (!c->comm) {
+        set_error("ssm_comm_init has not been called on this context");
+        return SSM_ERR_COMM;
+    }
+    uint32_t* word = c->d_send_counts + 1;   // scratch (word 0 is the barrier's)
+    SSM_CUDA(cudaMemcpyAsync(word, value, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    SSM_NCCL(g_nccl.AllReduce(word, word, 1, ncclUint32, 2 /* ncclMax */, (ncclComm_t)c->comm, s));
+    SSM_CUDA(cudaMemcpyAsync(value, word, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    SSM_CUDA(cudaStreamSynchronize(s));
+    return SSM_OK;
+}
+
+// SURVEY 8e "Export": every rank compacts the occupied records of its table and sends them to rank 0, which returns the
+// dense union (the tables are disjoint by ownership).  *d_all is a cudaMalloc'ed array the caller frees (NULL off rank 0).
+int comm_gather_records(ssm_ctx* c, Voxel** d_all, uint64_t* n_all, cudaStream_t s)
+{
+    *d_all = nullptr;
+    *n_all = 0;
+    if (!c->comm) {
+        set_error("ssm_comm_init has not been called on this context");
+        return SSM_ERR_COMM;
+    }
+    const int R = c->nranks, me = c->rank;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    uint32_t mine = 0;
+    SSM_CUDA(cudaMemcpyAsync(&mine, c->d_counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    uint32_t* d_cnt = c->d_send_counts + 3 * R;   // [R] gathered voxel counts (the [R][R] scratch of the routing path)
+    SSM_NCCL(g_nccl.AllGather(c->d_counters + 1, d_cnt, 1, ncclUint32, comm, s));
+    std::vector<uint32_t> cnt(R);
+    SSM_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(uint32_t) * R, cudaMemcpyDeviceToHost, s));
+    SSM_CUDA(cudaStreamSynchronize(s));
+    uint64_t total = 0;
+    for (int r = 0; r < R; ++r) total += cnt[r];
+    Voxel* buf = nullptr;
+    const uint64_t need = me == 0 ? total : mine;
+    if (need) SSM_CUDA(cudaMalloc(reinterpret_cast<void**>(&buf), sizeof(Voxel) * need));
+    int rc = SSM_OK;
+    if (mine) rc = launch_export(c, buf, mine, s);   // rank 0's own records come first
+    if (rc == SSM_OK) {
+        ncclResult_t nr = g_nccl.GroupStart();
+        uint64_t off = cnt[0];
+        for (int r = 1; r < R && nr == 0; ++r) {
+            if (me == 0 && cnt[r]) nr = g_nccl.Recv(buf + off, (size_t)cnt[r] * sizeof(Voxel), ncclUint8, r, comm, s);
+            if (me == r && mine) nr = g_nccl.Send(buf, (size_t)mine * sizeof(Voxel), ncclUint8, 0, comm, s);
+            off += cnt[r];
+        }
+        const ncclResult_t ne = g_nccl.GroupEnd();
+        if (nr == 0) nr = ne;
+        if (nr != 0) rc = nccl_fail(nr, "record gather");
+    }
+    if (rc == SSM_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "record gather");
+    if (rc != SSM_OK || me != 0) {
+        if (buf) cudaFree(buf);
+        return rc;
+    }
+    *d_all = buf;
+    *n_all = total;
+    return SSM_OK;
+}
+
 int points_route_p2p(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t* d_sem, const uint8_t* d_rgb, const double* d_pose,
                      cudaStream_t s)
 {

@@ -6,11 +6,16 @@
 // rest -- PNG un-filtering (None / Sub / Up / Average / Paeth), palette expansion, alpha stripping, RGB -> BGR reordering
 // and the colour -> grey conversion -- runs on the GPU and writes straight into the [batch][h][w] / [batch][h][w][3] device
 // images the pipeline entry points take.  Bit-exact with cv2 4.13 imread / imdecode: grey from colour is libpng's
-// png_set_rgb_to_gray(0.299, 0.587) arithmetic, (9797 R + 19234 G + 3737 B) >> 15, which is what OpenCV asks libpng for.
+// png_set_rgb_to_gray(0.299, 0.587) arithmetic, (9797 R + 19234 G + 3737 B) >> 15, which is what OpenCV asks libpng for --
+// and, for files that carry a gAMA chunk outside 1 +- 0.05 or an sRGB chunk, libpng's linear-light variant of it (samples
+// through the gamma_to_1 table, weighted sum rounded, back through gamma_from_1; pixels with R == G == B pass unchanged).
+// Like libpng, the decoder verifies the CRC of the critical chunks and rejects scanline filter types above 4: cv::imread
+// returns an empty image for such files, so they are errors here, never silently different pixels.
 // Supported: 8-bit grey, grey + alpha, RGB, RGBA and palette images, non-interlaced (what KITTI and SegNet tools write).
 #include <zlib.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -24,7 +29,25 @@ struct PngInfo {
     int w = 0, h = 0, bpp = 0;        // bytes per pixel of the filtered scanlines (1, 2, 3, 4)
     int colour_type = 0;              // 0 grey, 2 RGB, 3 palette, 4 grey + alpha, 6 RGBA
     uint8_t palette[256 * 3] = {};
+    uint32_t file_gamma = 0;          // gAMA value (x 100000) or 45455 for an sRGB chunk; 0 = none / not significant
 };
+
+// libpng 1.6 png_build_gamma_table as it runs for OpenCV's grey read of a colour file (no png_set_gamma call, so the screen
+// gamma defaults to the reciprocal of the file gamma): to_1 = correct(i, 1 / file), from_1 = correct(i, 1 / screen) with
+// correct(i, g) = floor(255 * pow(i / 255, g * 1e-5) + .5), identity when g is within 1 +- 0.05 (png_gamma_significant).
+static inline long long png_reciprocal_fixed(long long a) { return (long long)floor(1e10 / (double)a + .5); }
+static void png_gamma_table(long long g, uint8_t* t)
+{
+    const bool significant = g < 95000 || g > 105000;
+    for (int i = 0; i < 256; ++i)
+        t[i] = (!significant || i == 0 || i == 255) ? (uint8_t)i : (uint8_t)floor(255.0 * pow(i / 255.0, (double)g * .00001) + .5);
+}
+static void png_gray_tables(uint32_t file_gamma, uint8_t* to1, uint8_t* from1)
+{
+    const long long screen = png_reciprocal_fixed(file_gamma);
+    png_gamma_table(png_reciprocal_fixed(file_gamma), to1);
+    png_gamma_table(png_reciprocal_fixed(screen), from1);
+}
 static inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
 // Parses the chunks and inflates the IDAT stream into `out` (h rows of 1 filter byte + w * bpp bytes).  Returns an
@@ -34,7 +57,8 @@ static const char* png_inflate(const uint8_t* png, size_t n, PngInfo& info, uint
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     if (n < 8 + 25 || memcmp(png, sig, 8) != 0) return "not a PNG file";
     size_t pos = 8;
-    bool have_ihdr = false, stream_open = false, done = false;
+    bool have_ihdr = false, stream_open = false, done = false, seen_idat = false, have_srgb = false;
+    uint32_t gama = 0;
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
     const char* err = nullptr;
@@ -43,6 +67,11 @@ static const char* png_inflate(const uint8_t* png, size_t n, PngInfo& info, uint
         const uint8_t* type = png + pos + 4;
         const uint8_t* data = png + pos + 8;
         if ((size_t)len > n - pos - 12) { err = "truncated PNG chunk"; break; }
+        // libpng treats a CRC mismatch in a critical chunk (upper-case first letter) as an error, in an ancillary one as a warning
+        if (!(type[0] & 0x20) && (uint32_t)crc32(crc32(0L, Z_NULL, 0), type, (uInt)(4 + len)) != be32(data + len)) {
+            err = "PNG chunk CRC mismatch";
+            break;
+        }
         if (!memcmp(type, "IHDR", 4)) {
             if (len != 13) { err = "bad IHDR"; break; }
             info.w = (int)be32(data); info.h = (int)be32(data + 4);
@@ -75,7 +104,12 @@ static const char* png_inflate(const uint8_t* png, size_t n, PngInfo& info, uint
         } else if (!memcmp(type, "PLTE", 4)) {
             if (len > 768 || len % 3) { err = "bad PLTE"; break; }
             memcpy(info.palette, data, len);
+        } else if (!memcmp(type, "gAMA", 4) && !seen_idat) {
+            if (len == 4 && be32(data) >= 16 && be32(data) <= 625000000u) gama = be32(data);   // out-of-range values are ignored by libpng
+        } else if (!memcmp(type, "sRGB", 4) && !seen_idat) {
+            have_srgb = true;
         } else if (!memcmp(type, "IDAT", 4)) {
+            seen_idat = true;
             zs.next_in = const_cast<Bytef*>(data);
             zs.avail_in = len;
             const int rc = inflate(&zs, Z_NO_FLUSH);
@@ -90,6 +124,13 @@ static const char* png_inflate(const uint8_t* png, size_t n, PngInfo& info, uint
         inflateEnd(&zs);
     }
     if (!err && !have_ihdr) err = "PNG without IHDR";
+    if (!err) {
+        const size_t rb = (size_t)info.w * info.bpp + 1;
+        for (int y = 0; y < info.h; ++y)
+            if (out[(size_t)y * rb] > 4) { err = "bad PNG scanline filter type"; break; }
+        const uint32_t g = have_srgb ? 45455u : gama;   // an sRGB chunk overrides gAMA
+        info.file_gamma = (g != 0 && (g < 95000u || g > 105000u)) ? g : 0u;
+    }
     return err;
 }
 
@@ -98,6 +139,7 @@ struct PngDesc {                      // one image of the batch
     unsigned long long src_off;       // byte offset of its filtered scanlines in the staging buffer
     int bpp, colour_type;
     int palette_index;                // index into the palette table, or -1
+    int gamma_index;                  // index into the gamma table pairs (to_1, from_1), or -1: plain integer weights
 };
 
 __device__ __forceinline__ int paeth(int a, int b, int c)
@@ -114,10 +156,12 @@ __device__ __forceinline__ int paeth(int a, int b, int c)
 // the machine's other slots free for the path's own kernels.
 template <int MODE /* 0: grey [h][w], 1: BGR [h][w][3] */>
 __global__ void __launch_bounds__(128) k_png_unfilter(const uint8_t* __restrict__ staged, const PngDesc* __restrict__ desc,
-                                                      const uint8_t* __restrict__ palettes, uint8_t* __restrict__ out, int W, int H)
+                                                      const uint8_t* __restrict__ palettes, const uint8_t* __restrict__ gammas,
+                                                      uint8_t* __restrict__ out, int W, int H)
 {
     extern __shared__ __align__(16) uint8_t png_smem[];
     __shared__ int chunk_sum[128 * 4];
+    __shared__ uint8_t gam[512];
     const PngDesc d = desc[blockIdx.x];
     const int bpp = d.bpp, rb = W * bpp, tid = threadIdx.x, nt = blockDim.x;
     uint8_t* rowA = png_smem;
@@ -126,6 +170,9 @@ __global__ void __launch_bounds__(128) k_png_unfilter(const uint8_t* __restrict_
     const uint8_t* pal = d.palette_index >= 0 ? palettes + (size_t)d.palette_index * 768 : nullptr;
     uint8_t* dst = out + (size_t)blockIdx.x * W * H * (MODE ? 3 : 1);
     for (int i = tid; i < rb; i += nt) rowB[i] = 0;      // the row above the first one is all zeros
+    const bool linear = MODE == 0 && d.gamma_index >= 0;
+    if (linear)
+        for (int i = tid; i < 512; i += nt) gam[i] = gammas[(size_t)d.gamma_index * 512 + i];
     __syncthreads();
     uint8_t* cur = rowA;
     uint8_t* prev = rowB;
@@ -189,7 +236,11 @@ __global__ void __launch_bounds__(128) k_png_unfilter(const uint8_t* __restrict_
             else { r = g = b = cur[x * bpp]; }
             if (MODE == 0) {
                 // libpng's rgb_to_gray as OpenCV configures it (png_set_rgb_to_gray(png, 1, 0.299, 0.587)); the weights sum to 2^15
-                dst[(size_t)y * W + x] = (uint8_t)((9797 * r + 19234 * g + 3737 * b) >> 15);
+                // (libpng's linear-light variant when the file carries a significant gamma; grey pixels pass unchanged)
+                if (linear && (r != g || r != b))
+                    dst[(size_t)y * W + x] = gam[256 + ((9797 * gam[r] + 19234 * gam[g] + 3737 * gam[b] + 16384) >> 15)];
+                else
+                    dst[(size_t)y * W + x] = (uint8_t)((9797 * r + 19234 * g + 3737 * b) >> 15);
             } else {
                 uint8_t* q = dst + ((size_t)y * W + x) * 3;
                 q[0] = (uint8_t)b; q[1] = (uint8_t)g; q[2] = (uint8_t)r;
@@ -207,6 +258,7 @@ struct IngestSet {
     size_t staged_cap = 0;
     PngDesc *h_desc = nullptr, *d_desc = nullptr;
     uint8_t *h_pal = nullptr, *d_pal = nullptr;
+    uint8_t *h_gam = nullptr, *d_gam = nullptr;   // [images][2][256] gamma_to_1 / gamma_from_1
     int cap_images = 0;
     cudaEvent_t done = nullptr;       // the set's last batch has left the staging buffers
 };
@@ -223,6 +275,8 @@ static void ingest_set_free(IngestSet& w)
     if (w.d_desc) cudaFree(w.d_desc);
     if (w.h_pal) cudaFreeHost(w.h_pal);
     if (w.d_pal) cudaFree(w.d_pal);
+    if (w.h_gam) cudaFreeHost(w.h_gam);
+    if (w.d_gam) cudaFree(w.d_gam);
     if (w.done) cudaEventDestroy(w.done);
     w = IngestSet();
 }
@@ -255,11 +309,15 @@ static int ingest_reserve(IngestSet& w, int images, size_t per_image)
         if (w.d_desc) cudaFree(w.d_desc);
         if (w.h_pal) cudaFreeHost(w.h_pal);
         if (w.d_pal) cudaFree(w.d_pal);
-        w.h_desc = nullptr; w.d_desc = nullptr; w.h_pal = nullptr; w.d_pal = nullptr; w.cap_images = 0;
+        if (w.h_gam) cudaFreeHost(w.h_gam);
+        if (w.d_gam) cudaFree(w.d_gam);
+        w.h_desc = nullptr; w.d_desc = nullptr; w.h_pal = nullptr; w.d_pal = nullptr; w.h_gam = nullptr; w.d_gam = nullptr; w.cap_images = 0;
         SSM_CUDA(cudaMallocHost(&w.h_desc, sizeof(PngDesc) * images));
         SSM_CUDA(cudaMalloc(&w.d_desc, sizeof(PngDesc) * images));
         SSM_CUDA(cudaMallocHost(&w.h_pal, (size_t)768 * images));
         SSM_CUDA(cudaMalloc(&w.d_pal, (size_t)768 * images));
+        SSM_CUDA(cudaMallocHost(&w.h_gam, (size_t)512 * images));
+        SSM_CUDA(cudaMalloc(&w.d_gam, (size_t)512 * images));
         w.cap_images = images;
     }
     return SSM_OK;
@@ -311,6 +369,9 @@ int ssm_png_decode_batch_device(ssm_ctx* c, int batch, const uint8_t* const* png
             d.bpp = info.bpp; d.colour_type = info.colour_type;
             d.palette_index = info.colour_type == 3 ? i : -1;
             if (info.colour_type == 3) memcpy(ws->h_pal + (size_t)768 * i, info.palette, 768);
+            const bool colour_file = info.colour_type == 2 || info.colour_type == 3 || info.colour_type == 6;
+            d.gamma_index = (mode == 0 && colour_file && info.file_gamma) ? i : -1;
+            if (d.gamma_index >= 0) png_gray_tables(info.file_gamma, ws->h_gam + (size_t)512 * i, ws->h_gam + (size_t)512 * i + 256);
         }
     };
     const int nthreads = std::max(1, std::min(host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency(), batch));
@@ -328,14 +389,15 @@ int ssm_png_decode_batch_device(ssm_ctx* c, int batch, const uint8_t* const* png
     SSM_CUDA(cudaMemcpyAsync(ws->d_staged, ws->h_staged, per_image * batch, cudaMemcpyHostToDevice, s));
     SSM_CUDA(cudaMemcpyAsync(ws->d_desc, ws->h_desc, sizeof(PngDesc) * batch, cudaMemcpyHostToDevice, s));
     SSM_CUDA(cudaMemcpyAsync(ws->d_pal, ws->h_pal, (size_t)768 * batch, cudaMemcpyHostToDevice, s));
+    SSM_CUDA(cudaMemcpyAsync(ws->d_gam, ws->h_gam, (size_t)512 * batch, cudaMemcpyHostToDevice, s));
     const size_t smem = 2 * (((size_t)w * max_bpp + 15) & ~(size_t)15);
     if (smem > 200 * 1024) { set_error("PNG rows too wide for the un-filter kernel"); return SSM_ERR_INVALID_ARGUMENT; }
     if (mode == 0) {
         SSM_CUDA(cudaFuncSetAttribute(k_png_unfilter<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_png_unfilter<0><<<batch, 128, smem, s>>>(ws->d_staged, ws->d_desc, ws->d_pal, d_out, w, h);
+        k_png_unfilter<0><<<batch, 128, smem, s>>>(ws->d_staged, ws->d_desc, ws->d_pal, ws->d_gam, d_out, w, h);
     } else {
         SSM_CUDA(cudaFuncSetAttribute(k_png_unfilter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_png_unfilter<1><<<batch, 128, smem, s>>>(ws->d_staged, ws->d_desc, ws->d_pal, d_out, w, h);
+        k_png_unfilter<1><<<batch, 128, smem, s>>>(ws->d_staged, ws->d_desc, ws->d_pal, ws->d_gam, d_out, w, h);
     }
     SSM_LAUNCH_CHECK(c);
     SSM_CUDA(cudaEventRecord(ws->done, s));

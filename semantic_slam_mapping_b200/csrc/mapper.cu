@@ -270,9 +270,13 @@ __device__ __forceinline__ bool make_point_from(const DevParams& p, size_t idx, 
 // keys, the run's sums are formed with segmented shuffles, and only the run's first lane probes the table and issues the
 // atomics -- the kernel is bound by the L2 atomic units, not by issue slots.  All accumulators are integers, so the table is
 // bit-identical to the point-by-point insert.
-__device__ __forceinline__ void fuse_point_warp(const DevParams& p, Voxel* __restrict__ table, uint64_t mask, const Point& pt, bool ok,
-                                                uint32_t* counters)
+// An insert that finds neither its key nor a free slot within kMaxProbe probes parks the run's points in the spill list
+// (TableRef::spill); the host grows the table and re-inserts them (voxel_table.cu).
+__device__ __forceinline__ void fuse_point_warp(const DevParams& p, const TableRef& tr, const Point& pt, bool ok)
 {
+    Voxel* __restrict__ table = tr.table;
+    const uint64_t mask = tr.mask;
+    uint32_t* counters = tr.counters;
     const uint32_t full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     unsigned long long key = kEmptyKey;
@@ -319,7 +323,8 @@ __device__ __forceinline__ void fuse_point_warp(const DevParams& p, Voxel* __res
     uint32_t slot32 = 0xffffffffu;
     if (head) {
         uint64_t slot = mix64(key) & mask;
-        for (uint64_t probe = 0; probe <= mask; ++probe, slot = (slot + 1) & mask) {
+        const uint64_t probe_end = mask < (uint64_t)kMaxProbe ? mask : (uint64_t)kMaxProbe;
+        for (uint64_t probe = 0; probe <= probe_end; ++probe, slot = (slot + 1) & mask) {
             Voxel* v = table + slot;
             unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&v->key);
             if (cur == kEmptyKey) {
@@ -342,11 +347,15 @@ __device__ __forceinline__ void fuse_point_warp(const DevParams& p, Voxel* __res
                 break;
             }
         }
-        if (slot32 == 0xffffffffu) atomicOr(&counters[2], 1u);   // table full
     }
     __syncwarp();
     slot32 = __shfl_sync(full, slot32, head_lane);
     if (vhead && label != 0xffffffffu && slot32 != 0xffffffffu) atomicAdd(&table[slot32].votes[label], vcount);
+    if (ok && slot32 == 0xffffffffu) {   // no slot within reach: park the point (rare; every lane of the run parks its own)
+        const uint32_t o = tr.spill ? atomicAdd(&counters[4], 1u) : 0xffffffffu;
+        if (o < tr.spill_cap) tr.spill[o] = pt;
+        else atomicOr(&counters[2], 1u);   // spill list full as well: the table is full for good
+    }
 }
 
 // L2 prefetch of the record a point's first probe will touch
@@ -364,8 +373,7 @@ constexpr int kPixPerThread = 4;
 __global__ void __launch_bounds__(256) k_points_fuse(const uint16_t* __restrict__ depth, const uint8_t* __restrict__ label,
                                                      const uint8_t* __restrict__ mask, const uint8_t* __restrict__ sem,
                                                      const uint8_t* __restrict__ rgb, const double* __restrict__ pose,
-                                                     Voxel* __restrict__ table, uint64_t slot_mask, uint32_t* counters,
-                                                     size_t total, SSM_DP)
+                                                     TableRef tr, size_t total, SSM_DP)
 {
     const int lane = threadIdx.x & 31;
     const size_t span = ((size_t)blockIdx.x * blockDim.x + (threadIdx.x - lane)) * kPixPerThread;   // first pixel of my warp
@@ -386,15 +394,15 @@ __global__ void __launch_bounds__(256) k_points_fuse(const uint16_t* __restrict_
         const size_t idx = span + k * 32 + lane;
         ok[k] = idx < total && make_point_from(p, idx, d[k], m[k], l[k], sem, rgb, pose, pt[k]);
         if (ok[k]) {
-            prefetch_voxel_line(table, slot_mask, pt[k], p.inv_leaf);   // same slot as the insert's first probe; a stray prefetch is harmless
+            prefetch_voxel_line(tr.table, tr.mask, pt[k], p.inv_leaf);   // same slot as the insert's first probe; a stray prefetch is harmless
             ++made;
         }
     }
 #pragma unroll
-    for (int k = 0; k < kPixPerThread; ++k) fuse_point_warp(p, table, slot_mask, pt[k], ok[k], counters);
+    for (int k = 0; k < kPixPerThread; ++k) fuse_point_warp(p, tr, pt[k], ok[k]);
     // points of this call: one atomic per warp instead of one per point
     made = __reduce_add_sync(0xffffffffu, made);
-    if (lane == 0 && made) atomicAdd(&counters[0], made);
+    if (lane == 0 && made) atomicAdd(&tr.counters[0], made);
 }
 
 // P2P mode (multi-GPU): straight from pixels; locally owned points go into this rank's hash, the others are appended
@@ -406,7 +414,7 @@ __global__ void __launch_bounds__(256) k_points_fuse(const uint16_t* __restrict_
 __global__ void __launch_bounds__(256) k_points_p2p(const uint16_t* __restrict__ depth, const uint8_t* __restrict__ label,
                                                     const uint8_t* __restrict__ mask, const uint8_t* __restrict__ sem,
                                                     const uint8_t* __restrict__ rgb, const double* __restrict__ pose,
-                                                    Voxel* __restrict__ table, uint64_t slot_mask, uint32_t* counters,
+                                                    TableRef tr,
                                                     void* const* __restrict__ peer_base, int rank, int nranks, int parity,
                                                     uint32_t inbox_cap, size_t total, SSM_DP)
 {
@@ -440,7 +448,7 @@ __global__ void __launch_bounds__(256) k_points_p2p(const uint16_t* __restrict__
             const int kk = (int)floorf(__fmul_rn(pt[k].z, p.inv_leaf));
             owner[k] = voxel_owner(i, j, kk, nranks);
             ++made;
-            if (owner[k] == rank) prefetch_voxel_line(table, slot_mask, pt[k], p.inv_leaf);
+            if (owner[k] == rank) prefetch_voxel_line(tr.table, tr.mask, pt[k], p.inv_leaf);
         }
         // remote points: the warp's lanes with the same owner take consecutive places in the CTA's block for that owner
         uint32_t pending = __ballot_sync(0xffffffffu, owner[k] >= 0 && owner[k] != rank);
@@ -473,9 +481,9 @@ __global__ void __launch_bounds__(256) k_points_p2p(const uint16_t* __restrict__
         }
     }
 #pragma unroll
-    for (int k = 0; k < kPixPerThread; ++k) fuse_point_warp(p, table, slot_mask, pt[k], owner[k] == rank, counters);
+    for (int k = 0; k < kPixPerThread; ++k) fuse_point_warp(p, tr, pt[k], owner[k] == rank);
     made = __reduce_add_sync(0xffffffffu, made);
-    if (lane == 0 && made) atomicAdd(&counters[0], made);
+    if (lane == 0 && made) atomicAdd(&tr.counters[0], made);
 }
 
 // COMPACT mode (ordered, row-major like the reference's push_back loop): count per block, scan, scatter
@@ -560,8 +568,7 @@ __global__ void __launch_bounds__(kCompactBlock) k_points_scatter(const uint16_t
 
 // fuse an explicit list of points (host-provided clouds, or points received from other ranks)
 __global__ void __launch_bounds__(256) k_fuse_list(const Point* __restrict__ pts, const uint32_t* __restrict__ count,
-                                                   uint32_t max_count, Voxel* __restrict__ table, uint64_t slot_mask,
-                                                   uint32_t* counters, SSM_DP)
+                                                   uint32_t max_count, TableRef tr, SSM_DP)
 {
     const uint32_t n = count ? min(*count, max_count) : max_count;
     const uint32_t lane = threadIdx.x & 31;
@@ -579,17 +586,16 @@ __global__ void __launch_bounds__(256) k_fuse_list(const Point* __restrict__ pts
         }
 #pragma unroll
         for (int k = 0; k < kPixPerThread; ++k)
-            if (ok[k]) prefetch_voxel_line(table, slot_mask, pt[k], p.inv_leaf);
+            if (ok[k]) prefetch_voxel_line(tr.table, tr.mask, pt[k], p.inv_leaf);
 #pragma unroll
-        for (int k = 0; k < kPixPerThread; ++k) fuse_point_warp(p, table, slot_mask, pt[k], ok[k], counters);
+        for (int k = 0; k < kPixPerThread; ++k) fuse_point_warp(p, tr, pt[k], ok[k]);
     }
 }
 
 // Cached keyframe clouds (mapper.cpp:17-20 keeps frame->pointcloud in camera coordinates; :90-91 re-transforms it by
 // the frame's current pose on every redraw): pcl::transformPointCloud in double, rounded to float, then the hash insert.
 struct Pose12 { double m[12]; };
-__global__ void __launch_bounds__(256) k_transform_fuse(const Point* __restrict__ pts, uint32_t n, Pose12 T, Voxel* __restrict__ table,
-                                                        uint64_t slot_mask, uint32_t* counters, SSM_DP)
+__global__ void __launch_bounds__(256) k_transform_fuse(const Point* __restrict__ pts, uint32_t n, Pose12 T, TableRef tr, SSM_DP)
 {
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += gridDim.x * blockDim.x) {   // warp-uniform trips
@@ -606,7 +612,7 @@ __global__ void __launch_bounds__(256) k_transform_fuse(const Point* __restrict_
             w[k] = (float)acc;
         }
         pt.x = w[0]; pt.y = w[1]; pt.z = w[2];
-        fuse_point_warp(p, table, slot_mask, pt, i < n, counters);
+        fuse_point_warp(p, tr, pt, i < n);
     }
 }
 
@@ -675,7 +681,7 @@ int launch_points(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t* d_s
     SSM_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t), s));   // counters[0] = points of this call
     if (fuse_into_map) {
         k_points_fuse<<<(unsigned)((total + 256 * kPixPerThread - 1) / (256 * kPixPerThread)), 256, 0, s>>>(d_depth, c->d_label, c->d_mask, d_sem, d_rgb, d_pose,
-                                                                      c->d_table, c->table_slots - 1, c->d_counters, total, p);
+                                                                      table_ref(c), total, p);
         SSM_LAUNCH_CHECK(c);
         return SSM_OK;
     }
@@ -696,8 +702,8 @@ int launch_points_p2p(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t*
     const DevParams& p = c->dp;
     const size_t total = (size_t)p.W * p.H * B;
     SSM_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t), s));
-    k_points_p2p<<<(unsigned)((total + 256 * kPixPerThread - 1) / (256 * kPixPerThread)), 256, 0, s>>>(d_depth, c->d_label, c->d_mask, d_sem, d_rgb, d_pose, c->d_table,
-                                                                 c->table_slots - 1, c->d_counters, d_peer_base, c->rank, c->nranks, parity,
+    k_points_p2p<<<(unsigned)((total + 256 * kPixPerThread - 1) / (256 * kPixPerThread)), 256, 0, s>>>(d_depth, c->d_label, c->d_mask, d_sem, d_rgb, d_pose, table_ref(c),
+                                                                 d_peer_base, c->rank, c->nranks, parity,
                                                                  (uint32_t)c->inbox_cap, total, p);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
@@ -708,7 +714,7 @@ int launch_fuse_inbox(ssm_ctx* c, int parity, cudaStream_t s)
     char* base = static_cast<char*>(c->ipc_base);
     const Point* pts = reinterpret_cast<const Point*>(base + kInboxHeader) + (size_t)parity * c->inbox_cap;
     uint32_t* count = reinterpret_cast<uint32_t*>(base) + parity;
-    k_fuse_list<<<c->sm_count * 16, 256, 0, s>>>(pts, count, (uint32_t)c->inbox_cap, c->d_table, c->table_slots - 1, c->d_counters, c->dp);
+    k_fuse_list<<<c->sm_count * 16, 256, 0, s>>>(pts, count, (uint32_t)c->inbox_cap, table_ref(c), c->dp);
     SSM_LAUNCH_CHECK(c);
     SSM_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));   // ready for the step after next
     return SSM_OK;
@@ -718,7 +724,7 @@ int launch_fuse_points(ssm_ctx* c, const Point* d_pts, const uint32_t* d_count, 
 {
     if (max_count == 0) return SSM_OK;
     const unsigned grid = (unsigned)std::min<size_t>(((size_t)max_count + 255) / 256, (size_t)c->sm_count * 16);
-    k_fuse_list<<<grid, 256, 0, s>>>(d_pts, d_count, max_count, c->d_table, c->table_slots - 1, c->d_counters, c->dp);
+    k_fuse_list<<<grid, 256, 0, s>>>(d_pts, d_count, max_count, table_ref(c), c->dp);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }
@@ -729,7 +735,7 @@ int launch_transform_fuse(ssm_ctx* c, const Point* d_pts, uint32_t n, const doub
     Pose12 T;
     for (int i = 0; i < 12; ++i) T.m[i] = T16[i];
     const unsigned grid = (unsigned)std::min<size_t>(((size_t)n + 255) / 256, (size_t)c->sm_count * 16);
-    k_transform_fuse<<<grid, 256, 0, s>>>(d_pts, n, T, c->d_table, c->table_slots - 1, c->d_counters, c->dp);
+    k_transform_fuse<<<grid, 256, 0, s>>>(d_pts, n, T, table_ref(c), c->dp);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }
@@ -739,7 +745,7 @@ int launch_map_clear(ssm_ctx* c, cudaStream_t s)
     const size_t words16 = c->table_slots * (sizeof(Voxel) / 16);
     k_table_clear<<<c->sm_count * 8, 256, 0, s>>>(c->d_table, words16);
     SSM_LAUNCH_CHECK(c);
-    SSM_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(uint32_t), s));
+    SSM_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(uint32_t), s));   // points, voxels, flags, export count, parked points
     return SSM_OK;
 }
 

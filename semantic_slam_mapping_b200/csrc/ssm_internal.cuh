@@ -87,6 +87,18 @@ struct Point {                              // routed between ranks, 20 bytes
     uint32_t label;
 };
 
+// what an insert kernel needs of the voxel hash: the table, the device counters ([0] points of the call, [1] voxels, [2] flags:
+// bit 0 = table and spill list full, bit 1 = coordinate outside the key range, [3] export count, [4] parked points, [5] drain
+// count) and the spill list that takes the points of inserts that found no slot within kMaxProbe probes
+constexpr int kMaxProbe = 1024;
+struct TableRef {
+    Voxel* table;
+    uint64_t mask;
+    uint32_t* counters;
+    Point* spill;
+    uint32_t spill_cap;
+};
+
 }  // namespace ssm
 
 // ---------------------------------------------------------------------------------------------
@@ -151,9 +163,21 @@ struct ssm_ctx {
     ssm::Point* d_points = nullptr;                  // [B*H*W] compacted cloud
     uint32_t* d_blk_count = nullptr;                 // per-block counts / offsets for ordered compaction
     uint32_t* d_counters = nullptr;                  // [8] misc device counters (0: n_points, 1: n_voxels, 2: overflow flag, 3: export count)
-    // voxel hash
+    // voxel hash (voxel_table.cu: growth, export)
     ssm::Voxel* d_table = nullptr;
     uint64_t table_slots = 0;
+    ssm::Point* d_spill[2] = {};                     // points whose insert found no slot within kMaxProbe probes (current / draining)
+    size_t spill_cap = 0;
+    int spill_cur = 0;
+    uint32_t* h_mirror = nullptr;                    // pinned copy of d_counters, refreshed behind every pipeline call (stale by <= 2 batches)
+    uint64_t mirror_prev = 0, mirror_dmax = 0;       // voxel count seen at the previous pipeline call; largest increase per call
+    uint64_t pipeline_calls = 0;                     // pipeline calls since the map was last cleared
+    uint64_t grows = 0;                              // growth steps so far
+    bool auto_grow = true;                           // SSM_NO_GROW=1: a full table is SSM_ERR_CAPACITY, as in round 1
+    void* export_ws = nullptr;                       // export workspace (grow-only)
+    size_t export_ws_bytes = 0;
+    float last_export_ms = 0.f;                      // device time of the latest export's kernels (index, sort, finalize)
+    cudaStream_t user_stream = nullptr;              // stream of the latest ssm_pipeline_batch_device call, if the caller passed one
     // multi-GPU
     void* comm = nullptr;                            // ncclComm_t
     int rank = 0, nranks = 1;
@@ -193,6 +217,9 @@ int cuda_fail(cudaError_t e, const char* what);
         if (_e != cudaSuccess) return ::ssm::cuda_fail(_e, #expr);          \
     } while (0)
 
+// first statement of every extern "C" entry point that takes a context: the caller's thread may have another device current
+#define SSM_ENTER(ctx) SSM_CUDA(cudaSetDevice((ctx)->device))
+
 #define SSM_LAUNCH_CHECK(ctx)                                               \
     do {                                                                    \
         (ctx)->launches++;                                                  \
@@ -221,7 +248,20 @@ int launch_points(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t* d_s
 int launch_fuse_points(ssm_ctx* c, const Point* d_pts, const uint32_t* d_count, uint32_t max_count, cudaStream_t s);
 int launch_map_clear(ssm_ctx* c, cudaStream_t s);
 int launch_transform_fuse(ssm_ctx* c, const Point* d_pts, uint32_t n, const double* T16, cudaStream_t s);
-int launch_export(ssm_ctx* c, Voxel* d_out, uint32_t max_out, cudaStream_t s);
+int launch_export(ssm_ctx* c, Voxel* d_out, uint32_t max_out, cudaStream_t s);   // dense, unordered copy of the occupied records
+// voxel_table.cu
+inline TableRef table_ref(const ssm_ctx* c)
+{
+    return TableRef{c->d_table, c->table_slots - 1, c->d_counters, c->d_spill[c->spill_cur], (uint32_t)c->spill_cap};
+}
+int table_grow(ssm_ctx* c, uint64_t min_slots, cudaStream_t s);   // stream-ordered: allocate, move the records, free, drain the spill list
+int spill_drain(ssm_ctx* c, cudaStream_t s);
+int table_stats(ssm_ctx* c, cudaStream_t s, unsigned long long out[3]);   // occupied, sum of probe displacements, longest
+// index -> (sort by (k, j, i)) -> K9 finalize -> D2H; d_recs = the hash table or a dense record list; ms_device (optional) = the
+// device time of the kernels
+int export_records_device(ssm_ctx* c, const Voxel* d_recs, uint64_t slots, uint64_t n_expected, bool sorted, const ssm_voxel_export* out,
+                          uint64_t max_voxels, uint64_t* n_out, cudaStream_t s, float* ms_device);
+int comm_gather_records(ssm_ctx* c, Voxel** d_all, uint64_t* n_all, cudaStream_t s);   // comm.cu: every rank's records on rank 0
 int launch_route_bucket(ssm_ctx* c, uint32_t max_points, cudaStream_t s);   // d_points -> d_send grouped by owner rank
 int route_and_fuse(ssm_ctx* c, cudaStream_t s);   // multi-GPU: bucket by owner, NCCL all-to-all, fuse received
 // multi-GPU, peer-memory path: one kernel makes the points, fuses the locally owned ones and appends the others to
@@ -232,6 +272,7 @@ int launch_points_p2p(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t*
                       void* const* d_peer_base, int parity, cudaStream_t s);
 int launch_fuse_inbox(ssm_ctx* c, int parity, cudaStream_t s);
 int comm_barrier(ssm_ctx* c, cudaStream_t s);
+int comm_allreduce_max(ssm_ctx* c, uint32_t* value, cudaStream_t s);   // blocking: *value = max over the ranks
 
 // packed 16x2 helpers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t dup16(int v) { return (uint32_t)(v & 0xffff) * 0x10001u; }

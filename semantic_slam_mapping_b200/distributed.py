@@ -90,6 +90,21 @@ def merge_exports(parts: list[dict]) -> dict:
     return {k: v[order] for k, v in out.items()}
 
 
+def gather_map_native(ctx, group=None, sorted: bool = True, fields=None) -> dict | None:
+    """The same through the C ABI alone (ssm_map_export_gathered: NCCL record gather + device finalize / sort on rank 0);
+    the process group only adds up the sizes so that rank 0 can allocate."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return ctx.map_export(sorted=sorted, fields=fields)
+    n = torch.tensor([ctx.map_size()], dtype=torch.int64)
+    if dist.get_backend(group) == "nccl":
+        n = n.cuda()
+    dist.all_reduce(n, group=group)
+    return ctx.map_export_gathered(int(n.item()) if dist.get_rank(group) == 0 else None, sorted=sorted, fields=fields)
+
+
 def gather_map(ctx, group=None) -> dict | None:
     """All ranks export their table; rank 0 returns the merged map, the others None."""
     import torch.distributed as dist

@@ -196,6 +196,31 @@ int Mapper::cloudOf(const Frame::Ptr& frame)
 
 void Mapper::viewer()
 {
+    // The body runs on its own std::thread: an exception that left it would end the process through std::terminate (the
+    // reference's thread has the same property for cv::Exception / PCL exceptions).  A library error -- the voxel hash out
+    // of device memory, a CUDA failure -- is recorded instead and stops the updates; failed() / lastError() report it and
+    // shutdown() still joins cleanly.
+    try {
+        viewerLoop();
+    } catch (const std::exception& e) {
+        {
+            std::lock_guard<std::mutex> lk(errorMutex);
+            errorText = e.what();
+        }
+        failedFlag = true;
+        std::fprintf(stderr, "Mapper::viewer stopped: %s\n", e.what());
+    }
+}
+
+bool Mapper::failed() const { return failedFlag; }
+std::string Mapper::lastError() const
+{
+    std::lock_guard<std::mutex> lk(errorMutex);
+    return errorText;
+}
+
+void Mapper::viewerLoop()
+{
     while (!shutdownFlag) {
         std::vector<Frame::Ptr> kfs;
         {

@@ -17,6 +17,8 @@
 
 #include <atomic>
 #include <functional>
+#include <mutex>
+#include <string>
 #include <thread>
 
 #include "frame.hpp"
@@ -53,7 +55,9 @@ public:
     ~Mapper();
 
     void shutdown();
-    void viewer();       // thread body
+    void viewer();       // thread body; library errors stop the updates and are reported by failed() / lastError()
+    bool failed() const;
+    std::string lastError() const;
     void SaveMap();      // writes the fused map as binary PCD to config.save_path (reference body is empty)
 
     // inspection (the reference prints "points in global map", mapper.cpp:161)
@@ -70,6 +74,10 @@ public:
 
 protected:
     int cloudOf(const Frame::Ptr& frame);   // device-resident camera-space cloud of a keyframe (built on first use)
+    void viewerLoop();
+    std::atomic<bool> failedFlag{false};
+    mutable std::mutex errorMutex;
+    std::string errorText;
 
     std::shared_ptr<std::thread> viewerThread;
     MapperConfig config;

@@ -28,6 +28,7 @@ SYMBOLS = [
     "ssm_labels_from_indices", "ssm_labels_from_indices_batch_device",
     "ssm_motion_cues_stage1_device", "ssm_motion_cues_stage2_device", "ssm_motion_cues_overflow",
     "ssm_png_info", "ssm_png_decode_batch_device", "ssm_png_decode",
+    "ssm_map_export_device_ms", "ssm_map_export_gathered", "ssm_map_reserve", "ssm_map_stats",
 ]
 
 
@@ -40,6 +41,11 @@ class SsmError(RuntimeError):
 class _VoxelExport(C.Structure):
     _fields_ = [("ijk", C.c_void_p), ("xyz", C.c_void_p), ("rgba", C.c_void_p), ("label", C.c_void_p),
                 ("count", C.c_void_p), ("votes", C.c_void_p)]
+
+
+class _MapStats(C.Structure):
+    _fields_ = [("slots", C.c_uint64), ("voxels", C.c_uint64), ("load_factor", C.c_double), ("mean_probe", C.c_double),
+                ("max_probe", C.c_uint64), ("grow_steps", C.c_uint64), ("table_bytes", C.c_uint64)]
 
 
 _lib = None
@@ -80,6 +86,10 @@ def load() -> C.CDLL:
     L.ssm_map_size.argtypes = [vp, C.POINTER(u64)]
     L.ssm_map_export.argtypes = [vp, C.POINTER(_VoxelExport), u64, i, C.POINTER(u64)]
     L.ssm_map_save_pcd.argtypes = [vp, C.c_char_p]
+    L.ssm_map_export_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.ssm_map_export_gathered.argtypes = [vp, C.POINTER(_VoxelExport), u64, i, C.POINTER(u64)]
+    L.ssm_map_reserve.argtypes = [vp, u64]
+    L.ssm_map_stats.argtypes = [vp, C.POINTER(_MapStats)]
     L.ssm_pipeline_batch_device.argtypes = [vp, i, vp, vp, vp, vp, vp, i, i, vp, vp]
     L.ssm_pipeline_batch_host.argtypes = [vp, i, vp, vp, vp, vp, vp, i, i, vp, C.POINTER(u64)]
     L.ssm_pipeline_batch_host_async.argtypes = [vp, i, vp, vp, vp, vp, vp, i, i, vp]
@@ -265,18 +275,60 @@ class Context:
         self._check(self._L.ssm_map_size(self._h, C.byref(n)))
         return int(n.value)
 
-    def map_export(self, sorted: bool = True) -> dict:
-        n = self.map_size()
+    _EXPORT_KEYS = ("ijk", "xyz", "rgba", "label", "count", "votes")
+
+    def _export_arrays(self, n: int, fields):
         L = self.params.num_labels
-        out = {
-            "ijk": np.empty((n, 3), np.int32), "xyz": np.empty((n, 3), np.float32), "rgba": np.empty(n, np.uint32),
-            "label": np.empty(n, np.uint8), "count": np.empty(n, np.uint32), "votes": np.empty((n, L), np.uint32),
-        }
-        ex = _VoxelExport(*[_ptr(out[k]) for k in ("ijk", "xyz", "rgba", "label", "count", "votes")])
+        shapes = {"ijk": ((n, 3), np.int32), "xyz": ((n, 3), np.float32), "rgba": ((n,), np.uint32), "label": ((n,), np.uint8),
+                  "count": ((n,), np.uint32), "votes": ((n, L), np.uint32)}
+        return {k: np.empty(*shapes[k]) for k in self._EXPORT_KEYS if fields is None or k in fields}
+
+    def map_export(self, sorted: bool = True, fields=None, into: dict | None = None) -> dict:
+        """K9 on the device (finalize + radix sort into pcl::VoxelGrid's order) and one D2H per requested array.
+        fields: subset of ("ijk", "xyz", "rgba", "label", "count", "votes"), default all.  into: caller-owned (e.g. pinned)
+        arrays of at least map_size() rows; the returned dict holds views of the first n rows."""
+        if into is not None:
+            out = into
+            cap = min(len(v) for v in out.values())
+        else:
+            cap = self.map_size()
+            out = self._export_arrays(cap, fields)
+        ex = _VoxelExport(*[_ptr(out.get(k)) for k in self._EXPORT_KEYS])
         got = C.c_uint64(0)
-        self._check(self._L.ssm_map_export(self._h, C.byref(ex), n, 1 if sorted else 0, C.byref(got)))
-        assert got.value == n
-        return out
+        self._check(self._L.ssm_map_export(self._h, C.byref(ex), cap, 1 if sorted else 0, C.byref(got)))
+        n = int(got.value)
+        if n > cap:
+            raise ValueError(f"export arrays hold {cap} voxels, the map has {n}")
+        return {k: v[:n] for k, v in out.items()}
+
+    def map_export_gathered(self, total_voxels: int, sorted: bool = True, fields=None) -> dict | None:
+        """Collective: every rank calls it; rank 0 (ssm_comm_init's rank) gets the union of the ranks' tables, the others None.
+        total_voxels: capacity of rank 0's arrays (e.g. the sum of the ranks' map_size())."""
+        rank0 = total_voxels is not None and total_voxels >= 0
+        out = self._export_arrays(total_voxels, fields) if rank0 else None
+        ex = _VoxelExport(*[_ptr(out.get(k)) for k in self._EXPORT_KEYS]) if rank0 else None
+        got = C.c_uint64(0)
+        self._check(self._L.ssm_map_export_gathered(self._h, C.byref(ex) if rank0 else None, total_voxels if rank0 else 0,
+                                                    1 if sorted else 0, C.byref(got)))
+        if not rank0:
+            return None
+        n = int(got.value)
+        if n > total_voxels:
+            raise ValueError(f"export arrays hold {total_voxels} voxels, the gathered map has {n}")
+        return {k: v[:n] for k, v in out.items()}
+
+    def map_export_device_ms(self) -> float:
+        ms = C.c_float(0)
+        self._check(self._L.ssm_map_export_device_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def map_reserve(self, slots: int):
+        self._check(self._L.ssm_map_reserve(self._h, slots))
+
+    def map_stats(self) -> dict:
+        st = _MapStats()
+        self._check(self._L.ssm_map_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _MapStats._fields_}
 
     def map_save_pcd(self, path: str):
         self._check(self._L.ssm_map_save_pcd(self._h, path.encode()))

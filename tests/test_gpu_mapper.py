@@ -126,15 +126,102 @@ def test_whole_path_batch_host_vs_oracle(tmp_path):
     assert "FIELDS x y z rgba" in head and f"POINTS {nvox}" in head
 
 
-def test_table_full_is_reported():
+def test_table_full_is_reported(monkeypatch):
+    """SSM_NO_GROW=1 pins the table at ssm_params.map_capacity: a full table (and spill list) is SSM_ERR_CAPACITY."""
     from semantic_slam_mapping_b200 import SsmError
-    p = Params(num_disparities=32, max_width=200, max_height=60, resolution=0.02, map_capacity=1024)
+    monkeypatch.setenv("SSM_NO_GROW", "1")
+    p = Params(num_disparities=32, max_width=16, max_height=16, resolution=0.02, map_capacity=1024)
     rng = np.random.default_rng(1)
     xyz = rng.uniform(-20, 20, (20000, 3)).astype(np.float32)
     with Context(p) as ctx:
         with pytest.raises(SsmError) as e:
             ctx.map_integrate_points(xyz, np.zeros(20000, np.uint32), np.zeros(20000, np.uint8))
         assert e.value.code == -4
+
+
+def _random_cloud(rng, n, span):
+    xyz = rng.uniform(-span, span, (n, 3)).astype(np.float32)
+    xyz[: n // 4] = np.round(xyz[: n // 4] * 4) / 4            # many points sharing voxels
+    return xyz, rng.integers(0, 1 << 24, n).astype(np.uint32), rng.integers(0, 12, n).astype(np.uint8)
+
+
+@pytest.mark.parametrize("span,leaf", [(30.0, 0.05), (900.0, 0.02), (3.0, 0.1)])
+def test_table_grows_and_device_export_orders_like_pcl(span, leaf):
+    """A 1024-slot table takes 60 k random points: the spill list + growth steps keep every point (map == oracle), and the
+    device radix sort orders the export by (k, j, i) over 1 to 7 digit passes (extent from 60 to 90 000 cells per axis)."""
+    p = Params(num_disparities=32, max_width=64, max_height=64, resolution=leaf, map_capacity=1024)
+    rng = np.random.default_rng(5)
+    vm = oracle.VoxelMap(leaf, p.num_labels)
+    with Context(p) as ctx:
+        for _ in range(3):
+            xyz, rgba, lab = _random_cloud(rng, 20000, span)
+            ctx.map_integrate_points(xyz, rgba, lab)
+            vm.insert(xyz, rgba & 0xffffff, lab)
+        st = ctx.map_stats()
+        got = ctx.map_export(sorted=True)
+        raw = ctx.map_export(sorted=False)
+        part = ctx.map_export(sorted=True, fields=("xyz", "label"))
+        assert ctx.map_export_device_ms() > 0
+    want = vm.export()
+    assert st["grow_steps"] >= 1 and st["voxels"] == len(vm) and st["load_factor"] <= 0.5 and st["slots"] >= 2 * len(vm)
+    assert st["max_probe"] < 1024 and st["table_bytes"] == 128 * st["slots"]
+    _compare_maps(got, want)
+    order = np.lexsort((raw["ijk"][:, 0], raw["ijk"][:, 1], raw["ijk"][:, 2]))
+    for k in got:
+        assert (raw[k][order] == got[k]).all()
+    assert set(part) == {"xyz", "label"} and (part["xyz"] == got["xyz"]).all() and (part["label"] == got["label"]).all()
+
+
+def test_streaming_growth_from_tiny_table():
+    """Streaming entry point with a table far too small for the sequence: the pinned counter mirror drives the growth steps
+    between batches, points that found no slot wait in the spill list; the final map is the oracle's, vote for vote."""
+    import torch
+    H, W, D, B, nb = 96, 320, 64, 2, 4
+    p = Params(num_disparities=D, max_width=W, max_height=H, max_batch=B, resolution=0.02, map_capacity=1024)
+    mp = _mp(p)
+    seq = synth.sequence(B * nb, H, W, D, 12, seed=31)
+    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in seq.items() if k != "label"}
+    vm = oracle.VoxelMap(p.resolution, p.num_labels)
+    for i in range(B * nb):
+        d = oracle.sgbm(seq["left"][i], seq["right"][i], _op(p))
+        pc = oracle.generate_point_cloud(oracle.disparity_to_depth(d, mp), seq["semantic"][i], seq["rgb"][i], mp, seq["pose"][i])
+        vm.insert(pc["xyz"], pc["rgba"], pc["label"])
+    assert len(vm) > 20 * 1024
+    with Context(p) as ctx:
+        for k in range(nb):
+            sl = slice(k * B, (k + 1) * B)
+            ctx.pipeline_batch_host_async(pin["left"][sl].numpy(), pin["right"][sl].numpy(), pin["semantic"][sl].numpy(),
+                                          pin["rgb"][sl].numpy(), pin["pose"][sl].numpy(), None)
+        ctx.synchronize()
+        assert ctx.map_size() == len(vm)
+        st = ctx.map_stats()
+        got = ctx.map_export()
+        ctx.map_reserve(1 << 20)
+        assert ctx.map_stats()["slots"] == 1 << 20
+        again = ctx.map_export()
+    assert st["grow_steps"] >= 2
+    _compare_maps(got, vm.export())
+    for k in got:
+        assert (again[k] == got[k]).all()
+
+
+def test_export_into_pinned_arrays_and_empty_map():
+    import torch
+    p = Params(num_disparities=32, max_width=64, max_height=64, resolution=0.1, map_capacity=1 << 12)
+    rng = np.random.default_rng(9)
+    xyz, rgba, lab = _random_cloud(rng, 5000, 5.0)
+    with Context(p) as ctx:
+        empty = ctx.map_export()
+        assert all(len(v) == 0 for v in empty.values())
+        ctx.map_integrate_points(xyz, rgba, lab)
+        n = ctx.map_size()
+        pinned = {"xyz": torch.empty((n + 7, 3), dtype=torch.float32).pin_memory().numpy(),
+                  "rgba": torch.empty(n + 7, dtype=torch.int32).pin_memory().numpy().view(np.uint32)}
+        got = ctx.map_export(into=pinned)
+        ref = ctx.map_export()
+        with pytest.raises(ValueError):
+            ctx.map_export(into={"xyz": np.empty((n - 1, 3), np.float32)})
+    assert len(got["xyz"]) == n and (got["xyz"] == ref["xyz"]).all() and (got["rgba"] == ref["rgba"]).all()
 
 
 def test_async_host_pipeline_matches_oracle():

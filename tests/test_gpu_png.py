@@ -81,6 +81,15 @@ def test_decoded_frames_feed_the_pipeline(ctx):
     assert n_png == n_raw > 1000
 
 
+def test_files_cv2_refuses_are_errors(ctx):
+    """CRC mismatch in a critical chunk, scanline filter type 5: cv2.imdecode returns None, the C ABI returns an error."""
+    from test_oracle_png import _broken
+    for name, png in _broken():
+        for colour in (False, True):
+            with pytest.raises(SsmError):
+                ctx.png_decode(png, colour)
+
+
 def test_rejected_files(ctx):
     import struct
     import zlib

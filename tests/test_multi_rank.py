@@ -137,6 +137,11 @@ def _nccl_worker(rank, world, port, q, p2p, split=0, n=6):
             else:
                 ctx.pipeline_batch_host(seq["left"][sl], seq["right"][sl], seq["semantic"][sl], seq["rgb"][sl], seq["pose"][sl])
             merged = D.gather_map(ctx)
+            native = D.gather_map_native(ctx)     # the C-ABI gather (NCCL records -> rank 0 -> device finalize + sort)
+            if rank == 0:
+                assert set(native) == set(merged)
+                for k in merged:
+                    assert native[k].shape == merged[k].shape and (native[k] == merged[k]).all(), k
         if rank == 0:
             q.put(merged)
     finally:
