@@ -130,7 +130,7 @@ def test_table_full_is_reported(monkeypatch):
     """SSM_NO_GROW=1 pins the table at ssm_params.map_capacity: a full table (and spill list) is SSM_ERR_CAPACITY."""
     from semantic_slam_mapping_b200 import SsmError
     monkeypatch.setenv("SSM_NO_GROW", "1")
-    p = Params(num_disparities=32, max_width=16, max_height=16, resolution=0.02, map_capacity=1024)
+    p = Params(num_disparities=32, max_width=64, max_height=16, resolution=0.02, map_capacity=1024)
     rng = np.random.default_rng(1)
     xyz = rng.uniform(-20, 20, (20000, 3)).astype(np.float32)
     with Context(p) as ctx:
