@@ -255,7 +255,9 @@ int ssm_pipeline_batch_host(ssm_ctx* ctx, int batch, const uint8_t* left, const 
  * k.  The host buffers must stay valid (and should be pinned) until ssm_synchronize returns or two further calls have
  * been made.  n_voxels_pinned (optional, pinned host memory) receives the map size after this batch, by an
  * asynchronous D2H copy ordered after the batch's kernels.  Errors of the voxel hash (capacity) surface at the next
- * ssm_map_size / ssm_map_export / blocking call. */
+ * ssm_map_size / ssm_map_export / blocking call.  The pipeline entry points let the host run at most two batches ahead
+ * of the device (a call waits for the batch three calls back): that is what lets the library size the voxel hash from
+ * the counts of completed batches before the table fills. */
 int ssm_pipeline_batch_host_async(ssm_ctx* ctx, int batch, const uint8_t* left, const uint8_t* right,
                                   const uint8_t* semantic, const uint8_t* rgb, const double* poses, int w, int h,
                                   uint32_t* n_voxels_pinned);

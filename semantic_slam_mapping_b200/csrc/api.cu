@@ -111,6 +111,12 @@ static void free_all(ssm_ctx* c)
         if (q) cudaFree(q);
     if (c->h_mirror) cudaFreeHost(c->h_mirror);
     if (c->export_ws) cudaFree(c->export_ws);
+    for (auto& e : c->ev_batch)
+        if (e) cudaEventDestroy(e);
+    for (int i = 0; i < ssm_ctx::kRetired; ++i) {
+        if (c->retired[i]) cudaFree(c->retired[i]);
+        if (c->retired_ev[i]) cudaEventDestroy(c->retired_ev[i]);
+    }
     for (auto& set : c->ev)
         for (auto& e : set)
             if (e) cudaEventDestroy(e);
@@ -226,6 +232,14 @@ static int maybe_grow(ssm_ctx* c, cudaStream_t s)
         int rr = sync_route(c);
         if (rr) return rr;
         SSM_CUDA(cudaStreamSynchronize(s));
+    } else if (calls >= 2 && c->ev_batch[(calls - 2) % ssm_ctx::kBatchRing]) {
+        // the host may run ahead of the device by two batches, not more: the mirror then reflects every batch but the two in
+        // flight, which (with the one being enqueued) is what the head-room of three increases below covers
+        SSM_CUDA(cudaEventSynchronize(c->ev_batch[(calls - 2) % ssm_ctx::kBatchRing]));
+    }
+    {
+        int rp = table_reap(c, false);
+        if (rp) return rp;
     }
     const volatile uint32_t* m = c->h_mirror;
     const uint64_t nvox = m[1], parked = m[4];
@@ -252,7 +266,11 @@ static int maybe_grow(ssm_ctx* c, cudaStream_t s)
 }
 static int refresh_mirror(ssm_ctx* c, cudaStream_t s)
 {
-    if (c->h_mirror) SSM_CUDA(cudaMemcpyAsync(c->h_mirror, c->d_counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (!c->h_mirror || !c->auto_grow) return SSM_OK;
+    SSM_CUDA(cudaMemcpyAsync(c->h_mirror, c->d_counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    cudaEvent_t& e = c->ev_batch[(c->pipeline_calls - 1) % ssm_ctx::kBatchRing];   // this call's slot (maybe_grow counted it)
+    if (!e) SSM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    SSM_CUDA(cudaEventRecord(e, s));
     return SSM_OK;
 }
 
@@ -388,6 +406,10 @@ static int check_overflow(ssm_ctx* c, cudaStream_t s, uint64_t* n_voxels)
         if (rc) return rc;
     }
     if (c->h_mirror) memcpy(c->h_mirror, h, sizeof(h));
+    {
+        int rp = table_reap(c, true);
+        if (rp) return rp;
+    }
     if (c->p2p && c->ipc_base) {
         uint32_t flag = 0;
         SSM_CUDA(cudaMemcpy(&flag, static_cast<char*>(c->ipc_base) + 8, sizeof(flag), cudaMemcpyDeviceToHost));
@@ -509,8 +531,7 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
     A(dalloc(&c->d_sem, npix * 3)); A(dalloc(&c->d_rgb, npix * 3));
     A(dalloc(&c->d_pose, (size_t)16 * c->cap_b)); A(dalloc(&c->d_min_disp, (size_t)c->cap_b));
     A(dalloc(&c->d_points, npix)); A(dalloc(&c->d_blk_count, npix / 1024 + 2)); A(dalloc(&c->d_counters, 16));
-    // the table comes from the stream-ordered allocator, so that a growth step can release it without stalling the host
-    A(cudaMallocAsync(reinterpret_cast<void**>(&c->d_table), sizeof(Voxel) * slots, c->stream));
+    A(dalloc(&c->d_table, slots));
     c->spill_cap = std::min<size_t>(std::max<size_t>(npix, (size_t)1 << 16), (size_t)1 << 22);
     A(dalloc(&c->d_spill[0], c->spill_cap)); A(dalloc(&c->d_spill[1], c->spill_cap));
     A(cudaHostAlloc(reinterpret_cast<void**>(&c->h_mirror), 8 * sizeof(uint32_t), cudaHostAllocDefault));

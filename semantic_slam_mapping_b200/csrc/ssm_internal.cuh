@@ -171,7 +171,12 @@ struct ssm_ctx {
     int spill_cur = 0;
     uint32_t* h_mirror = nullptr;                    // pinned copy of d_counters, refreshed behind every pipeline call (stale by <= 2 batches)
     uint64_t mirror_prev = 0, mirror_dmax = 0;       // voxel count seen at the previous pipeline call; largest increase per call
+    static constexpr int kBatchRing = 4;
+    cudaEvent_t ev_batch[kBatchRing] = {};           // completion of the latest pipeline calls (the host runs at most two batches ahead)
     uint64_t pipeline_calls = 0;                     // pipeline calls since the map was last cleared
+    static constexpr int kRetired = 3;
+    ssm::Voxel* retired[kRetired] = {};              // tables replaced by a growth step, freed once their records have moved
+    cudaEvent_t retired_ev[kRetired] = {};
     uint64_t grows = 0;                              // growth steps so far
     bool auto_grow = true;                           // SSM_NO_GROW=1: a full table is SSM_ERR_CAPACITY, as in round 1
     void* export_ws = nullptr;                       // export workspace (grow-only)
@@ -256,6 +261,7 @@ inline TableRef table_ref(const ssm_ctx* c)
 }
 int table_grow(ssm_ctx* c, uint64_t min_slots, cudaStream_t s);   // stream-ordered: allocate, move the records, free, drain the spill list
 int spill_drain(ssm_ctx* c, cudaStream_t s);
+int table_reap(ssm_ctx* c, bool wait);   // free the tables earlier growth steps replaced (wait: block until their moves are done)
 int table_stats(ssm_ctx* c, cudaStream_t s, unsigned long long out[3]);   // occupied, sum of probe displacements, longest
 // index -> (sort by (k, j, i)) -> K9 finalize -> D2H; d_recs = the hash table or a dense record list; ms_device (optional) = the
 // device time of the kernels

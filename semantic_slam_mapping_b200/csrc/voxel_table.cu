@@ -12,8 +12,8 @@
 // Growth: the reference's map is a std::vector that grows without bound, and pcl::VoxelGrid refuses grids of more than
 // 2^31 cells (App. B-2) -- the 0.02 m stress config of BASELINE.json is the one PCL cannot run.  Here an insert that does not
 // find a free slot within kMaxProbe probes parks its point in a spill list instead of failing; the next pipeline call (or
-// any blocking map call) doubles the table -- stream-ordered allocation, record-level re-insertion, no host stall -- and
-// drains the list.  Nothing is lost unless the spill list itself overflows (reported as SSM_ERR_CAPACITY).
+// any blocking map call) doubles the table -- record-level re-insertion ordered on the stream, no host stall -- and drains
+// the list.  Nothing is lost unless the spill list itself overflows (reported as SSM_ERR_CAPACITY).
 #include <algorithm>
 #include <vector>
 
@@ -375,8 +375,23 @@ __global__ void __launch_bounds__(256) k_table_clear2(Voxel* __restrict__ table,
         t[i] = (i & 7) == 0 ? make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
 }
 
-// Doubles the table until it has at least `min_slots` slots, stream-ordered on `s`: allocate, clear, move the records,
-// free the old allocation, then re-insert the parked points.  Every stream that touches the table must already be ordered
+// Old tables wait here until the kernels that moved their records are done (cudaFree synchronises the whole device, so it
+// is only called for tables whose move has completed, or from blocking calls).
+int table_reap(ssm_ctx* c, bool wait)
+{
+    for (int i = 0; i < ssm_ctx::kRetired; ++i) {
+        if (!c->retired[i]) continue;
+        if (!wait && cudaEventQuery(c->retired_ev[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (wait) SSM_CUDA(cudaEventSynchronize(c->retired_ev[i]));
+        SSM_CUDA(cudaFree(c->retired[i]));
+        c->retired[i] = nullptr;
+    }
+    return SSM_OK;
+}
+
+// Doubles the table until it has at least `min_slots` slots, stream-ordered on `s`: allocate (plain cudaMalloc: 6 ms for
+// 68 GB on a B200, against 1.8 s from the stream-ordered allocator -- scripts/micro/alloc_time.cu), clear, move the records,
+// retire the old allocation, then re-insert the parked points.  Every stream that touches the table must already be ordered
 // before `s` (the pipeline joins its sub-batch streams into `s`; callers wait for the route stream).
 int table_grow(ssm_ctx* c, uint64_t min_slots, cudaStream_t s)
 {
@@ -387,8 +402,17 @@ int table_grow(ssm_ctx* c, uint64_t min_slots, cudaStream_t s)
         set_error("voxel hash cannot grow beyond 2^32 slots");
         return SSM_ERR_CAPACITY;
     }
+    int rc = table_reap(c, false);
+    if (rc) return rc;
+    int free_slot = -1;
+    for (int i = 0; i < ssm_ctx::kRetired; ++i)
+        if (!c->retired[i]) free_slot = i;
+    if (free_slot < 0) {   // every slot still busy (three growth steps within two batches): wait for them
+        if ((rc = table_reap(c, true))) return rc;
+        free_slot = 0;
+    }
     Voxel* nt = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&nt), sizeof(Voxel) * slots, s);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&nt), sizeof(Voxel) * slots);
     if (e != cudaSuccess) {
         cudaGetLastError();
         set_error("voxel hash is full and the device has no room for a table of twice the size");
@@ -398,7 +422,9 @@ int table_grow(ssm_ctx* c, uint64_t min_slots, cudaStream_t s)
     SSM_LAUNCH_CHECK(c);
     k_rehash<<<c->sm_count * 8, 256, 0, s>>>(c->d_table, c->table_slots, nt, slots - 1, c->d_counters);
     SSM_LAUNCH_CHECK(c);
-    SSM_CUDA(cudaFreeAsync(c->d_table, s));   // every table comes from the stream-ordered allocator (ssm_create included)
+    if (!c->retired_ev[free_slot]) SSM_CUDA(cudaEventCreateWithFlags(&c->retired_ev[free_slot], cudaEventDisableTiming));
+    SSM_CUDA(cudaEventRecord(c->retired_ev[free_slot], s));
+    c->retired[free_slot] = c->d_table;
     c->d_table = nt;
     c->table_slots = slots;
     c->grows++;
