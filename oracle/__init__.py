@@ -450,6 +450,92 @@ def ref_set_image_roi(xyz) -> np.ndarray:
     return m
 
 
+# ---- the mapper half from the reference's own compiled sources (oracle/_ref/libref_mapper.so, oracle/ref_mapper_wrap.cpp) ----
+_REF_MAPPER = {}
+
+
+def build_ref_mapper(native: bool = False) -> str | None:
+    """Compile src/mapper.cpp, src/rgbdframe.cpp, src/parameter_reader.cpp and src/stereo.cpp where they lie (needs
+    /root/reference; elsewhere the prebuilt file that travelled with the snapshot is used).  native=True: the reference's own
+    flags (-march=native -O3, so GCC's default -ffp-contract=fast) instead of the canonical -ffp-contract=off."""
+    name = "libref_mapper_native.so" if native else "libref_mapper.so"
+    path = os.path.join(_HERE, "_ref", name)
+    src = os.path.join(_REFERENCE_ROOT, "src", "mapper.cpp")
+    if os.path.exists(src):
+        deps = [src, os.path.join(_REFERENCE_ROOT, "src", "rgbdframe.cpp"), os.path.join(_REFERENCE_ROOT, "include", "rgbdframe.h"),
+                os.path.join(_HERE, "ref_mapper_wrap.cpp"), os.path.join(_HERE, "ref_stereo_wrap.cpp"), os.path.join(_HERE, "Makefile"),
+                os.path.join(_HERE, "cvstub", "cvstub.hpp"), os.path.join(_HERE, "cvstub", "cvstub_more.hpp"),
+                os.path.join(_HERE, "refstub", "prelude.hpp"), os.path.join(_HERE, "refstub", "pcl", "common", "transforms.h")]
+        if (not os.path.exists(path)) or any(os.path.getmtime(f) > os.path.getmtime(path) for f in deps):
+            subprocess.check_call(["make", "-C", _HERE, "-B", f"_ref/{name}", f"REF={_REFERENCE_ROOT}"], stdout=subprocess.DEVNULL)
+    return path if os.path.exists(path) else None
+
+
+def ref_mapper(native: bool = False):
+    """ctypes handle on oracle/_ref/libref_mapper[_native].so, or None when it is not available."""
+    if native not in _REF_MAPPER:
+        path = build_ref_mapper(native)
+        if path is None:
+            return None
+        R = C.CDLL(path)
+        vp = C.c_void_p
+        R.ref_set_sgbm.argtypes = [_SGBM_CB]
+        R.ref_frame_next.argtypes = [C.c_char_p, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
+        R.ref_frame_next.restype = C.c_int
+        R.ref_mapper_cloud.argtypes = [C.c_char_p, vp, vp, vp, C.c_int, C.c_int, vp, C.c_double, vp, vp, vp, vp, vp, C.c_int]
+        R.ref_mapper_cloud.restype = C.c_int
+        R.ref_set_sgbm(_sgbm_cb)
+        _REF_MAPPER[native] = R
+    return _REF_MAPPER[native]
+
+
+def _cam9(mp: MapParams) -> np.ndarray:
+    return np.array([mp.cx, mp.cy, mp.fx, mp.fy, mp.baseline, mp.scale, mp.roix, mp.roiy, mp.roiz], np.float64)
+
+
+def ref_frame_next(left, right, rgb_bgr, semantic_bgr, mp: MapParams, native: bool = False):
+    """The reference's FrameReader::next (src/rgbdframe.cpp:34-191) on one stereo frame: (depth u16, disparity i16).  The
+    images are served to its cv::imread calls from memory; cv::StereoSGBM runs the C oracle's SGBM with the parameter block
+    the reference's calDisparity_SGBM sets (80 disparities)."""
+    import tempfile
+    left = np.ascontiguousarray(left, np.uint8)
+    right = np.ascontiguousarray(right, np.uint8)
+    rgb = np.ascontiguousarray(rgb_bgr, np.uint8)
+    sem = np.ascontiguousarray(semantic_bgr, np.uint8)
+    H, W = left.shape
+    depth = np.empty((H, W), np.uint16)
+    disp = np.empty((H, W), np.int16)
+    cam = _cam9(mp)
+    with tempfile.TemporaryDirectory() as tmp:
+        rc = ref_mapper(native).ref_frame_next(tmp.encode(), _p(left), _p(right), _p(rgb), _p(sem), W, H, _p(cam), _p(depth), _p(disp))
+    if rc != 0:
+        raise RuntimeError("the reference's FrameReader::next returned no frame")
+    return depth, disp
+
+
+def ref_mapper_cloud(depth, semantic_bgr, rgb_bgr, mp: MapParams, T, native: bool = False):
+    """The reference's Mapper::semantic_motion_fuse + Mapper::generatePointCloud (src/mapper.cpp:12-94, 189-216) with
+    RGBDFrame::project2dTo3d (include/rgbdframe.h:63-75) on one frame.  Returns dict(mask, xyz_cam, xyz, rgba): xyz_cam / rgba
+    are the frame's cached camera-space cloud (the reference's own loop), xyz the cloud after the stand-in's
+    pcl::transformPointCloud (written definition, SURVEY App. B-1)."""
+    import tempfile
+    depth = np.ascontiguousarray(depth, np.uint16)
+    sem = np.ascontiguousarray(semantic_bgr, np.uint8)
+    rgb = np.ascontiguousarray(rgb_bgr, np.uint8)
+    T = np.ascontiguousarray(T, np.float64).reshape(16)
+    H, W = depth.shape
+    n = H * W
+    mask = np.empty((H, W), np.uint8)
+    cam_xyz = np.empty((n, 3), np.float32)
+    xyz = np.empty((n, 3), np.float32)
+    rgba = np.empty(n, np.uint32)
+    cam = _cam9(mp)
+    with tempfile.TemporaryDirectory() as tmp:
+        k = ref_mapper(native).ref_mapper_cloud(tmp.encode(), _p(depth), _p(sem), _p(rgb), W, H, _p(cam), float(mp.max_distance), _p(T),
+                                                _p(mask), _p(cam_xyz), _p(xyz), _p(rgba), n)
+    return {"mask": mask, "xyz_cam": cam_xyz[:k].copy(), "xyz": xyz[:k].copy(), "rgba": rgba[:k].copy()}
+
+
 # ---- label production before the path (SURVEY 8f row 3): experiment/segnet.cpp:131-146, src/rgbdframe.cpp:118-136 --------
 def resize_linear_tables(dst: int, src: int, clamp: bool):
     """Source index and the two 11-bit fixed-point weights of cv::resize(INTER_LINEAR) for every destination coordinate

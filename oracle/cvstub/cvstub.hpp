@@ -64,10 +64,14 @@ public:
     int rows, cols;
     uchar* data;
     size_t step;   // bytes per row
-    Mat() : rows(0), cols(0), data(0), step(0), type_(0) {}
-    Mat(int r, int c, int t) : rows(0), cols(0), data(0), step(0), type_(0) { create(r, c, t); }
+    Mat() : rows(0), cols(0), data(0), step(0), type_(0), uninit_(false) {}
+    // cv::Mat(rows, cols, type) leaves its pixels uninitialised in OpenCV; the stand-in zero-fills them and remembers that
+    // nobody has defined them (cv::dilate below reads the flag: SURVEY App. C-3)
+    Mat(int r, int c, int t) : rows(0), cols(0), data(0), step(0), type_(0), uninit_(false) { create(r, c, t); uninit_ = true; }
+    Mat(int r, int c, int t, const Scalar& v);      // filled (cvstub_more.hpp)
+    Mat(Size s, int t, const Scalar& v);
     // header over caller-owned memory (no copy), as cv::Mat(rows, cols, type, data, step)
-    Mat(int r, int c, int t, void* d, size_t s = 0) : rows(r), cols(c), data((uchar*)d), step(s), type_(t)
+    Mat(int r, int c, int t, void* d, size_t s = 0) : rows(r), cols(c), data((uchar*)d), step(s), type_(t), uninit_(false)
     {
         if (step == 0) step = (size_t)cols * elemSize();
     }
@@ -102,11 +106,13 @@ public:
     template <typename T> const T& at(int i, int j) const { return ((const T*)(data + (ptrdiff_t)step * i))[j]; }
     template <typename T> T& at(int i) { return rows == 1 ? ((T*)data)[i] : *(T*)(data + (ptrdiff_t)step * i); }
     template <typename T> const T& at(int i) const { return rows == 1 ? ((const T*)data)[i] : *(const T*)(data + (ptrdiff_t)step * i); }
-    static Mat zeros(int r, int c, int t) { return Mat(r, c, t); }   // create() zero-fills
-    static Mat zeros(Size s, int t) { return Mat(s.height, s.width, t); }
+    static Mat zeros(int r, int c, int t) { Mat m(r, c, t); m.uninit_ = false; return m; }   // create() zero-fills
+    static Mat zeros(Size s, int t) { return zeros(s.height, s.width, t); }
+    bool uninitialised() const { return uninit_; }
     Mat clone() const
     {
         Mat m(rows, cols, type_);
+        m.uninit_ = uninit_;
         for (int i = 0; i < rows; ++i) std::memcpy(m.data + m.step * (size_t)i, data + step * (size_t)i, (size_t)cols * elemSize());
         return m;
     }
@@ -116,9 +122,11 @@ public:
     Mat operator()(const Rect& roi) const;
     void copyTo(Mat& m, const Mat& mask) const;
     Mat& operator=(const Scalar& s);
+    void push_back(const Mat& m);
 
 private:
     int type_;
+    bool uninit_;
     std::shared_ptr<std::vector<uchar> > own_;
 };
 

@@ -9,6 +9,8 @@
 #ifndef SSM_CVSTUB_MORE_HPP
 #define SSM_CVSTUB_MORE_HPP
 
+#include <map>
+
 #define CV_GRAY2BGR 8
 #define CV_BGR2GRAY 6
 #define CV_DIST_L2 2
@@ -174,6 +176,76 @@ inline void cvtColor(const Mat& src, Mat& dst, int code, int = 0)
         }
 }
 
+// ---- implemented: what FrameReader::next and the Mapper execute (oracle/refstub/prelude.hpp) ---------------------------------------
+#define CV_LOAD_IMAGE_UNCHANGED -1
+#define CV_LOAD_IMAGE_GRAYSCALE 0
+#define CV_LOAD_IMAGE_COLOR 1
+inline void fill_scalar(Mat& m, const Scalar& v)
+{
+    const int cn = m.channels();
+    for (int i = 0; i < m.rows; ++i)
+        for (int j = 0; j < m.cols; ++j)
+            for (int c = 0; c < cn; ++c) {
+                const double x = v.val[c < 4 ? c : 3];
+                const int k = j * cn + c;
+                switch (m.depth()) {
+                    case CV_8U: m.ptr<uchar>(i)[k] = (uchar)x; break;
+                    case CV_16U: m.ptr<ushort>(i)[k] = (ushort)x; break;
+                    case CV_16S: m.ptr<short>(i)[k] = (short)x; break;
+                    case CV_32S: m.ptr<int>(i)[k] = (int)x; break;
+                    case CV_32F: m.ptr<float>(i)[k] = (float)x; break;
+                    default: m.ptr<double>(i)[k] = x; break;
+                }
+            }
+}
+inline Mat::Mat(int r, int c, int t, const Scalar& v) : rows(0), cols(0), data(0), step(0), type_(0), uninit_(false) { create(r, c, t); fill_scalar(*this, v); }
+inline Mat::Mat(Size s, int t, const Scalar& v) : rows(0), cols(0), data(0), step(0), type_(0), uninit_(false) { create(s.height, s.width, t); fill_scalar(*this, v); }
+
+// cv::imread served from memory: the test harness registers the images under the paths the reference will ask for
+// (FrameReader::next reads the same file once with the default flag -- colour -- and once with flag 0 -- grey).  An
+// unregistered path is a missing file: an empty matrix, as cv::imread returns.
+struct ImreadRegistry {
+    std::map<std::string, Mat> colour, grey;
+    static ImreadRegistry& get() { static ImreadRegistry r; return r; }
+};
+inline Mat imread(const std::string& path, int flags = 1)
+{
+    ImreadRegistry& r = ImreadRegistry::get();
+    std::map<std::string, Mat>& m = flags == 0 ? r.grey : r.colour;
+    std::map<std::string, Mat>::const_iterator it = m.find(path);
+    if (it == m.end() && flags < 0) { it = r.grey.find(path); if (it == r.grey.end()) return Mat(); return it->second.clone(); }
+    return it == m.end() ? Mat() : it->second.clone();
+}
+
+// cv::dilate on 8UC1 with the default border (out-of-image pixels never win) and the anchor at the kernel centre.  A kernel
+// whose pixels were never defined -- the reference passes cv::Mat(3,3,CV_8UC1) straight from the constructor,
+// src/mapper.cpp:214 -- acts as all ones: the canonical choice of SURVEY App. C-3 (heap garbage is non-zero).
+inline void dilate(const Mat& src, Mat& dst, const Mat& kernel, Point anchor = Point(-1, -1), int iterations = 1)
+{
+    if (src.type() != CV_8UC1) stub_unreachable("dilate (other than 8UC1)");
+    const int kr = kernel.rows, kc = kernel.cols;
+    const int ay = anchor.y < 0 ? kr / 2 : anchor.y, ax = anchor.x < 0 ? kc / 2 : anchor.x;
+    Mat cur = src.clone();
+    for (int it = 0; it < iterations; ++it) {
+        Mat out = Mat::zeros(cur.rows, cur.cols, CV_8UC1);
+        for (int y = 0; y < cur.rows; ++y)
+            for (int x = 0; x < cur.cols; ++x) {
+                int best = 0;
+                for (int i = 0; i < kr; ++i)
+                    for (int j = 0; j < kc; ++j) {
+                        if (!kernel.uninitialised() && kernel.ptr<uchar>(i)[j] == 0) continue;
+                        const int yy = y + i - ay, xx = x + j - ax;
+                        if (yy < 0 || yy >= cur.rows || xx < 0 || xx >= cur.cols) continue;
+                        const int v = cur.ptr<uchar>(yy)[xx];
+                        if (v > best) best = v;
+                    }
+                out.ptr<uchar>(y)[x] = (uchar)best;
+            }
+        cur = out;
+    }
+    dst = cur;
+}
+
 // ---- declared only ---------------------------------------------------------------------------------------------------------
 enum { THRESH_BINARY = 0, THRESH_BINARY_INV = 1, THRESH_TRUNC = 2, THRESH_TOZERO = 3, THRESH_OTSU = 8 };
 enum { MORPH_RECT = 0, MORPH_CROSS = 1, MORPH_ELLIPSE = 2 };
@@ -187,7 +259,6 @@ inline int waitKey(int = 0) { stub_unreachable("waitKey"); }
 inline bool imwrite(const std::string&, const Mat&) { stub_unreachable("imwrite"); }
 inline Mat getStructuringElement(int, Size, Point = Point(-1, -1)) { stub_unreachable("getStructuringElement"); }
 inline void erode(const Mat&, Mat&, const Mat&, Point = Point(-1, -1), int = 1) { stub_unreachable("erode"); }
-inline void dilate(const Mat&, Mat&, const Mat&, Point = Point(-1, -1), int = 1) { stub_unreachable("dilate"); }
 inline void bitwise_or(const Mat&, const Mat&, Mat&) { stub_unreachable("bitwise_or"); }
 inline void bitwise_and(const Mat&, const Mat&, Mat&) { stub_unreachable("bitwise_and"); }
 inline int floodFill(Mat&, Point, Scalar, Rect* = 0, Scalar = Scalar(), Scalar = Scalar(), int = 4) { stub_unreachable("floodFill"); }
@@ -197,6 +268,7 @@ inline Mat Mat::operator()(const Range&, const Range&) const { stub_unreachable(
 inline Mat Mat::operator()(const Rect&) const { stub_unreachable("Mat::operator()(Rect)"); }
 inline void Mat::copyTo(Mat&, const Mat&) const { stub_unreachable("Mat::copyTo(dst, mask)"); }
 inline Mat& Mat::operator=(const Scalar&) { stub_unreachable("Mat::operator=(Scalar)"); }
+inline void Mat::push_back(const Mat&) { stub_unreachable("Mat::push_back"); }
 template <typename P> inline void fitLine(const std::vector<P>&, Vec4f&, int, double, double, double) { stub_unreachable("fitLine"); }
 inline void fitLine(const Mat&, Vec4f&, int, double, double, double) { stub_unreachable("fitLine"); }
 

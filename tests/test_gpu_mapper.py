@@ -59,6 +59,33 @@ def test_depth_mask_cloud_bit_exact():
     assert (pc["rgba"] == want["rgba"]).all() and (pc["label"] == want["label"]).all()
 
 
+def test_reference_compiled_mapper_vectors(golden_dir):
+    """tests/golden/mapper_ref.npz holds what the REFERENCE's own compiled FrameReader::next / Mapper::semantic_motion_fuse /
+    Mapper::generatePointCloud / RGBDFrame::project2dTo3d produce (oracle/_ref/libref_mapper.so, generator
+    tests/golden/make_golden_mapper.py): the CUDA path reproduces them bit for bit -- disparity at the reference's 80
+    disparities, depth image, moving mask, camera-space cloud (identity pose), colours and the transformed cloud."""
+    import os
+    g = np.load(os.path.join(golden_dir, "mapper_ref.npz"))
+    for name in ("frame0", "frame1", "adv"):
+        sem, rgb, T = g[f"{name}/semantic"], g[f"{name}/rgb"], g[f"{name}/pose"]
+        H, W = sem.shape[:2]
+        p = Params(num_disparities=80, max_width=max(W, 96), max_height=H)
+        with Context(p) as ctx:
+            if name != "adv":
+                disp = ctx.sgbm(g[f"{name}/left"], g[f"{name}/right"])
+                assert (disp == g[f"{name}/disp"]).all()
+                depth = ctx.disparity_to_depth(disp)
+                assert (depth == g[f"{name}/depth"]).all()
+            depth = g[f"{name}/depth"]
+            assert (ctx.semantic_motion_fuse(sem) == g[f"{name}/mask"]).all()
+            cam = ctx.generate_point_cloud(depth, sem, rgb, np.eye(4))
+            world = ctx.generate_point_cloud(depth, sem, rgb, T)
+        assert cam["xyz"].shape == g[f"{name}/xyz_cam"].shape
+        assert (cam["xyz"].view(np.uint32) == g[f"{name}/xyz_cam"].view(np.uint32)).all()
+        assert (world["xyz"].view(np.uint32) == g[f"{name}/xyz"].view(np.uint32)).all()
+        assert (cam["rgba"] == g[f"{name}/rgba"]).all() and (world["rgba"] == g[f"{name}/rgba"]).all()
+
+
 def test_semantic_colour_variant_and_unknown_colours():
     H, W, D = 60, 200, 32
     p = Params(num_disparities=D, max_width=W, max_height=H, colour_source=1)
