@@ -489,11 +489,46 @@ def ref_mapper(native: bool = False):
     return _REF_MAPPER[native]
 
 
+def build_dropin() -> str | None:
+    """oracle/_ref/libdropin.so: the harness of ref_mapper_wrap.cpp / ref_stereo_wrap.cpp over the product's DROP-IN sources
+    (semantic_slam_mapping_b200/host/dropin/stereo.cpp, mapper.cpp) compiled against the reference's own headers in place of its
+    src/stereo.cpp and src/mapper.cpp.  Building it is the type check of the drop-in; running it needs a GPU (it calls libssm.so)."""
+    path = os.path.join(_HERE, "_ref", "libdropin.so")
+    if os.path.exists(os.path.join(_REFERENCE_ROOT, "include", "mapper.h")):
+        drop = os.path.join(_HERE, "..", "semantic_slam_mapping_b200", "host", "dropin")
+        deps = [os.path.join(drop, f) for f in ("stereo.cpp", "mapper.cpp", "dropin.hpp")] + [
+            os.path.join(_HERE, "ref_mapper_wrap.cpp"), os.path.join(_HERE, "ref_stereo_wrap.cpp"), os.path.join(_HERE, "Makefile"),
+            os.path.join(_HERE, "..", "include", "ssm.h"), os.path.join(_HERE, "..", "semantic_slam_mapping_b200", "libssm.so")]
+        if (not os.path.exists(path)) or any(os.path.getmtime(f) > os.path.getmtime(path) for f in deps if os.path.exists(f)):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "_ref/libdropin.so", f"REF={_REFERENCE_ROOT}"], stdout=subprocess.DEVNULL)
+    return path if os.path.exists(path) else None
+
+
+def dropin():
+    """ctypes handle on oracle/_ref/libdropin.so (same entry points as ref_mapper() and ref()), or None."""
+    if "dropin" not in _REF_MAPPER:
+        path = build_dropin()
+        if path is None:
+            return None
+        R = C.CDLL(path)
+        vp, d = C.c_void_p, C.c_double
+        R.ref_frame_next.argtypes = [C.c_char_p, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
+        R.ref_frame_next.restype = C.c_int
+        R.ref_mapper_cloud.argtypes = [C.c_char_p, vp, vp, vp, C.c_int, C.c_int, vp, C.c_double, vp, vp, vp, vp, vp, C.c_int]
+        R.ref_mapper_cloud.restype = C.c_int
+        R.ref_calDisparity_SGBM.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+        R.ref_triangulate10D.argtypes = [vp, vp, C.c_int, C.c_int, d, d, d, d, d, d, d, vp]
+        R.ref_correct3DPoints.argtypes = [vp, C.c_int, C.c_int, d, d, d, d, d]
+        R.ref_setImageROI.argtypes = [vp, C.c_int, C.c_int, vp]
+        _REF_MAPPER["dropin"] = R
+    return _REF_MAPPER["dropin"]
+
+
 def _cam9(mp: MapParams) -> np.ndarray:
     return np.array([mp.cx, mp.cy, mp.fx, mp.fy, mp.baseline, mp.scale, mp.roix, mp.roiy, mp.roiz], np.float64)
 
 
-def ref_frame_next(left, right, rgb_bgr, semantic_bgr, mp: MapParams, native: bool = False):
+def ref_frame_next(left, right, rgb_bgr, semantic_bgr, mp: MapParams, native: bool = False, handle=None):
     """The reference's FrameReader::next (src/rgbdframe.cpp:34-191) on one stereo frame: (depth u16, disparity i16).  The
     images are served to its cv::imread calls from memory; cv::StereoSGBM runs the C oracle's SGBM with the parameter block
     the reference's calDisparity_SGBM sets (80 disparities)."""
@@ -507,13 +542,13 @@ def ref_frame_next(left, right, rgb_bgr, semantic_bgr, mp: MapParams, native: bo
     disp = np.empty((H, W), np.int16)
     cam = _cam9(mp)
     with tempfile.TemporaryDirectory() as tmp:
-        rc = ref_mapper(native).ref_frame_next(tmp.encode(), _p(left), _p(right), _p(rgb), _p(sem), W, H, _p(cam), _p(depth), _p(disp))
+        rc = (handle or ref_mapper(native)).ref_frame_next(tmp.encode(), _p(left), _p(right), _p(rgb), _p(sem), W, H, _p(cam), _p(depth), _p(disp))
     if rc != 0:
         raise RuntimeError("the reference's FrameReader::next returned no frame")
     return depth, disp
 
 
-def ref_mapper_cloud(depth, semantic_bgr, rgb_bgr, mp: MapParams, T, native: bool = False):
+def ref_mapper_cloud(depth, semantic_bgr, rgb_bgr, mp: MapParams, T, native: bool = False, handle=None):
     """The reference's Mapper::semantic_motion_fuse + Mapper::generatePointCloud (src/mapper.cpp:12-94, 189-216) with
     RGBDFrame::project2dTo3d (include/rgbdframe.h:63-75) on one frame.  Returns dict(mask, xyz_cam, xyz, rgba): xyz_cam / rgba
     are the frame's cached camera-space cloud (the reference's own loop), xyz the cloud after the stand-in's
@@ -531,8 +566,10 @@ def ref_mapper_cloud(depth, semantic_bgr, rgb_bgr, mp: MapParams, T, native: boo
     rgba = np.empty(n, np.uint32)
     cam = _cam9(mp)
     with tempfile.TemporaryDirectory() as tmp:
-        k = ref_mapper(native).ref_mapper_cloud(tmp.encode(), _p(depth), _p(sem), _p(rgb), W, H, _p(cam), float(mp.max_distance), _p(T),
+        k = (handle or ref_mapper(native)).ref_mapper_cloud(tmp.encode(), _p(depth), _p(sem), _p(rgb), W, H, _p(cam), float(mp.max_distance), _p(T),
                                                 _p(mask), _p(cam_xyz), _p(xyz), _p(rgba), n)
+    if k < 0:
+        raise RuntimeError("generatePointCloud returned clouds of different sizes for two poses")
     return {"mask": mask, "xyz_cam": cam_xyz[:k].copy(), "xyz": xyz[:k].copy(), "rgba": rgba[:k].copy()}
 
 

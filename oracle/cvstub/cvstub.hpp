@@ -54,6 +54,8 @@ struct Size {
     Size() : width(0), height(0) {}
     Size(int w, int h) : width(w), height(h) {}
 };
+inline bool operator==(const Size& a, const Size& b) { return a.width == b.width && a.height == b.height; }
+inline bool operator!=(const Size& a, const Size& b) { return !(a == b); }
 
 struct Scalar;
 struct Range;

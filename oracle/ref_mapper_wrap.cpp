@@ -120,15 +120,21 @@ int ref_mapper_cloud(const char* tmpdir, const unsigned short* depth, const unsi
     frame->rgb = wrap(h, w, CV_8UC3, rgb);
     frame->result = frame->rgb.clone();          // read (and dropped) by generatePointCloud, src/mapper.cpp:62-68
     frame->camera = pr.getCamera();
+    // first under the identity pose: the returned cloud is the camera-space cloud (1 * x + 0 * y + 0 * z + 0 is exact); the
+    // reference also leaves it in frame->pointcloud (its own push_back loop, no library arithmetic), which is preferred when set
+    frame->setTransform(Eigen::Isometry3d::Identity());
+    Mapper::PointCloud::Ptr cam = mapper.generatePointCloud(frame);
+    if (frame->pointcloud != nullptr) cam = frame->pointcloud;
     Eigen::Isometry3d T;
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j) T(i, j) = T16[4 * i + j];
     frame->setTransform(T);
     Mapper::PointCloud::Ptr world = mapper.generatePointCloud(frame);
     for (int i = 0; i < h; ++i) std::memcpy(mask_out + (size_t)i * w, mapper.moving_mask.ptr<uchar>(i), w);
-    const int n = (int)frame->pointcloud->points.size();
+    const int n = (int)cam->points.size();
+    if ((int)world->points.size() != n) { mapper.shutdown(); return -1; }
     for (int i = 0; i < n && i < max_points; ++i) {
-        const Mapper::PointT& p = frame->pointcloud->points[i];
+        const Mapper::PointT& p = cam->points[i];
         const Mapper::PointT& q = world->points[i];
         xyz_cam[3 * i] = p.x; xyz_cam[3 * i + 1] = p.y; xyz_cam[3 * i + 2] = p.z;
         xyz_world[3 * i] = q.x; xyz_world[3 * i + 1] = q.y; xyz_world[3 * i + 2] = q.z;
