@@ -59,6 +59,11 @@ def main():
     np.savez_compressed(os.path.join(OUT, "sgbm_kitti_d128.npz"), disp=cv_sgbm(L, R, 128),
                         left_sum=np.int64(L.astype(np.int64).sum()), right_sum=np.int64(R.astype(np.int64).sum()))
 
+    # Cityscapes-shaped full frame at BASELINE.json configs[3]: 2048 x 1024, 256 disparities (inputs regenerated from the seed)
+    L, R, _ = synth.stereo_pair(1024, 2048, 256, 0)
+    np.savez_compressed(os.path.join(OUT, "sgbm_cityscapes_d256.npz"), disp=cv_sgbm(L, R, 256),
+                        left_sum=np.int64(L.astype(np.int64).sum()), right_sum=np.int64(R.astype(np.int64).sum()))
+
     # stage-level vectors
     img = rng.integers(-16, 2048, (50, 70)).astype(np.int16)
     img[rng.random(img.shape) < 0.3] = -16

@@ -346,6 +346,31 @@ def test_keyframe_cache_redraw_after_pose_update():
             ctx.keyframe_set_pose(ids[0], poses1[0])         # released id
 
 
+def test_full_size_map_equals_oracle_map():
+    """Full KITTI-size frames (1241 x 376, 128 disparities) through the whole path: the fused map equals the oracle's voxel for
+    voxel -- voxel set, counts, votes, majority labels, colours exactly, centroids within 1e-5 -- at 0.05 m and, re-fused, at 0.02 m."""
+    H, W, D, B = 376, 1241, 128, 4
+    seq = synth.sequence(B, H, W, D, 12, seed=41)
+    clouds = None
+    for leaf in (0.05, 0.02):
+        p = Params(num_disparities=D, max_width=W, max_height=H, max_batch=B, resolution=leaf, map_capacity=1 << 21)
+        mp = _mp(p)
+        if clouds is None:
+            clouds = []
+            for i in range(B):
+                d = oracle.sgbm(seq["left"][i], seq["right"][i], _op(p))
+                clouds.append((d, oracle.generate_point_cloud(oracle.disparity_to_depth(d, mp), seq["semantic"][i], seq["rgb"][i], mp, seq["pose"][i])))
+        vm = oracle.VoxelMap(leaf, p.num_labels)
+        for _, pc in clouds:
+            vm.insert(pc["xyz"], pc["rgba"], pc["label"])
+        with Context(p) as ctx:
+            nvox, disp = ctx.pipeline_batch_host(seq["left"], seq["right"], seq["semantic"], seq["rgb"], seq["pose"], want_disp=True)
+            got = ctx.map_export()
+        assert all(int((disp[i] != clouds[i][0]).sum()) == 0 for i in range(B))
+        assert nvox == len(vm) > 100000
+        _compare_maps(got, vm.export())
+
+
 def test_full_size_stress_properties_19_classes_2cm_voxels():
     """BASELINE configs[3]/[4] flavour at full KITTI size: 19-class palette, 0.02 m voxels, a batch through the whole path.
     Size-independent properties: every generated point lands in exactly one voxel (sum of counts == points), label votes

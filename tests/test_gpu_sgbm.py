@@ -63,6 +63,26 @@ def test_kitti_d128_golden_from_cv2(golden_dir):
     assert int((got != z["disp"]).sum()) == 0
 
 
+def test_cityscapes_d256_golden_from_cv2(golden_dir):
+    """BASELINE configs[3] at full size: one 2048 x 1024 frame, 256 disparities (16-CTA clusters in the vertical kernel, 8 disparities
+    per lane and 32-byte winner records in the horizontal sweep), against cv2 4.13's output committed by tests/golden/make_golden.py."""
+    z = np.load(os.path.join(golden_dir, "sgbm_cityscapes_d256.npz"))
+    L, R, _ = synth.stereo_pair(1024, 2048, 256, 0)
+    assert int(L.astype(np.int64).sum()) == int(z["left_sum"]) and int(R.astype(np.int64).sum()) == int(z["right_sum"])
+    with Context(_params(256, 2048, 1024)) as ctx:
+        got = ctx.sgbm(L, R)
+        import torch
+        dL = torch.from_numpy(np.stack([L, L])).cuda()
+        dR = torch.from_numpy(np.stack([R, R])).cuda()
+    assert got.shape == (1024, 2048) and int((got != z["disp"]).sum()) == 0
+    with Context(_params(256, 2048, 1024, max_batch=2)) as ctx:      # the batched shape of the bench (smaller clusters)
+        dD = torch.empty((2, 1024, 2048), dtype=torch.int16, device="cuda")
+        ctx.sgbm_batch_device(dL, dR, dD, 2, 2048, 1024)
+        torch.cuda.synchronize()
+        both = dD.cpu().numpy()
+    assert int((both[0] != z["disp"]).sum()) == 0 and int((both[1] != z["disp"]).sum()) == 0
+
+
 def test_reference_default_d80_full_frame():
     """The reference's own setting (src/stereo.cpp:18: 80 disparities) at KITTI size, vs the oracle."""
     L, R, _ = synth.stereo_pair(376, 1241, 80, 21)
