@@ -84,6 +84,8 @@ static void fill_dev_params(ssm_ctx* c, int w, int h)
                                         : 0xffffffffu;
     d.drop_mask = p.drop_mask; d.dynamic_mask = p.dynamic_mask;
     d.dilate_radius = p.dilate_iterations; d.colour_source = p.colour_source;
+    c->ptab_margin = d.Dl != d.D ? (d.Dl - d.D + 4 + 3) / 4 * 4 : 0;
+    c->ptab_pitch = c->ptab_margin + (w + 3) / 4 * 4 + 4;
 }
 
 static int set_shape(ssm_ctx* c, int w, int h, int batch)
@@ -101,7 +103,7 @@ static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<
 
 static void free_all(ssm_ctx* c)
 {
-    void* ptrs[] = {c->d_left, c->d_right, c->d_recL, c->d_recR, c->d_C, c->d_S, c->d_disp_raw, c->d_disp_lr, c->d_disp_med,
+    void* ptrs[] = {c->d_left, c->d_right, c->d_recL, c->d_recR, c->d_ptab, c->d_C, c->d_S, c->d_disp_raw, c->d_disp_lr, c->d_disp_med,
                     c->d_disp, c->d_disp2key, c->d_wta_rec, c->d_ck, c->d_uniq_thr, c->d_cc_label, c->d_cc_size, c->d_depth, c->d_label, c->d_mask, c->d_label_lut, c->d_sem,
                     c->d_rgb, c->d_pose, c->d_min_disp, c->d_points, c->d_blk_count, c->d_counters, c->d_table, c->d_send,
                     c->d_recv, c->d_send_counts};
@@ -207,6 +209,7 @@ static void offset_buffers(ssm_ctx* c, ptrdiff_t frames)
     const ptrdiff_t npix = (ptrdiff_t)c->dp.W * c->dp.H * frames;
     const ptrdiff_t cells = (ptrdiff_t)c->dp.W1 * c->dp.H * c->dp.Dl * frames;
     c->d_recL += npix; c->d_recR += npix;
+    if (c->d_ptab) c->d_ptab += (ptrdiff_t)c->dp.H * 6 * c->ptab_pitch * frames;
     c->d_C += cells; c->d_S += cells; c->d_hs += cells;
     c->d_disp_raw += npix; c->d_disp_lr += npix; c->d_disp_med += npix; c->d_disp += npix;
     c->d_disp2key += npix; c->d_wta_rec += (c->dp.Dl > 128 ? 4 : 2) * npix; c->d_cc_label += npix;
@@ -501,6 +504,8 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
         c->no_pad = np && np[0] == '1';
         const char* sr = getenv("SSM_SELECT_ROWS");
         if (sr && atoi(sr) > 0) c->select_rows = atoi(sr);
+        const char* nt = getenv("SSM_NO_COST_TMA");
+        c->no_cost_tma = nt && nt[0] == '1';
         const char* ng = getenv("SSM_NO_GROW");
         c->auto_grow = !(ng && ng[0] == '1');
         const char* m = getenv("SSM_MAX_CLUSTER");
@@ -521,6 +526,11 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
         for (auto& ev : set) A(cudaEventCreate(&ev));
     A(dalloc(&c->d_left, npix)); A(dalloc(&c->d_right, npix));
     A(dalloc(&c->d_recL, npix)); A(dalloc(&c->d_recR, npix));
+    if (layout_disparities(c, p->num_disparities) == 128) {   // right image in table format for k_cost_tma (sgbm_cost.cu)
+        const int ld = layout_disparities(c, p->num_disparities);
+        const size_t margin = ld != p->num_disparities ? (size_t)(ld - p->num_disparities + 4 + 3) / 4 * 4 : 0;
+        A(dalloc(&c->d_ptab, (margin + (size_t)(c->cap_w + 3) / 4 * 4 + 4) * 6 * c->cap_h * c->cap_b));
+    }
     A(dalloc(&c->d_C, ncell)); A(dalloc(&c->d_S, ncell));
     c->d_hs = c->d_S;   // horizontal sums are dead once C exists; S is written afterwards
     A(dalloc(&c->d_disp_raw, npix)); A(dalloc(&c->d_disp_lr, npix)); A(dalloc(&c->d_disp_med, npix)); A(dalloc(&c->d_disp, npix));

@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "ssm_internal.cuh"
+#include "ssm_tma.cuh"
 
 namespace ssm {
 
@@ -567,15 +568,356 @@ __global__ void __launch_bounds__(256, 2) k_cost_fused(const uint2* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1 fused, r2: the same three phases with the per-row table building taken off the instruction stream.
+//
+//   * k_prefilter_tab writes the RIGHT image's six Birchfield-Tomasi quantities directly in table format: one 32-bit word
+//     P_q[x] = val_q[x] | val_q[x-1] << 16 per pixel and quantity (array [frame][row][q][pitch], zero margin on the left for
+//     padded layouts).  The packed pair (d, d+1) = 2w, 2w+1 of pixel x is then the single word P_q[x - 2w]: sixteen lanes on
+//     consecutive words read sixteen banks of one parity, the other half-warp (the adjacent pixel) the other parity.
+//   * The cost kernel pulls the six table rows of an image row with SIX TMA 1-D BULK COPIES tracked by one mbarrier, two
+//     rows ahead (double-buffered): phase 0 of k_cost_fused (record extraction + 12 STS.U16 per right pixel, 13 % of its
+//     instructions) and one of its two per-row fetch/convert steps are gone.
+//   * The left image's 8 pre-combined words per pixel are built for the NEXT row by the spare warp of phase 1, which has
+//     two thirds of a main warp's work to spare.
+//   * Phase 2b keeps each thread's 8-column slice of the ring contiguous ([slot][group][half][word][4 columns]): two
+//     LDS.128 + two STS.128 instead of 8 + 8 32-bit accesses; the output pointer is advanced, not recomputed.
+// Shapes: D >= 128 layouts with the diagonal sweep and two table buffers inside the 113 KB of a CTA pair (D = 128).
+// ------------------------------------------------------------------------------------------------
+// 12 consecutive bytes starting at byte address `a` of a 4-byte aligned array, from four aligned 32-bit loads
+__device__ __forceinline__ uint3 load12_unaligned(const uint8_t* __restrict__ base, size_t a)
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (a >> 2);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    const uint32_t sh = (uint32_t)(a & 3) * 8u;
+    return make_uint3(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh));
+}
+__device__ __forceinline__ int byte12(const uint3& v, int i)
+{
+    return (int)(((i < 4 ? v.x : (i < 8 ? v.y : v.z)) >> (8 * (i & 3))) & 0xffu);
+}
+
+// One thread makes 4 consecutive pixels x0 .. x0 + 3 (and the values of pixel x0 - 1, the upper half of P[x0]).
+// blockIdx.y = 0: left image -> 8-byte records (as k_prefilter8); 1: right image -> table words.
+__global__ void __launch_bounds__(256) k_prefilter_tab(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right,
+                                                       uint2* __restrict__ recL, uint32_t* __restrict__ ptab, int W, int H, int ftzero,
+                                                       int quads_per_row, size_t total_quads, int aligned4, int pitch, int margin)
+{
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total_quads) return;
+    const int which = blockIdx.y;
+    const uint8_t* img_all = which ? right : left;
+    const int x0 = (int)(q % quads_per_row) * 4;
+    const size_t row = q / quads_per_row;            // frame * H + y
+    const int y = (int)(row % H);
+    const size_t cur_o = row * (size_t)W;
+    const size_t up_o = y > 0 ? cur_o - W : cur_o, dn_o = y < H - 1 ? cur_o + W : cur_o;
+    int g[7], r[7];                                  // columns x0 - 2 .. x0 + 4
+    if (aligned4 && x0 >= 8 && x0 + 16 <= W) {
+        const uint3 a = load12_unaligned(img_all, up_o + x0 - 3), b = load12_unaligned(img_all, cur_o + x0 - 3),
+                    c = load12_unaligned(img_all, dn_o + x0 - 3);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const int sx = (byte12(b, i + 2) - byte12(b, i)) * 2 + (byte12(a, i + 2) - byte12(a, i)) + (byte12(c, i + 2) - byte12(c, i));
+            g[i] = max(-ftzero, min(ftzero, sx)) + ftzero;
+            r[i] = byte12(b, i + 1);
+        }
+    } else {
+        const uint8_t* cur = img_all + cur_o;
+        const uint8_t* up = img_all + up_o;
+        const uint8_t* dn = img_all + dn_o;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const int x = x0 - 2 + i;
+            const int xm = min(max(x - 1, 0), W - 1), xc = min(max(x, 0), W - 1), xp = min(max(x + 1, 0), W - 1);
+            const bool border = x <= 0 || x >= W - 1;    // first / last column (and beyond) are ftzero in both channels (A-1)
+            int sx = ((int)cur[xp] - (int)cur[xm]) * 2 + ((int)up[xp] - (int)up[xm]) + ((int)dn[xp] - (int)dn[xm]);
+            sx = max(-ftzero, min(ftzero, sx)) + ftzero;
+            g[i] = border ? ftzero : sx;
+            r[i] = border ? ftzero : (int)cur[xc];
+        }
+    }
+    // values of pixels x0 - 1 .. x0 + 3 (index p = 0 .. 4 <-> g[p + 1]); zero outside the image
+    uint32_t val[6][5];                              // loG, hiG, vG, loR, hiR, vR
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+        const int x = x0 - 1 + p;
+        const bool inside = x >= 0 && x < W;
+        const bool hl = x > 0, hr = x < W - 1;
+        const int gc = g[p + 1], rc = r[p + 1];
+        const int ga = hl ? (gc + g[p]) >> 1 : gc, gb = hr ? (gc + g[p + 2]) >> 1 : gc;
+        const int ra = hl ? (rc + r[p]) >> 1 : rc, rb = hr ? (rc + r[p + 2]) >> 1 : rc;
+        val[0][p] = inside ? (uint32_t)min(min(ga, gb), gc) : 0u;
+        val[1][p] = inside ? (uint32_t)max(max(ga, gb), gc) : 0u;
+        val[2][p] = inside ? (uint32_t)gc : 0u;
+        val[3][p] = inside ? (uint32_t)min(min(ra, rb), rc) : 0u;
+        val[4][p] = inside ? (uint32_t)max(max(ra, rb), rc) : 0u;
+        val[5][p] = inside ? (uint32_t)rc : 0u;
+    }
+    if (which == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (x0 + i >= W) break;
+            const int p = i + 1;
+            recL[cur_o + x0 + i] = make_uint2(val[2][p] | (val[0][p] << 8) | (val[1][p] << 16) | (val[5][p] << 24), val[3][p] | (val[4][p] << 8));
+        }
+        return;
+    }
+    uint32_t* trow = ptab + row * 6 * (size_t)pitch;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+        uint32_t* dst = trow + (size_t)t * pitch;
+        *reinterpret_cast<uint4*>(dst + margin + x0) = make_uint4(val[t][1] | (val[t][0] << 16), val[t][2] | (val[t][1] << 16),
+                                                                  val[t][3] | (val[t][2] << 16), val[t][4] | (val[t][3] << 16));
+        if (x0 == 0)
+            for (int i = 0; i < margin; i += 4) *reinterpret_cast<uint4*>(dst + i) = make_uint4(0u, 0u, 0u, 0u);
+        if (x0 + 4 >= W)
+            for (int i = margin + x0 + 4; i < pitch; i += 4) *reinterpret_cast<uint4*>(dst + i) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+template <int TX>
+struct CostGeom2 : CostGeom<TX> {
+    using G = CostGeom<TX>;
+    static constexpr int PTW = (G::D + G::NE + 2 + 3) / 4 * 4;          // words per table row in shared memory
+    static constexpr int NG = TX / 8;                                   // phase-2 column groups
+    static constexpr size_t smem_bytes(int bs)
+    {
+        return sizeof(uint32_t) * ((size_t)2 * 6 * PTW + (size_t)2 * G::NE * 8 + (size_t)G::NE * G::PS + (size_t)bs * TX * G::WPP) + 16;
+    }
+};
+
+template <int TX, int RAD, bool PAD>
+__global__ void __launch_bounds__(256, 2) k_cost_tma(const uint2* __restrict__ recL, const uint32_t* __restrict__ ptab,
+                                                     int16_t* __restrict__ C, int W, int H, int Dv, int band_rows, int pitch, int margin,
+                                                     uint32_t mone, uint32_t padw)
+{
+    using G = CostGeom2<TX>;
+    constexpr int D = G::D, WPP = G::WPP, PS = G::PS, LPP = G::LPP, WPL = G::WPL, PTW = G::PTW, NG = G::NG, SL = G::SL;
+    constexpr int radius = RAD, bs = 2 * RAD + 1;
+    static_assert(G::DIAG && RAD >= 0, "diagonal-sweep shapes with a compile-time window only");
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int W1 = W - Dv;
+    const int t0 = blockIdx.x * TX, b = blockIdx.z;
+    const int y0 = blockIdx.y * band_rows, y1 = min(H, y0 + band_rows);
+    const int e_lo = max(t0 - radius, 0), e_hi = min(t0 + TX - 1 + radius, W1 - 1);
+    const int n_e = e_hi - e_lo + 1;
+    const int xs = (e_lo + Dv - (D - 2)) & ~3;       // image pixel of table word 0 (may be negative: the zero margin)
+    const int xoff = e_lo + Dv - xs;                 // table index of (pixel e_lo, word 0); index(el, w) = xoff + el - 2w
+    const uint32_t copy_bytes = (uint32_t)((xoff + n_e + 3) & ~3) * 4u;
+    uint32_t one = 0u - mone;
+    asm volatile("" : "+r"(one));
+
+    uint32_t* Pt = smem;                             // [2 buffers][6 quantities][PTW]
+    uint32_t* Lt = Pt + 2 * 6 * PTW;                 // [2 buffers][NE][8]
+    uint32_t* pix = Lt + 2 * G::NE * 8;              // [NE][PS]
+    uint32_t* ring = pix + G::NE * PS;               // [bs][NG][2][WPP][4]
+    const uint32_t bar0 = smem_addr(ring + bs * TX * WPP);
+    {
+        uint4* r4 = reinterpret_cast<uint4*>(ring);
+        for (int i = threadIdx.x; i < bs * TX * WPP / 4; i += 256) r4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    const int j_begin = y0 - radius, j_end = y1 + radius;
+    const int r_first = max(j_begin, 0), r_last = min(j_end - 1, H - 1);
+    const bool spare = threadIdx.x >= 224;
+    const int sl = threadIdx.x - 224;                // lane of the spare warp
+
+    auto issue = [&](int r, int buf) {               // one thread: the six table rows of image row r
+        const uint32_t bar = bar0 + 8 * buf;
+        mbar_expect(bar, 6 * copy_bytes);
+        const uint32_t* src = ptab + ((size_t)b * H + r) * 6 * (size_t)pitch + margin + xs;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) tma_load_1d(smem_addr(Pt + (buf * 6 + t) * PTW), src + (size_t)t * pitch, copy_bytes, bar);
+    };
+    if (threadIdx.x == 224) {
+        mbar_init1(bar0);
+        mbar_init1(bar0 + 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue(r_first, 0);
+        if (r_first + 1 <= r_last) issue(r_first + 1, 1);
+    }
+    // left records: spare warp, two per lane, one row ahead
+    uint2 ql[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
+    auto fetch_left = [&](int r) {
+        const uint2* src = recL + ((size_t)b * H + r) * W + e_lo + Dv;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (sl + 32 * k < n_e) ql[k] = src[sl + 32 * k];
+    };
+    auto build_left = [&](int buf) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = sl + 32 * k;
+            if (i < n_e) {
+                const uint2 q = ql[k];
+                const uint32_t ug = q.x & 0xffu, log_ = (q.x >> 8) & 0xffu, hig = (q.x >> 16) & 0xffu;
+                const uint32_t ur = q.x >> 24, lor = q.y & 0xffu, hir = (q.y >> 8) & 0xffu;
+                uint4* dst = reinterpret_cast<uint4*>(Lt + (buf * G::NE + i) * 8);
+                dst[0] = make_uint4((ug + kKb) * 0x10001u, (kKb - ug) * 0x10001u, (kKb - hig) * 0x10001u, (log_ + kKb) * 0x10001u);
+                dst[1] = make_uint4((ur + kKb) * 0x10001u, (kKb - ur) * 0x10001u, (kKb - hir) * 0x10001u, (lor + kKb) * 0x10001u);
+            }
+        }
+    };
+    if (spare) {
+        fetch_left(r_first);
+        build_left(0);
+        if (r_first + 1 <= r_last) fetch_left(r_first + 1);
+    }
+
+    // phase-2 identity: 8 consecutive columns x one word
+    const int cgp = threadIdx.x / WPP;
+    const int w2 = threadIdx.x - cgp * WPP;
+    const int c0 = t0 + cgp * 8;
+    const bool interior = c0 - RAD >= 0 && c0 + 7 + RAD <= W1 - 1;
+    const int nvalid = min(8, W1 - c0);              // <= 0: this thread has no columns
+    const bool padded_word = PAD && 2 * w2 >= Dv;
+    uint32_t crun[8], hs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { crun[i] = 0u; hs[i] = 0u; }
+    uint32_t* dst = reinterpret_cast<uint32_t*>(C) + (((size_t)b * H + y0) * W1 + c0) * WPP + w2;
+    const size_t rowstep = (size_t)W1 * WPP;
+    uint4* const ring_t = reinterpret_cast<uint4*>(ring) + (size_t)cgp * 2 * WPP + w2;   // this thread's cell of slot 0
+    __syncthreads();                                 // ring zeroed, Lt[0] built, mbarriers initialised
+
+    auto bt_word = [&](const uint4& la, const uint4& lb, uint32_t loG, uint32_t hiG, uint32_t vG, uint32_t loR, uint32_t hiR,
+                       uint32_t vR) -> uint32_t {
+        const uint32_t g0 = __vimax3_s16x2(hiG * mone + la.x, loG * one + la.y, kKw);
+        const uint32_t g1 = __vimax3_s16x2(vG * one + la.z, vG * mone + la.w, kKw);
+        const uint32_t r0 = __vimax3_s16x2(hiR * mone + lb.x, loR * one + lb.y, kKw);
+        const uint32_t r1 = __vimax3_s16x2(vR * one + lb.z, vR * mone + lb.w, kKw);
+        const uint32_t cgv = __vmins2(g0, g1), crv = __vmins2(r0, r1);
+        return cgv + ((crv >> 2) & 0x3fff3fffu) + kUnbias;
+    };
+
+    auto phase2b = [&](int jj, int slot_) {          // vertical running sum against the ring, output of row jj - radius
+        if (nvalid > 0) {
+            uint4* rg = ring_t + (size_t)slot_ * (NG * 2 * WPP);
+            const uint4 o0 = rg[0], o1 = rg[WPP];
+            rg[0] = make_uint4(hs[0], hs[1], hs[2], hs[3]);
+            rg[WPP] = make_uint4(hs[4], hs[5], hs[6], hs[7]);
+            crun[0] = crun[0] + hs[0] - o0.x; crun[1] = crun[1] + hs[1] - o0.y; crun[2] = crun[2] + hs[2] - o0.z; crun[3] = crun[3] + hs[3] - o0.w;
+            crun[4] = crun[4] + hs[4] - o1.x; crun[5] = crun[5] + hs[5] - o1.y; crun[6] = crun[6] + hs[6] - o1.z; crun[7] = crun[7] + hs[7] - o1.w;
+            if (jj - radius >= y0) {
+                if (nvalid == 8) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) dst[c * WPP] = padded_word ? padw : crun[c];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (c < nvalid) dst[c * WPP] = padded_word ? padw : crun[c];
+                }
+                dst += rowstep;
+            }
+        }
+    };
+
+    int slot = 0, prev_r = -1;
+    for (int j = j_begin; j < j_end; ++j) {
+        const int r = min(max(j, 0), H - 1);
+        const bool fresh = r != prev_r;              // CTA-uniform
+        prev_r = r;
+        const int k = r - r_first, buf = k & 1;
+        if (fresh) {
+            mbar_wait(bar0 + 8 * buf, (uint32_t)(k >> 1) & 1u);
+            const uint32_t* P = Pt + buf * 6 * PTW + xoff;
+            const uint32_t* L = Lt + buf * G::NE * 8;
+            // ---- phase 1: pixel costs.  Diagonal sweep as in k_cost_fused (word w of pixel e and word w + 1 of pixel e + 2 read the
+            // same right-image words), closed into a ring: the lane whose top word runs off the disparity range at step t takes the
+            // word that enters at the bottom (w = jl + t - LPP) -- six fresh table loads for that lane, then the sweep property
+            // holds for it as well.  No left-over items: the eighth warp only prepares the next row's left tables.
+            if (!spare) {
+                const int sg = threadIdx.x >> 4, jl = threadIdx.x & 15;
+                const int el0 = (sg >> 1) * 2 * SL + (sg & 1);
+                const bool work = el0 < n_e;
+                uint32_t loG[WPL], hiG[WPL], vG[WPL], loR[WPL], hiR[WPL], vR[WPL];
+                if (work) {
+                    const uint32_t* q = P + el0 - 2 * jl;
+#pragma unroll
+                    for (int kk = 0; kk < WPL; ++kk) {
+                        loG[kk] = q[0 * PTW - 2 * kk * LPP]; hiG[kk] = q[1 * PTW - 2 * kk * LPP]; vG[kk] = q[2 * PTW - 2 * kk * LPP];
+                        loR[kk] = q[3 * PTW - 2 * kk * LPP]; hiR[kk] = q[4 * PTW - 2 * kk * LPP]; vR[kk] = q[5 * PTW - 2 * kk * LPP];
+                    }
+                }
+                if (work) {
+#pragma unroll
+                    for (int t = 0; t < SL; ++t) {
+                        const int el = el0 + 2 * t;
+                        if (el < n_e) {
+                            if (t > 0 && jl + t == LPP) {
+                                const uint32_t* q2 = P + el;         // word 0 of pixel el
+                                loG[WPL - 1] = q2[0]; hiG[WPL - 1] = q2[PTW]; vG[WPL - 1] = q2[2 * PTW];
+                                loR[WPL - 1] = q2[3 * PTW]; hiR[WPL - 1] = q2[4 * PTW]; vR[WPL - 1] = q2[5 * PTW];
+                            }
+                            const uint4 la = reinterpret_cast<const uint4*>(L + el * 8)[0];
+                            const uint4 lb = reinterpret_cast<const uint4*>(L + el * 8)[1];
+                            uint32_t* out = pix + el * PS;
+#pragma unroll
+                            for (int kk = 0; kk < WPL; ++kk)
+                                out[(kk * LPP + jl + t) & (WPP - 1)] = bt_word(la, lb, loG[kk], hiG[kk], vG[kk], loR[kk], hiR[kk], vR[kk]);
+                        }
+                    }
+                }
+            } else if (r + 1 <= r_last) {
+                build_left(buf ^ 1);
+                if (r + 2 <= r_last) fetch_left(r + 2);
+            }
+            __syncthreads();                         // tile (and the next row's left table) complete; table buffer `buf` is free
+            // ---- phase 2a: horizontal window sums of my 8 columns (registers): the middle one as a tree, the others outwards from it
+            if (nvalid > 0) {
+                uint32_t v[8 + 2 * RAD];
+                if (interior) {
+                    const uint32_t* src = pix + (c0 - RAD - e_lo) * PS + w2;
+#pragma unroll
+                    for (int i = 0; i < 8 + 2 * RAD; ++i) v[i] = src[i * PS];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8 + 2 * RAD; ++i) {
+                        const int e = min(max(c0 + i - RAD, 0), W1 - 1) - e_lo;
+                        v[i] = pix[e * PS + w2];
+                    }
+                }
+                uint32_t part[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int i = 0; i < 2 * RAD + 1; ++i) part[i & 3] += v[3 + i];
+                hs[3] = (part[0] + part[1]) + (part[2] + part[3]);
+#pragma unroll
+                for (int c = 4; c < 8; ++c) hs[c] = hs[c - 1] + v[c + 2 * RAD] - v[c - 1];
+#pragma unroll
+                for (int c = 2; c >= 0; --c) hs[c] = hs[c + 1] + v[c] - v[c + 2 * RAD + 1];
+            }
+            __syncthreads();                         // tile consumed
+            if (threadIdx.x == 224 && r + 2 <= r_last) issue(r + 2, buf);   // behind the barrier: the eighth warp has the slack
+        }
+        phase2b(j, slot);                            // flows into the next row's phase 1 without a barrier
+        slot = slot + 1 == bs ? 0 : slot + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 static bool use_fused_cost(const ssm_ctx* c)
 {
     const int D = c->dp.Dl;
     return !c->force_legacy_cost && (D == 16 || D == 32 || D == 64 || D == 128 || D == 256 || D == 512);
 }
 
+// k_cost_tma: 128-disparity layouts (D = 128, or 80 / 96 / 112 padded), the reference's block size
+static bool use_cost_tma(const ssm_ctx* c)
+{
+    return use_fused_cost(c) && !c->no_cost_tma && c->d_ptab && c->dp.Dl == 128 && c->dp.bs == 11;
+}
+
 int launch_prefilter(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, cudaStream_t s)
 {
     const DevParams& p = c->dp;
+    if (use_cost_tma(c)) {
+        const int quads_per_row = (p.W + 3) / 4;
+        const size_t total_quads = (size_t)B * p.H * quads_per_row;
+        dim3 grid((unsigned)((total_quads + 255) / 256), 2);
+        k_prefilter_tab<<<grid, 256, 0, s>>>(dL, dR, reinterpret_cast<uint2*>(c->d_recL), c->d_ptab, p.W, p.H, p.ftzero, quads_per_row, total_quads,
+                                             (int)(((reinterpret_cast<uintptr_t>(dL) | reinterpret_cast<uintptr_t>(dR)) & 3) == 0), c->ptab_pitch,
+                                             c->ptab_margin);
+        SSM_LAUNCH_CHECK(c);
+        return SSM_OK;
+    }
     if (use_fused_cost(c)) {
         const int quads_per_row = (p.W + 3) / 4;
         const size_t total_quads = (size_t)B * p.H * quads_per_row;
@@ -612,9 +954,27 @@ static int launch_cost_fused_t(ssm_ctx* c, int B, cudaStream_t s)
     return SSM_OK;
 }
 
+template <int TX, int RAD, bool PAD>
+static int launch_cost_tma_t(ssm_ctx* c, int B, cudaStream_t s)
+{
+    const DevParams& p = c->dp;
+    const size_t smem = CostGeom2<TX>::smem_bytes(p.bs);
+    SSM_CUDA(cudaFuncSetAttribute(k_cost_tma<TX, RAD, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = (p.W1 + TX - 1) / TX;
+    int bands = std::max(1, std::min(p.H / 32, (c->sm_count * 8 + tiles * B - 1) / (tiles * B)));
+    const int band_rows = (p.H + bands - 1) / bands;
+    bands = (p.H + band_rows - 1) / band_rows;
+    dim3 grid(tiles, bands, B);
+    k_cost_tma<TX, RAD, PAD><<<grid, 256, smem, s>>>(reinterpret_cast<const uint2*>(c->d_recL), c->d_ptab, c->d_C, p.W, p.H, p.D, band_rows,
+                                                     c->ptab_pitch, c->ptab_margin, 0xffffffffu, (kBig - (uint32_t)p.P2) * 0x10001u);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
 int launch_cost_volume(ssm_ctx* c, int B, cudaStream_t s)
 {
     const DevParams& p = c->dp;
+    if (use_cost_tma(c)) return p.Dl != p.D ? launch_cost_tma_t<32, 5, true>(c, B, s) : launch_cost_tma_t<32, 5, false>(c, B, s);
     if (use_fused_cost(c)) {
         // TX * D/2 = 2048 words per CTA row
         const bool r5 = p.bs == 11;   // the reference's block size gets the compile-time window; others the generic one

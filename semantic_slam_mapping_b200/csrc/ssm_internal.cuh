@@ -144,6 +144,9 @@ struct ssm_ctx {
     // stereo
     uint8_t *d_left = nullptr, *d_right = nullptr;   // [B][H][W] staging for host calls
     uint4 *d_recL = nullptr, *d_recR = nullptr;      // [B][H][W] prefilter + BT records
+    uint32_t* d_ptab = nullptr;                      // [B][H][6][ptab_pitch] right image in table format (k_prefilter_tab -> k_cost_tma), 128-disparity layouts
+    int ptab_pitch = 0, ptab_margin = 0;             // words per (row, quantity); zero words left of pixel 0 (padded layouts)
+    bool no_cost_tma = false;                        // SSM_NO_COST_TMA=1: k_cost_fused (tables built per row inside the kernel) instead of k_cost_tma
     uint16_t* d_hs = nullptr;                        // [B][H][W1][D] horizontal window sums (aliases d_S)
     int16_t* d_C = nullptr;                          // [B][H][W1][D] matching cost
     uint16_t* d_S = nullptr;                         // [B][H][W1][D] aggregated cost

@@ -188,6 +188,35 @@ def test_fused_cost_kernel_matches_oracle_cost_volume(H, W, D, bs, seed):
     assert int((got != want).sum()) == 0
 
 
+@pytest.mark.parametrize("H,W,D,seed", [(130, 333, 128, 54), (36, 150, 80, 56), (47, 421, 112, 59)])
+def test_in_kernel_table_cost_path_still_exact(monkeypatch, H, W, D, seed):
+    """SSM_NO_COST_TMA=1: k_cost_fused (tables built inside the kernel) on the shapes that k_cost_tma serves by default."""
+    monkeypatch.setenv("SSM_NO_COST_TMA", "1")
+    L, R, _ = synth.stereo_pair(H, W, D, seed)
+    p = _params(D, W, H)
+    want, vols = oracle.sgbm(L, R, _oparams(p), want_volumes=True)
+    with Context(p) as ctx:
+        got = ctx.sgbm(L, R)
+        C = ctx.debug_volume("C", W, H)
+    assert int((C != vols["C"]).sum()) == 0 and int((got != want).sum()) == 0
+
+
+@pytest.mark.parametrize("H,W,D,seed", [(33, 161, 128, 91), (70, 500, 128, 92), (64, 257, 96, 93), (41, 1241, 128, 94), (12, 140, 128, 95)])
+def test_tma_table_cost_kernel_edges(H, W, D, seed):
+    """k_prefilter_tab + k_cost_tma: widths that leave a partial last tile / partial last quad, a single short band, the padded margin."""
+    L, R, _ = synth.stereo_pair(H, W, D, seed)
+    p = _params(D, W, H)
+    want, vols = oracle.sgbm(L, R, _oparams(p), want_volumes=True)
+    with Context(p) as ctx:
+        got = ctx.sgbm(L, R)
+        C = ctx.debug_volume("C", W, H)
+        # a second call with a smaller frame re-uses the table buffer with another pitch
+        L2, R2, _ = synth.stereo_pair(H - 3, W - 9, D, seed + 100)
+        got2 = ctx.sgbm(L2, R2)
+    assert int((C != vols["C"]).sum()) == 0 and int((got != want).sum()) == 0
+    assert int((got2 != oracle.sgbm(L2, R2, _oparams(p))).sum()) == 0
+
+
 def test_legacy_two_kernel_cost_path_still_exact(monkeypatch):
     monkeypatch.setenv("SSM_LEGACY_COST", "1")
     L, R, _ = synth.stereo_pair(64, 240, 64, 61)
