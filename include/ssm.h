@@ -230,13 +230,26 @@ int ssm_labels_from_indices_batch_device(ssm_ctx* ctx, int batch, const uint8_t*
 /* The reference reads every image with cv::imread: the grey stereo pair with flag 0, the colour and label images with
  * the default flag.  ssm_png_decode_batch_device decodes `batch` PNG files held in host memory into device images of
  * the layout the pipeline entry points take: mode 0 -> [batch][h][w] u8 (== imread(path, 0)), mode 1 -> [batch][h][w][3]
- * u8 BGR (== imread(path)).  The zlib streams are inflated on `host_threads` host threads (0 = all cores); PNG
+ * u8 BGR (== imread(path)).  host_threads = 0: the zlib streams are inflated ON THE GPU, one warp per file (the host threads only
+ * walk the chunks, verify their CRCs and gather the IDAT payloads; SSM_HOST_INFLATE=1 in the environment turns this off);
+ * host_threads >= 1: they are inflated with zlib on that many host threads.  PNG
  * un-filtering, palette expansion, alpha stripping, channel reordering and the colour -> grey conversion run on the GPU
  * on `stream` (NULL = the context's stream).  Every file must be w x h, 8 bits per sample, non-interlaced (grey,
- * grey + alpha, RGB, RGBA or palette).  Bit-exact with cv2 4.13.  The host returns when the batch is queued. */
+ * grey + alpha, RGB, RGBA or palette).  Bit-exact with cv2 4.13.  The host returns when the batch is queued.  Container
+ * errors (signature, chunk CRC, size, colour type) are returned by the call itself; with the GPU decoder a corrupt or short
+ * zlib stream or a scanline filter type above 4 is only known when the batch has run: it is returned by ssm_png_batch_wait,
+ * or by the next-but-one ssm_png_decode_batch_device call (the one that re-uses the batch's staging buffers). */
 int ssm_png_info(const uint8_t* png, size_t png_bytes, int* w, int* h, int* channels /* 1 or 3, may be NULL */);
 int ssm_png_decode_batch_device(ssm_ctx* ctx, int batch, const uint8_t* const* png, const size_t* png_bytes, int w, int h,
                                 int mode, uint8_t* d_out, int host_threads, void* stream);
+/* Blocks until every queued ingest batch has been decoded; returns the first stream error of a GPU-inflated batch, if any. */
+int ssm_png_batch_wait(ssm_ctx* ctx);
+/* The GPU decoder on its own (blocking; test and tooling entry point): n zlib streams (RFC 1950 / 1951) in host memory ->
+ * out[i][0 .. out_bytes[i]) in host memory.  status[i]: 0 = ok, 1 bad zlib header, 2 bad block, 3 bad code lengths, 4 bad
+ * symbol, 5 distance too far back, 6 input ends early, 7 Adler-32 mismatch, 8 fewer than out_bytes[i] bytes in the stream.
+ * As with inflate() and a full output buffer, data beyond out_bytes[i] is ignored. */
+int ssm_zlib_inflate_batch(ssm_ctx* ctx, int n, const uint8_t* const* streams, const size_t* stream_bytes, uint8_t* const* out,
+                           const size_t* out_bytes, int* status);
 /* one file, host buffer out (blocking): == cv::imread(path, mode ? 1 : 0) */
 int ssm_png_decode(ssm_ctx* ctx, const uint8_t* png, size_t png_bytes, int mode, uint8_t* out, size_t out_bytes, int* w, int* h);
 

@@ -2,7 +2,9 @@
 //
 // Replaces the cv::imread calls of FrameReader::next (/root/reference src/rgbdframe.cpp:45-78, 138-180: the grey stereo
 // pair via imread(path, 0), the colour and label images via imread(path)) for batches of frames.  A PNG is a zlib stream
-// of filtered scanlines.  The stream is inherently serial, so it is inflated on host threads (one image per task); the
+// of filtered scanlines.  The stream is inherently serial: it is inflated either on the GPU -- one warp per stream, hundreds
+// to thousands of streams per batch (k_inflate below; the host only walks the chunks, checks their CRCs and gathers the
+// IDAT payloads) -- or on host threads with zlib (one image per task; host_threads >= 1).  The
 // rest -- PNG un-filtering (None / Sub / Up / Average / Paeth), palette expansion, alpha stripping, RGB -> BGR reordering
 // and the colour -> grey conversion -- runs on the GPU and writes straight into the [batch][h][w] / [batch][h][w][3] device
 // images the pipeline entry points take.  Bit-exact with cv2 4.13 imread / imdecode: grey from colour is libpng's
@@ -52,7 +54,9 @@ static inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | 
 
 // Parses the chunks and inflates the IDAT stream into `out` (h rows of 1 filter byte + w * bpp bytes).  Returns an
 // error text or nullptr.
-static const char* png_inflate(const uint8_t* png, size_t n, PngInfo& info, uint8_t* out, size_t out_cap, bool header_only)
+// With `gather` != nullptr the IDAT payloads are concatenated there instead (the zlib stream for k_inflate; *gathered = its size).
+static const char* png_inflate(const uint8_t* png, size_t n, PngInfo& info, uint8_t* out, size_t out_cap, bool header_only,
+                               uint8_t* gather = nullptr, size_t gather_cap = 0, size_t* gathered = nullptr)
 {
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     if (n < 8 + 25 || memcmp(png, sig, 8) != 0) return "not a PNG file";
@@ -94,10 +98,12 @@ static const char* png_inflate(const uint8_t* png, size_t n, PngInfo& info, uint
             if (info.w < 1 || info.h < 1 || info.w > (1 << 20) || info.h > (1 << 20)) { err = "PNG dimensions out of range"; break; }
             if ((size_t)info.h * ((size_t)info.w * info.bpp + 1) > out_cap) { err = "PNG larger than the batch's frame size"; break; }
             if ((size_t)info.h * ((size_t)info.w * info.bpp + 1) > 0x7fffffffull) { err = "PNG too large"; break; }
-            if (inflateInit(&zs) != Z_OK) { err = "zlib inflateInit failed"; break; }
-            stream_open = true;
-            zs.next_out = out;
-            zs.avail_out = (uInt)((size_t)info.h * ((size_t)info.w * info.bpp + 1));
+            if (!gather) {
+                if (inflateInit(&zs) != Z_OK) { err = "zlib inflateInit failed"; break; }
+                stream_open = true;
+                zs.next_out = out;
+                zs.avail_out = (uInt)((size_t)info.h * ((size_t)info.w * info.bpp + 1));
+            }
         } else if (!have_ihdr) {
             err = "PNG does not start with IHDR";
             break;
@@ -110,6 +116,13 @@ static const char* png_inflate(const uint8_t* png, size_t n, PngInfo& info, uint
             have_srgb = true;
         } else if (!memcmp(type, "IDAT", 4)) {
             seen_idat = true;
+            if (gather) {
+                if (*gathered + len > gather_cap) { err = "PNG data stream larger than the file"; break; }
+                memcpy(gather + *gathered, data, len);
+                *gathered += len;
+                pos += 12 + (size_t)len;
+                continue;
+            }
             zs.next_in = const_cast<Bytef*>(data);
             zs.avail_in = len;
             const int rc = inflate(&zs, Z_NO_FLUSH);
@@ -124,14 +137,330 @@ static const char* png_inflate(const uint8_t* png, size_t n, PngInfo& info, uint
         inflateEnd(&zs);
     }
     if (!err && !have_ihdr) err = "PNG without IHDR";
+    if (!err && gather && !seen_idat) err = "PNG without image data";
     if (!err) {
         const size_t rb = (size_t)info.w * info.bpp + 1;
-        for (int y = 0; y < info.h; ++y)
+        for (int y = 0; y < info.h && !gather; ++y)
             if (out[(size_t)y * rb] > 4) { err = "bad PNG scanline filter type"; break; }
         const uint32_t g = have_srgb ? 45455u : gama;   // an sRGB chunk overrides gAMA
         info.file_gamma = (g != 0 && (g < 95000u || g > 105000u)) ? g : 0u;
     }
     return err;
+}
+
+// ---- device: DEFLATE (RFC 1951) inside a zlib wrapper (RFC 1950), one warp per stream ------------------------------------
+// A deflate stream is serial, so a warp decodes ONE stream: every lane runs the same bit-level decode on the same state (the
+// compressed words are broadcast loads, the Huffman tables sit in the warp's slice of shared memory), lane 0 stores the
+// literals and all 32 lanes copy the bytes of a match.  The parallelism is across streams: a KITTI frame is four files, a
+// batch of frames a few hundred to a few thousand streams -- one warp each, 8 warps per CTA, as many CTAs as there are
+// streams.  Tables: 10-bit (literal / length) and 8-bit (distance) first-level look-ups, longer codes through the canonical
+// count / symbol lists (the rare path).  Table building is warp-parallel (one symbol per lane fills its slots).
+// Stream rules follow zlib 1.3's inflate: header check, stored / fixed / dynamic blocks, over-subscribed and incomplete code
+// sets are errors (except a single one-bit code), distances beyond the start are errors, the Adler-32 trailer is checked
+// when the stream ends inside the output window; once the output window is full the rest of the stream is ignored, which
+// is what inflate() does with avail_out = the image size (libpng calls that "too much image data", a warning).
+constexpr int kLB = 10, kDB = 8;                 // first-level table bits
+struct InflateJob {
+    unsigned long long in_off, out_off;          // byte offsets (in_off 4-byte aligned) into the compressed / output buffers
+    uint32_t in_bytes, out_cap;                  // compressed size; bytes to produce
+    uint32_t rows, row_bytes;                    // PNG: rows of 1 + row_bytes bytes whose first byte must be a filter type 0..4 (rows = 0: no check)
+};
+enum { INF_OK = 0, INF_BAD_HEADER = 1, INF_BAD_BLOCK = 2, INF_BAD_CODES = 3, INF_BAD_SYMBOL = 4, INF_BAD_DISTANCE = 5, INF_TRUNCATED = 6,
+       INF_BAD_CHECK = 7, INF_SHORT = 8, INF_BAD_FILTER = 9 };
+
+struct InflateTabs {
+    uint16_t llut[1 << kLB];                     // (symbol << 4) | length, 0 = not a first-level code
+    uint16_t dlut[1 << kDB];
+    uint16_t lsym[288], dsym[32];                // symbols in canonical order
+    uint16_t lcnt[16], dcnt[16];                 // codes per length
+    uint16_t code[320];                          // canonical code of every symbol (table building)
+    uint8_t lens[320];
+};
+
+__constant__ uint16_t c_lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t c_clorder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+struct BitReader {
+    const uint32_t* w;
+    uint32_t nwords, wi;
+    unsigned long long buf;
+    int cnt;
+    __device__ __forceinline__ void refill()
+    {
+        if (cnt <= 32) {
+            const uint32_t v = wi < nwords ? __ldg(w + wi) : 0u;   // past the end: zeros (the caller checks consumed() against the size)
+            ++wi;
+            buf |= (unsigned long long)v << cnt;
+            cnt += 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1u); }
+    __device__ __forceinline__ void drop(int n) { buf >>= n; cnt -= n; }
+    __device__ __forceinline__ uint32_t take(int n) { const uint32_t v = peek(n); drop(n); return v; }
+    __device__ __forceinline__ unsigned long long consumed_bits() const { return (unsigned long long)wi * 32ull - (unsigned long long)cnt; }
+};
+
+// Builds the first-level table and the canonical lists for `n` code lengths.  Returns 0, or an INF_ error.  Warp-collective.
+__device__ int build_table(const uint8_t* lens, int n, uint16_t* lut, int bits, uint16_t* sym, uint16_t* cnt, uint16_t* code, int lane)
+{
+    int err = 0;
+    if (lane == 0) {
+        for (int l = 0; l < 16; ++l) cnt[l] = 0;
+        for (int s = 0; s < n; ++s) cnt[lens[s]]++;
+        int left = 1, maxlen = 0;
+        for (int l = 1; l < 16; ++l) {
+            left <<= 1;
+            left -= cnt[l];
+            if (left < 0) { err = INF_BAD_CODES; break; }   // over-subscribed
+            if (cnt[l]) maxlen = l;
+        }
+        if (!err && left > 0 && maxlen != 1 && maxlen != 0) err = INF_BAD_CODES;   // incomplete (zlib allows a lone one-bit code; an empty set decodes nothing)
+        uint16_t offs[16], next[16];
+        offs[1] = 0; next[1] = 0;
+        uint32_t c = 0;
+        for (int l = 1; l < 15; ++l) offs[l + 1] = offs[l] + cnt[l];
+        for (int l = 1; l < 16; ++l) { c = (c + (l > 1 ? cnt[l - 1] : 0)) << (l > 1 ? 1 : 0); next[l] = (uint16_t)c; }
+        for (int s = 0; s < n; ++s) {
+            const int l = lens[s];
+            if (l) { code[s] = next[l]++; sym[offs[l]++] = (uint16_t)s; }
+        }
+    }
+    err = __shfl_sync(0xffffffffu, err, 0);
+    for (int i = lane; i < (1 << bits); i += 32) lut[i] = 0;
+    __syncwarp();
+    if (err) return err;
+    for (int s = lane; s < n; s += 32) {
+        const int l = lens[s];
+        if (l && l <= bits) {
+            const uint32_t r = __brev((uint32_t)code[s]) >> (32 - l);
+            const uint16_t e = (uint16_t)((s << 4) | l);
+            for (uint32_t k = r; k < (1u << bits); k += 1u << l) lut[k] = e;
+        }
+    }
+    __syncwarp();
+    return 0;
+}
+
+// a code longer than the first-level table (or an unused pattern): canonical bit-by-bit decode; -1 = invalid
+__device__ __forceinline__ int decode_slow(BitReader& br, const uint16_t* cnt, const uint16_t* sym)
+{
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l < 16; ++l) {
+        code |= (int)((br.buf >> (l - 1)) & 1ull);
+        const int count = cnt[l];
+        if (code - count < first) { br.drop(l); return sym[index + (code - first)]; }
+        index += count;
+        first += count;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) k_inflate(const uint8_t* __restrict__ in_base, const InflateJob* __restrict__ jobs, int njobs,
+                                                 uint8_t* out_base, int* __restrict__ status)
+{
+    __shared__ InflateTabs tabs_all[8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int job = blockIdx.x * 8 + wib;
+    if (job >= njobs) return;
+    InflateTabs& T = tabs_all[wib];
+    const InflateJob J = jobs[job];
+    uint8_t* out = out_base + J.out_off;
+    const uint32_t cap = J.out_cap;
+    BitReader br;
+    br.w = reinterpret_cast<const uint32_t*>(in_base + J.in_off);
+    br.nwords = (J.in_bytes + 3u) >> 2;
+    br.wi = 0; br.buf = 0ull; br.cnt = 0;
+    uint32_t pos = 0;
+    int err = 0;
+    bool full = false;                               // the output window is full: the rest of the stream is ignored
+    br.refill();
+    {   // zlib header
+        const uint32_t cmf = br.take(8), flg = br.take(8);
+        if ((cmf & 15u) != 8u || (cmf >> 4) > 7u || ((cmf << 8) | flg) % 31u != 0u || (flg & 32u)) err = INF_BAD_HEADER;
+    }
+    int tables = 0;                                  // 0 none, 1 fixed, 2 dynamic
+    bool last = false;
+    while (!err && !last && !full) {
+        br.refill();
+        last = br.take(1) != 0u;
+        const uint32_t type = br.take(2);
+        if (type == 0u) {
+            br.drop(br.cnt & 7);
+            br.refill();
+            const uint32_t len = br.take(16);
+            br.refill();
+            const uint32_t nlen = br.take(16);
+            if ((len ^ 0xffffu) != nlen) { err = INF_BAD_BLOCK; break; }
+            // the bit buffer is byte aligned: copy `len` bytes starting at the current byte position
+            const unsigned long long byte0 = br.consumed_bits() >> 3;
+            if (byte0 + len > J.in_bytes) { err = INF_TRUNCATED; break; }
+            const uint32_t n = min(len, cap - pos);
+            const uint8_t* src = in_base + J.in_off + byte0;
+            for (uint32_t i = lane; i < n; i += 32) out[pos + i] = __ldg(src + i);
+            __syncwarp();
+            pos += n;
+            if (n < len) { full = true; break; }
+            // restart the bit reader behind the stored bytes
+            const unsigned long long nb = byte0 + len;
+            br.wi = (uint32_t)(nb >> 2); br.buf = 0ull; br.cnt = 0;
+            br.refill();
+            br.drop((int)(nb & 3ull) * 8);
+            continue;
+        }
+        if (type == 3u) { err = INF_BAD_BLOCK; break; }
+        if (type == 1u) {
+            if (tables != 1) {
+                for (int s = lane; s < 288; s += 32) T.lens[s] = s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8));
+                __syncwarp();
+                build_table(T.lens, 288, T.llut, kLB, T.lsym, T.lcnt, T.code, lane);
+                for (int s = lane; s < 32; s += 32) T.lens[s] = 5;
+                __syncwarp();
+                build_table(T.lens, 30, T.dlut, kDB, T.dsym, T.dcnt, T.code, lane);
+                tables = 1;
+            }
+        } else {
+            br.refill();
+            const int nlen = (int)br.take(5) + 257, ndist = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
+            if (nlen > 286 || ndist > 30) { err = INF_BAD_CODES; break; }
+            for (int s = lane; s < 19; s += 32) T.lens[s] = 0;
+            __syncwarp();
+            for (int i = 0; i < ncode; ++i) {
+                br.refill();
+                const uint32_t v = br.take(3);
+                if (lane == 0) T.lens[c_clorder[i]] = (uint8_t)v;
+            }
+            __syncwarp();
+            // the code-length code: its first-level table (7 bits) goes into dlut, its lists into dsym / dcnt
+            if ((err = build_table(T.lens, 19, T.dlut, 7, T.dsym, T.dcnt, T.code, lane))) break;
+            // zlib: an incomplete code-length set is an error as well (build_table lets a lone one-bit code pass; so does zlib only
+            // for the literal / distance sets) -- check it here
+            {
+                int left = 1;
+                for (int l = 1; l < 8; ++l) left = (left << 1) - T.dcnt[l];
+                int used = 0;
+                for (int l = 1; l < 8; ++l) used += T.dcnt[l];
+                if (left > 0 && used > 0) { err = INF_BAD_CODES; break; }
+                if (used == 0) { err = INF_BAD_CODES; break; }
+            }
+            int idx = 0, prev = 0;
+            while (idx < nlen + ndist) {
+                br.refill();
+                const uint16_t e = T.dlut[br.peek(7)];
+                if (e == 0) { err = INF_BAD_CODES; break; }
+                br.drop(e & 15);
+                const int s = e >> 4;
+                int rep = 1, val = s;
+                if (s == 16) {
+                    if (idx == 0) { err = INF_BAD_CODES; break; }
+                    val = prev; rep = 3 + (int)br.take(2);
+                } else if (s == 17) {
+                    val = 0; rep = 3 + (int)br.take(3);
+                } else if (s == 18) {
+                    val = 0; rep = 11 + (int)br.take(7);
+                }
+                if (idx + rep > nlen + ndist) { err = INF_BAD_CODES; break; }
+                // lens[] is being read by nobody else now: write the run (the first 19 entries are dead once the table above is built)
+                __syncwarp();
+                for (int i = lane; i < rep; i += 32) T.code[idx + i] = (uint16_t)val;   // staged in code[] (lens[0..18] still holds the code-length lengths)
+                idx += rep;
+                prev = val;
+            }
+            if (err) break;
+            __syncwarp();
+            if (T.code[256] == 0) { err = INF_BAD_CODES; break; }   // no end-of-block code
+            // distance lengths first (they sit behind the literal lengths in code[]), then the literal lengths
+            for (int s = lane; s < ndist; s += 32) T.lens[288 + s] = (uint8_t)T.code[nlen + s];
+            for (int s = lane; s < nlen; s += 32) T.lens[s] = (uint8_t)T.code[s];
+            __syncwarp();
+            if ((err = build_table(T.lens + 288, ndist, T.dlut, kDB, T.dsym, T.dcnt, T.code, lane))) break;
+            if ((err = build_table(T.lens, nlen, T.llut, kLB, T.lsym, T.lcnt, T.code, lane))) break;
+            tables = 2;
+        }
+        // ---- symbols of the block
+        for (;;) {
+            br.refill();
+            int s;
+            {
+                const uint16_t e = T.llut[br.peek(kLB)];
+                if (e) { br.drop(e & 15); s = e >> 4; }
+                else if ((s = decode_slow(br, T.lcnt, T.lsym)) < 0) { err = INF_BAD_SYMBOL; break; }
+            }
+            if (s < 256) {
+                if (pos >= cap) { full = true; break; }
+                if (lane == 0) out[pos] = (uint8_t)s;
+                ++pos;
+                continue;
+            }
+            if (s == 256) break;
+            s -= 257;
+            if (s >= 29) { err = INF_BAD_SYMBOL; break; }
+            const uint32_t length = c_lbase[s] + br.take(c_lext[s]);
+            br.refill();
+            int ds;
+            {
+                const uint16_t e = T.dlut[br.peek(kDB)];
+                if (e) { br.drop(e & 15); ds = e >> 4; }
+                else if ((ds = decode_slow(br, T.dcnt, T.dsym)) < 0) { err = INF_BAD_SYMBOL; break; }
+            }
+            if (ds >= 30) { err = INF_BAD_SYMBOL; break; }
+            const uint32_t dist = c_dbase[ds] + br.take(c_dext[ds]);
+            if (dist > pos) { err = INF_BAD_DISTANCE; break; }
+            if (pos >= cap) { full = true; break; }
+            const uint32_t n = min(length, cap - pos);
+            __syncwarp();                            // lane 0's literals are visible to the lanes that copy
+            {
+                const uint8_t* from = out + pos - dist;
+                for (uint32_t i = lane; i < n; i += 32) out[pos + i] = from[dist >= n ? i : i % dist];
+            }
+            __syncwarp();
+            pos += n;
+            if (n < length) { full = true; break; }
+        }
+        if (!err && br.consumed_bits() > (unsigned long long)J.in_bytes * 8ull) err = INF_TRUNCATED;
+    }
+    if (!err && !full) {
+        // stream ended inside the window: Adler-32 trailer
+        br.drop(br.cnt & 7);
+        br.refill();
+        const uint32_t t = (uint32_t)br.buf;          // (take() is for fewer than 32 bits)
+        br.drop(32);
+        const uint32_t want = __byte_perm(t, 0, 0x0123);
+        if (br.consumed_bits() > (unsigned long long)J.in_bytes * 8ull) err = INF_TRUNCATED;
+        else {
+            __syncwarp();
+            // per lane: a contiguous chunk; a = sum d, b = sum (chunk_len - idx) * d; combined below
+            const uint32_t chunk = (pos + 31u) / 32u;
+            const uint32_t s0 = min(pos, lane * chunk), s1 = min(pos, s0 + chunk);
+            unsigned long long a = 0ull, b = 0ull;
+            for (uint32_t i = s0; i < s1; ++i) {
+                const unsigned long long d = out[i];
+                a += d;
+                b += (unsigned long long)(s1 - i) * d;           // < 2^32 * 255 * 2^32 / ... : chunk < 2^27 keeps this far below 2^64
+            }
+            // total: A = 1 + sum a_l; B = pos + sum over lanes of (pos - s1) * a_l + b_l   (mod 65521)
+            unsigned long long A = a % 65521ull, Bv = (((unsigned long long)(pos - s1) % 65521ull) * (a % 65521ull) + b % 65521ull) % 65521ull;
+            for (int o = 16; o > 0; o >>= 1) {
+                A += __shfl_xor_sync(0xffffffffu, A, o);
+                Bv += __shfl_xor_sync(0xffffffffu, Bv, o);
+            }
+            A = (A + 1ull) % 65521ull;
+            Bv = (Bv + (unsigned long long)pos) % 65521ull;
+            if ((uint32_t)((Bv << 16) | A) != want) err = INF_BAD_CHECK;
+        }
+    }
+    if (!err && pos < cap) err = INF_SHORT;
+    if (!err && J.rows) {
+        __syncwarp();
+        int bad = 0;
+        for (uint32_t y = lane; y < J.rows; y += 32) bad |= out[(size_t)y * (J.row_bytes + 1u)] > 4;
+        if (__any_sync(0xffffffffu, bad)) err = INF_BAD_FILTER;
+    }
+    if (lane == 0) status[job] = err;
 }
 
 // ---- device: un-filter + convert --------------------------------------------------------------------------------
@@ -261,6 +590,12 @@ struct IngestSet {
     uint8_t *h_gam = nullptr, *d_gam = nullptr;   // [images][2][256] gamma_to_1 / gamma_from_1
     int cap_images = 0;
     cudaEvent_t done = nullptr;       // the set's last batch has left the staging buffers
+    // GPU inflate: the gathered zlib streams, one job per image, one status word per image
+    uint8_t *h_comp = nullptr, *d_comp = nullptr;
+    size_t comp_cap = 0;
+    InflateJob *h_jobs = nullptr, *d_jobs = nullptr;
+    int *h_status = nullptr, *d_status = nullptr;
+    int pending = 0;                  // images of the set's latest GPU-inflated batch whose status has not been looked at yet
 };
 struct IngestWs {
     IngestSet set[2];
@@ -278,6 +613,12 @@ static void ingest_set_free(IngestSet& w)
     if (w.h_gam) cudaFreeHost(w.h_gam);
     if (w.d_gam) cudaFree(w.d_gam);
     if (w.done) cudaEventDestroy(w.done);
+    if (w.h_comp) cudaFreeHost(w.h_comp);
+    if (w.d_comp) cudaFree(w.d_comp);
+    if (w.h_jobs) cudaFreeHost(w.h_jobs);
+    if (w.d_jobs) cudaFree(w.d_jobs);
+    if (w.h_status) cudaFreeHost(w.h_status);
+    if (w.d_status) cudaFree(w.d_status);
     w = IngestSet();
 }
 
@@ -291,10 +632,42 @@ void ingest_free(ssm_ctx* c)
     c->ingest_ws = nullptr;
 }
 
-static int ingest_reserve(IngestSet& w, int images, size_t per_image)
+static const char* inflate_error_text(int e)
+{
+    switch (e) {
+        case INF_SHORT: return "PNG data stream ends early";
+        case INF_BAD_FILTER: return "bad PNG scanline filter type";
+        default: return "corrupt PNG data stream";
+    }
+}
+
+// the status words of the set's latest GPU-inflated batch (call after its event has completed)
+static int ingest_check_status(IngestSet& w)
+{
+    const int n = w.pending;
+    w.pending = 0;
+    for (int i = 0; i < n; ++i)
+        if (w.h_status[i] != INF_OK) {
+            set_error(std::string("image ") + std::to_string(i) + " of an earlier batch: " + inflate_error_text(w.h_status[i]) + " (inflate status " +
+                      std::to_string(w.h_status[i]) + ")");
+            return SSM_ERR_INVALID_ARGUMENT;
+        }
+    return SSM_OK;
+}
+
+static int ingest_reserve(IngestSet& w, int images, size_t per_image, size_t comp_bytes = 0)
 {
     if (!w.done) SSM_CUDA(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
     SSM_CUDA(cudaEventSynchronize(w.done));   // (a never-recorded event is complete)
+    if (int rc = ingest_check_status(w)) return rc;
+    if (comp_bytes > w.comp_cap) {
+        if (w.h_comp) cudaFreeHost(w.h_comp);
+        if (w.d_comp) cudaFree(w.d_comp);
+        w.h_comp = nullptr; w.d_comp = nullptr; w.comp_cap = 0;
+        SSM_CUDA(cudaMallocHost(&w.h_comp, comp_bytes));
+        SSM_CUDA(cudaMalloc(&w.d_comp, comp_bytes));
+        w.comp_cap = comp_bytes;
+    }
     const size_t need = per_image * (size_t)images;
     if (need > w.staged_cap) {
         if (w.h_staged) cudaFreeHost(w.h_staged);
@@ -311,6 +684,11 @@ static int ingest_reserve(IngestSet& w, int images, size_t per_image)
         if (w.d_pal) cudaFree(w.d_pal);
         if (w.h_gam) cudaFreeHost(w.h_gam);
         if (w.d_gam) cudaFree(w.d_gam);
+        if (w.h_jobs) cudaFreeHost(w.h_jobs);
+        if (w.d_jobs) cudaFree(w.d_jobs);
+        if (w.h_status) cudaFreeHost(w.h_status);
+        if (w.d_status) cudaFree(w.d_status);
+        w.h_jobs = nullptr; w.d_jobs = nullptr; w.h_status = nullptr; w.d_status = nullptr;
         w.h_desc = nullptr; w.d_desc = nullptr; w.h_pal = nullptr; w.d_pal = nullptr; w.h_gam = nullptr; w.d_gam = nullptr; w.cap_images = 0;
         SSM_CUDA(cudaMallocHost(&w.h_desc, sizeof(PngDesc) * images));
         SSM_CUDA(cudaMalloc(&w.d_desc, sizeof(PngDesc) * images));
@@ -318,6 +696,10 @@ static int ingest_reserve(IngestSet& w, int images, size_t per_image)
         SSM_CUDA(cudaMalloc(&w.d_pal, (size_t)768 * images));
         SSM_CUDA(cudaMallocHost(&w.h_gam, (size_t)512 * images));
         SSM_CUDA(cudaMalloc(&w.d_gam, (size_t)512 * images));
+        SSM_CUDA(cudaMallocHost(&w.h_jobs, sizeof(InflateJob) * images));
+        SSM_CUDA(cudaMalloc(&w.d_jobs, sizeof(InflateJob) * images));
+        SSM_CUDA(cudaMallocHost(&w.h_status, sizeof(int) * images));
+        SSM_CUDA(cudaMalloc(&w.d_status, sizeof(int) * images));
         w.cap_images = images;
     }
     return SSM_OK;
@@ -348,19 +730,28 @@ int ssm_png_decode_batch_device(ssm_ctx* c, int batch, const uint8_t* const* png
     }
     SSM_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    static const bool force_host = [] { const char* e = getenv("SSM_HOST_INFLATE"); return e && e[0] == '1'; }();
+    const bool gpu_inflate = host_threads <= 0 && !force_host;
     const size_t per_image = (size_t)h * ((size_t)w * 4 + 1);          // worst case: RGBA
     if (!c->ingest_ws) c->ingest_ws = new IngestWs();
     IngestWs* all = static_cast<IngestWs*>(c->ingest_ws);
     IngestSet* ws = &all->set[all->calls++ & 1u];
-    int rc = ingest_reserve(*ws, batch, per_image);   // waits until the set's previous batch has left its buffers
+    // GPU inflate: the zlib streams (never longer than their files) sit back to back, 16-byte aligned, + one spare word each
+    std::vector<size_t> comp_off((size_t)batch + 1, 0);
+    if (gpu_inflate)
+        for (int i = 0; i < batch; ++i) comp_off[i + 1] = comp_off[i] + ((png_bytes[i] + 4 + 15) & ~(size_t)15);
+    int rc = ingest_reserve(*ws, batch, per_image, comp_off[batch]);   // waits until the set's previous batch has left its buffers
     if (rc) return rc;
-    // inflate: one image per task on host threads
+    // host: one image per task -- inflate (zlib), or chunk walk + CRC + IDAT gather for the GPU decoder
     std::atomic<int> next(0);
     std::vector<const char*> errs((size_t)batch, nullptr);
     auto worker = [&]() {
         for (int i = next.fetch_add(1); i < batch; i = next.fetch_add(1)) {
             PngInfo info;
-            const char* e = png_inflate(png[i], png_bytes[i], info, ws->h_staged + per_image * i, per_image, false);
+            size_t gathered = 0;
+            const char* e = gpu_inflate ? png_inflate(png[i], png_bytes[i], info, nullptr, per_image, false, ws->h_comp + comp_off[i],
+                                                      comp_off[i + 1] - comp_off[i] - 4, &gathered)
+                                        : png_inflate(png[i], png_bytes[i], info, ws->h_staged + per_image * i, per_image, false);
             if (!e && (info.w != w || info.h != h)) e = "PNG size differs from the batch's frame size";
             errs[i] = e;
             if (e) continue;
@@ -372,6 +763,14 @@ int ssm_png_decode_batch_device(ssm_ctx* c, int batch, const uint8_t* const* png
             const bool colour_file = info.colour_type == 2 || info.colour_type == 3 || info.colour_type == 6;
             d.gamma_index = (mode == 0 && colour_file && info.file_gamma) ? i : -1;
             if (d.gamma_index >= 0) png_gray_tables(info.file_gamma, ws->h_gam + (size_t)512 * i, ws->h_gam + (size_t)512 * i + 256);
+            if (gpu_inflate) {
+                memset(ws->h_comp + comp_off[i] + gathered, 0, comp_off[i + 1] - comp_off[i] - gathered);
+                InflateJob& j = ws->h_jobs[i];
+                j.in_off = comp_off[i]; j.out_off = per_image * i;
+                j.in_bytes = (uint32_t)gathered;
+                j.out_cap = (uint32_t)((size_t)h * ((size_t)w * info.bpp + 1));
+                j.rows = (uint32_t)h; j.row_bytes = (uint32_t)((size_t)w * info.bpp);
+            }
         }
     };
     const int nthreads = std::max(1, std::min(host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency(), batch));
@@ -386,7 +785,16 @@ int ssm_png_decode_batch_device(ssm_ctx* c, int batch, const uint8_t* const* png
         if (errs[i]) { set_error(std::string("image ") + std::to_string(i) + ": " + errs[i]); return SSM_ERR_INVALID_ARGUMENT; }
     int max_bpp = 1;
     for (int i = 0; i < batch; ++i) max_bpp = std::max(max_bpp, ws->h_desc[i].bpp);
-    SSM_CUDA(cudaMemcpyAsync(ws->d_staged, ws->h_staged, per_image * batch, cudaMemcpyHostToDevice, s));
+    if (gpu_inflate) {
+        SSM_CUDA(cudaMemcpyAsync(ws->d_comp, ws->h_comp, comp_off[batch], cudaMemcpyHostToDevice, s));
+        SSM_CUDA(cudaMemcpyAsync(ws->d_jobs, ws->h_jobs, sizeof(InflateJob) * batch, cudaMemcpyHostToDevice, s));
+        k_inflate<<<(batch + 7) / 8, 256, 0, s>>>(ws->d_comp, ws->d_jobs, batch, ws->d_staged, ws->d_status);
+        SSM_LAUNCH_CHECK(c);
+        SSM_CUDA(cudaMemcpyAsync(ws->h_status, ws->d_status, sizeof(int) * batch, cudaMemcpyDeviceToHost, s));
+        ws->pending = batch;
+    } else {
+        SSM_CUDA(cudaMemcpyAsync(ws->d_staged, ws->h_staged, per_image * batch, cudaMemcpyHostToDevice, s));
+    }
     SSM_CUDA(cudaMemcpyAsync(ws->d_desc, ws->h_desc, sizeof(PngDesc) * batch, cudaMemcpyHostToDevice, s));
     SSM_CUDA(cudaMemcpyAsync(ws->d_pal, ws->h_pal, (size_t)768 * batch, cudaMemcpyHostToDevice, s));
     SSM_CUDA(cudaMemcpyAsync(ws->d_gam, ws->h_gam, (size_t)512 * batch, cudaMemcpyHostToDevice, s));
@@ -401,6 +809,64 @@ int ssm_png_decode_batch_device(ssm_ctx* c, int batch, const uint8_t* const* png
     }
     SSM_LAUNCH_CHECK(c);
     SSM_CUDA(cudaEventRecord(ws->done, s));
+    return SSM_OK;
+}
+
+int ssm_png_batch_wait(ssm_ctx* c)
+{
+    if (!c) { set_error("null context"); return SSM_ERR_INVALID_ARGUMENT; }
+    SSM_CUDA(cudaSetDevice(c->device));
+    IngestWs* all = static_cast<IngestWs*>(c->ingest_ws);
+    if (!all) return SSM_OK;
+    int rc = SSM_OK;
+    for (unsigned k = 0; k < 2; ++k) {           // oldest first
+        IngestSet& w = all->set[(all->calls + k) & 1u];
+        if (!w.done) continue;
+        SSM_CUDA(cudaEventSynchronize(w.done));
+        const int r = ingest_check_status(w);
+        if (rc == SSM_OK) rc = r;
+    }
+    return rc;
+}
+
+int ssm_zlib_inflate_batch(ssm_ctx* c, int n, const uint8_t* const* streams, const size_t* stream_bytes, uint8_t* const* out,
+                           const size_t* out_bytes, int* status)
+{
+    if (!c || n < 1 || !streams || !stream_bytes || !out || !out_bytes || !status) { set_error("bad argument"); return SSM_ERR_INVALID_ARGUMENT; }
+    SSM_CUDA(cudaSetDevice(c->device));
+    std::vector<InflateJob> jobs((size_t)n);
+    size_t in_total = 0, out_total = 0;
+    for (int i = 0; i < n; ++i) {
+        if (stream_bytes[i] > 0xfffffff0ull || out_bytes[i] > 0xfffffff0ull) { set_error("stream too large"); return SSM_ERR_INVALID_ARGUMENT; }
+        jobs[i].in_off = in_total; jobs[i].out_off = out_total;
+        jobs[i].in_bytes = (uint32_t)stream_bytes[i]; jobs[i].out_cap = (uint32_t)out_bytes[i];
+        jobs[i].rows = 0; jobs[i].row_bytes = 0;
+        in_total += (stream_bytes[i] + 4 + 15) & ~(size_t)15;
+        out_total += (out_bytes[i] + 15) & ~(size_t)15;
+    }
+    std::vector<uint8_t> in_host(in_total, 0);
+    for (int i = 0; i < n; ++i) memcpy(in_host.data() + jobs[i].in_off, streams[i], stream_bytes[i]);
+    uint8_t *d_in = nullptr, *d_o = nullptr;
+    InflateJob* d_jobs = nullptr;
+    int* d_status = nullptr;
+    cudaError_t e = cudaMalloc(&d_in, in_total);
+    if (e == cudaSuccess) e = cudaMalloc(&d_o, std::max<size_t>(out_total, 16));
+    if (e == cudaSuccess) e = cudaMalloc(&d_jobs, sizeof(InflateJob) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_status, sizeof(int) * n);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_o, 0, std::max<size_t>(out_total, 16), c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, in_host.data(), in_total, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(InflateJob) * n, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        k_inflate<<<(n + 7) / 8, 256, 0, c->stream>>>(d_in, d_jobs, n, d_o, d_status);
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream);
+    for (int i = 0; i < n && e == cudaSuccess; ++i)
+        if (out_bytes[i]) e = cudaMemcpyAsync(out[i], d_o + jobs[i].out_off, out_bytes[i], cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_in); cudaFree(d_o); cudaFree(d_jobs); cudaFree(d_status);
+    if (e != cudaSuccess) return cuda_fail(e, "ssm_zlib_inflate_batch");
     return SSM_OK;
 }
 

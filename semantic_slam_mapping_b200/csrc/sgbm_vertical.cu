@@ -361,6 +361,8 @@ static int launch_vertical_plan(ssm_ctx* c, int B, const VerticalPlan& plan, cud
             return full ? launch_vertical_t<4, 16, true, 16>(c, B, plan, s, done) : launch_vertical_t<4, 16, false, 16>(c, B, plan, s, done);
         }
         if (D == 128 && full && c->tune[2] == 2) return launch_vertical_t<4, 24, true, 16>(c, B, plan, s, done);
+        if (D == 128 && full && c->tune[2] == 4) return launch_vertical_t<4, 18, true, 16>(c, B, plan, s, done);
+        if (D == 128 && full && c->tune[2] == 5) return launch_vertical_t<4, 20, true, 16>(c, B, plan, s, done);
         if (full && c->tune[2] == 1) return launch_vertical_t<2, 24, true>(c, B, plan, s, done);
         return full ? launch_vertical_t<2, 32, true>(c, B, plan, s, done) : launch_vertical_t<2, 32, false>(c, B, plan, s, done);
     }

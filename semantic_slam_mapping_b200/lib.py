@@ -27,7 +27,7 @@ SYMBOLS = [
     "ssm_map_integrate_keyframes",
     "ssm_labels_from_indices", "ssm_labels_from_indices_batch_device",
     "ssm_motion_cues_stage1_device", "ssm_motion_cues_stage2_device", "ssm_motion_cues_overflow",
-    "ssm_png_info", "ssm_png_decode_batch_device", "ssm_png_decode",
+    "ssm_png_info", "ssm_png_decode_batch_device", "ssm_png_decode", "ssm_png_batch_wait", "ssm_zlib_inflate_batch",
     "ssm_map_export_device_ms", "ssm_map_export_gathered", "ssm_map_reserve", "ssm_map_stats",
 ]
 
@@ -75,6 +75,8 @@ def load() -> C.CDLL:
     L.ssm_png_info.argtypes = [vp, sz, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     L.ssm_png_decode_batch_device.argtypes = [vp, i, C.POINTER(vp), C.POINTER(sz), i, i, i, vp, i, vp]
     L.ssm_png_decode.argtypes = [vp, vp, sz, i, vp, sz, C.POINTER(i), C.POINTER(i)]
+    L.ssm_png_batch_wait.argtypes = [vp]
+    L.ssm_zlib_inflate_batch.argtypes = [vp, i, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz), C.POINTER(i)]
     L.ssm_sgbm_batch_device.argtypes = [vp, i, vp, vp, i, i, vp, vp]
     L.ssm_debug_copy_volume.argtypes = [vp, i, i, vp, sz]
     L.ssm_disparity_to_depth.argtypes = [vp, vp, i, i, sz, vp, sz]
@@ -356,6 +358,23 @@ class Context:
         sizes = (C.c_size_t * n)(*[b.size for b in bufs])
         self._check(self._L.ssm_png_decode_batch_device(self._h, n, ptrs, sizes, w, h, 1 if colour else 0, _ptr(d_out), host_threads,
                                                         C.c_void_p(stream) if stream else None))
+
+    def png_batch_wait(self):
+        """Blocks until the queued ingest batches have run; raises on a corrupt stream of a GPU-inflated batch."""
+        self._check(self._L.ssm_png_batch_wait(self._h))
+
+    def zlib_inflate_batch(self, streams, out_sizes):
+        """The GPU DEFLATE decoder on its own: list of zlib streams (bytes) -> (list of uint8 arrays, status array)."""
+        bufs = [np.frombuffer(s, np.uint8) if len(s) else np.zeros(0, np.uint8) for s in streams]
+        n = len(bufs)
+        outs = [np.zeros(int(m), np.uint8) for m in out_sizes]
+        status = np.zeros(n, np.int32)
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = (C.c_size_t * n)(*[b.size for b in bufs])
+        optrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        osizes = (C.c_size_t * n)(*[o.size for o in outs])
+        self._check(self._L.ssm_zlib_inflate_batch(self._h, n, ptrs, sizes, optrs, osizes, status.ctypes.data_as(C.POINTER(C.c_int))))
+        return outs, status
 
     # -- label production (experiment/segnet.cpp:121-135) ---------------------------------------------------------------
     def labels_from_indices(self, index_img, dw: int, dh: int, lut_bgr, want_raw: bool = True):
