@@ -238,7 +238,7 @@ int ssm_labels_from_indices_batch_device(ssm_ctx* ctx, int batch, const uint8_t*
  * grey + alpha, RGB, RGBA or palette).  Bit-exact with cv2 4.13.  The host returns when the batch is queued.  Container
  * errors (signature, chunk CRC, size, colour type) are returned by the call itself; with the GPU decoder a corrupt or short
  * zlib stream or a scanline filter type above 4 is only known when the batch has run: it is returned by ssm_png_batch_wait,
- * or by the next-but-one ssm_png_decode_batch_device call (the one that re-uses the batch's staging buffers). */
+ * or by the fourth ssm_png_decode_batch_device call after it (the one that re-uses the batch's staging buffers). */
 int ssm_png_info(const uint8_t* png, size_t png_bytes, int* w, int* h, int* channels /* 1 or 3, may be NULL */);
 int ssm_png_decode_batch_device(ssm_ctx* ctx, int batch, const uint8_t* const* png, const size_t* png_bytes, int w, int h,
                                 int mode, uint8_t* d_out, int host_threads, void* stream);

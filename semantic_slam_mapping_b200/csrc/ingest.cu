@@ -185,16 +185,23 @@ __constant__ uint8_t c_clorder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 1
 
 struct BitReader {
     const uint32_t* w;
-    uint32_t nwords, wi;
+    uint32_t nwords, wi;                         // wi: index of the next word to enter the bit buffer
+    uint32_t ahead;                              // word wi, loaded when word wi - 1 entered: its latency hides behind 32 bits of decoding
     unsigned long long buf;
     int cnt;
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return i < nwords ? __ldg(w + i) : 0u; }   // past the end: zeros (the caller checks consumed_bits())
+    __device__ __forceinline__ void start(uint32_t first_word)
+    {
+        wi = first_word; buf = 0ull; cnt = 0;
+        ahead = word(wi);
+    }
     __device__ __forceinline__ void refill()
     {
         if (cnt <= 32) {
-            const uint32_t v = wi < nwords ? __ldg(w + wi) : 0u;   // past the end: zeros (the caller checks consumed() against the size)
-            ++wi;
-            buf |= (unsigned long long)v << cnt;
+            buf |= (unsigned long long)ahead << cnt;
             cnt += 32;
+            ++wi;
+            ahead = word(wi);
         }
     }
     __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1u); }
@@ -204,7 +211,7 @@ struct BitReader {
 };
 
 // Builds the first-level table and the canonical lists for `n` code lengths.  Returns 0, or an INF_ error.  Warp-collective.
-__device__ int build_table(const uint8_t* lens, int n, uint16_t* lut, int bits, uint16_t* sym, uint16_t* cnt, uint16_t* code, int lane)
+__device__ __noinline__ int build_table(const uint8_t* lens, int n, uint16_t* lut, int bits, uint16_t* sym, uint16_t* cnt, uint16_t* code, int lane)
 {
     int err = 0;
     if (lane == 0) {
@@ -260,12 +267,13 @@ __device__ __forceinline__ int decode_slow(BitReader& br, const uint16_t* cnt, c
     return -1;
 }
 
-__global__ void __launch_bounds__(256) k_inflate(const uint8_t* __restrict__ in_base, const InflateJob* __restrict__ jobs, int njobs,
+constexpr int kInflateWarps = 2;   // streams per CTA: few, so that a batch of some hundred streams spreads over all SMs
+__global__ void __launch_bounds__(32 * kInflateWarps) k_inflate(const uint8_t* __restrict__ in_base, const InflateJob* __restrict__ jobs, int njobs,
                                                  uint8_t* out_base, int* __restrict__ status)
 {
-    __shared__ InflateTabs tabs_all[8];
+    __shared__ InflateTabs tabs_all[kInflateWarps];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int job = blockIdx.x * 8 + wib;
+    const int job = blockIdx.x * kInflateWarps + wib;
     if (job >= njobs) return;
     InflateTabs& T = tabs_all[wib];
     const InflateJob J = jobs[job];
@@ -274,7 +282,7 @@ __global__ void __launch_bounds__(256) k_inflate(const uint8_t* __restrict__ in_
     BitReader br;
     br.w = reinterpret_cast<const uint32_t*>(in_base + J.in_off);
     br.nwords = (J.in_bytes + 3u) >> 2;
-    br.wi = 0; br.buf = 0ull; br.cnt = 0;
+    br.start(0u);
     uint32_t pos = 0;
     int err = 0;
     bool full = false;                               // the output window is full: the rest of the stream is ignored
@@ -307,7 +315,7 @@ __global__ void __launch_bounds__(256) k_inflate(const uint8_t* __restrict__ in_
             if (n < len) { full = true; break; }
             // restart the bit reader behind the stored bytes
             const unsigned long long nb = byte0 + len;
-            br.wi = (uint32_t)(nb >> 2); br.buf = 0ull; br.cnt = 0;
+            br.start((uint32_t)(nb >> 2));
             br.refill();
             br.drop((int)(nb & 3ull) * 8);
             continue;
@@ -381,15 +389,39 @@ __global__ void __launch_bounds__(256) k_inflate(const uint8_t* __restrict__ in_
             if ((err = build_table(T.lens, nlen, T.llut, kLB, T.lsym, T.lcnt, T.code, lane))) break;
             tables = 2;
         }
-        // ---- symbols of the block
+        // ---- symbols of the block.  Literals dominate photo-like PNG data, and every symbol is a chain of dependent steps (table
+        // look-up -> code length -> shift -> next look-up), so the literal path is kept to that chain: up to three first-level
+        // literals (3 x 10 bits) per refill, each one = store, shift, next look-up; everything else takes the general path.
         for (;;) {
             br.refill();
-            int s;
-            {
-                const uint16_t e = T.llut[br.peek(kLB)];
-                if (e) { br.drop(e & 15); s = e >> 4; }
-                else if ((s = decode_slow(br, T.lcnt, T.lsym)) < 0) { err = INF_BAD_SYMBOL; break; }
+            uint32_t e = T.llut[(uint32_t)br.buf & ((1u << kLB) - 1u)];
+            // entry = (symbol << 4) | length: a first-level literal is 0 < e < 0x1000.  The look-up behind the current code is
+            // issued before the literal test (it only assumes a first-level code; a wrong guess is simply not used), so the
+            // branch resolves under the shared-memory latency instead of in front of it.
+#define SSM_INFLATE_LITERAL()                                                      \
+            {                                                                              \
+                const unsigned long long nbuf = br.buf >> (e & 15u);                       \
+                const uint32_t e2 = T.llut[(uint32_t)nbuf & ((1u << kLB) - 1u)];           \
+                if (e - 1u < 0x0fffu && pos < cap) {                                       \
+                    if (lane == 0) out[pos] = (uint8_t)(e >> 4);                           \
+                    ++pos;                                                                 \
+                    br.buf = nbuf; br.cnt -= (int)(e & 15u);                               \
+                    e = e2;
+            SSM_INFLATE_LITERAL()
+                    SSM_INFLATE_LITERAL()
+                            SSM_INFLATE_LITERAL()
+                                    continue;        // three literals: refill
+                                }
+                            }
+                        }
+                    }
+                    br.refill();                     // (the low bits, hence e, stay as they are)
+                }
             }
+#undef SSM_INFLATE_LITERAL
+            int s;
+            if (e) { br.drop((int)(e & 15u)); s = (int)(e >> 4); }
+            else if ((s = decode_slow(br, T.lcnt, T.lsym)) < 0) { err = INF_BAD_SYMBOL; break; }
             if (s < 256) {
                 if (pos >= cap) { full = true; break; }
                 if (lane == 0) out[pos] = (uint8_t)s;
@@ -417,8 +449,7 @@ __global__ void __launch_bounds__(256) k_inflate(const uint8_t* __restrict__ in_
                 const uint8_t* from = out + pos - dist;
                 for (uint32_t i = lane; i < n; i += 32) out[pos + i] = from[dist >= n ? i : i % dist];
             }
-            __syncwarp();
-            pos += n;
+            pos += n;                                // (no fence here: the one in front of the next copy orders these stores before its loads)
             if (n < length) { full = true; break; }
         }
         if (!err && br.consumed_bits() > (unsigned long long)J.in_bytes * 8ull) err = INF_TRUNCATED;
@@ -580,7 +611,7 @@ __global__ void __launch_bounds__(128) k_png_unfilter(const uint8_t* __restrict_
     }
 }
 
-// Two staging sets alternate between calls, so the host inflates call n + 1 while the GPU still copies and un-filters call n.
+// A ring of staging sets: the host prepares call n + 1 (and n + 2, n + 3) while the GPU still decodes call n.
 struct IngestSet {
     uint8_t* h_staged = nullptr;      // pinned: filtered scanlines of a batch
     uint8_t* d_staged = nullptr;
@@ -597,8 +628,9 @@ struct IngestSet {
     int *h_status = nullptr, *d_status = nullptr;
     int pending = 0;                  // images of the set's latest GPU-inflated batch whose status has not been looked at yet
 };
+constexpr unsigned kIngestSets = 4;   // batches in flight (e.g. the four images of a frame batch on four streams)
 struct IngestWs {
-    IngestSet set[2];
+    IngestSet set[kIngestSets];
     unsigned calls = 0;
 };
 
@@ -626,8 +658,7 @@ void ingest_free(ssm_ctx* c)
 {
     IngestWs* w = static_cast<IngestWs*>(c->ingest_ws);
     if (!w) return;
-    ingest_set_free(w->set[0]);
-    ingest_set_free(w->set[1]);
+    for (auto& st : w->set) ingest_set_free(st);
     delete w;
     c->ingest_ws = nullptr;
 }
@@ -657,6 +688,7 @@ static int ingest_check_status(IngestSet& w)
 
 static int ingest_reserve(IngestSet& w, int images, size_t per_image, size_t comp_bytes = 0)
 {
+    const bool host_staging = comp_bytes == 0;   // the GPU decoder writes the scanlines in device memory: no pinned copy of them
     if (!w.done) SSM_CUDA(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
     SSM_CUDA(cudaEventSynchronize(w.done));   // (a never-recorded event is complete)
     if (int rc = ingest_check_status(w)) return rc;
@@ -669,11 +701,11 @@ static int ingest_reserve(IngestSet& w, int images, size_t per_image, size_t com
         w.comp_cap = comp_bytes;
     }
     const size_t need = per_image * (size_t)images;
-    if (need > w.staged_cap) {
+    if (need > w.staged_cap || (host_staging && !w.h_staged)) {
         if (w.h_staged) cudaFreeHost(w.h_staged);
         if (w.d_staged) cudaFree(w.d_staged);
         w.h_staged = nullptr; w.d_staged = nullptr; w.staged_cap = 0;
-        SSM_CUDA(cudaMallocHost(&w.h_staged, need));
+        if (host_staging) SSM_CUDA(cudaMallocHost(&w.h_staged, need));
         SSM_CUDA(cudaMalloc(&w.d_staged, need));
         w.staged_cap = need;
     }
@@ -735,7 +767,7 @@ int ssm_png_decode_batch_device(ssm_ctx* c, int batch, const uint8_t* const* png
     const size_t per_image = (size_t)h * ((size_t)w * 4 + 1);          // worst case: RGBA
     if (!c->ingest_ws) c->ingest_ws = new IngestWs();
     IngestWs* all = static_cast<IngestWs*>(c->ingest_ws);
-    IngestSet* ws = &all->set[all->calls++ & 1u];
+    IngestSet* ws = &all->set[all->calls++ % kIngestSets];
     // GPU inflate: the zlib streams (never longer than their files) sit back to back, 16-byte aligned, + one spare word each
     std::vector<size_t> comp_off((size_t)batch + 1, 0);
     if (gpu_inflate)
@@ -788,7 +820,7 @@ int ssm_png_decode_batch_device(ssm_ctx* c, int batch, const uint8_t* const* png
     if (gpu_inflate) {
         SSM_CUDA(cudaMemcpyAsync(ws->d_comp, ws->h_comp, comp_off[batch], cudaMemcpyHostToDevice, s));
         SSM_CUDA(cudaMemcpyAsync(ws->d_jobs, ws->h_jobs, sizeof(InflateJob) * batch, cudaMemcpyHostToDevice, s));
-        k_inflate<<<(batch + 7) / 8, 256, 0, s>>>(ws->d_comp, ws->d_jobs, batch, ws->d_staged, ws->d_status);
+        k_inflate<<<(batch + kInflateWarps - 1) / kInflateWarps, 32 * kInflateWarps, 0, s>>>(ws->d_comp, ws->d_jobs, batch, ws->d_staged, ws->d_status);
         SSM_LAUNCH_CHECK(c);
         SSM_CUDA(cudaMemcpyAsync(ws->h_status, ws->d_status, sizeof(int) * batch, cudaMemcpyDeviceToHost, s));
         ws->pending = batch;
@@ -819,8 +851,8 @@ int ssm_png_batch_wait(ssm_ctx* c)
     IngestWs* all = static_cast<IngestWs*>(c->ingest_ws);
     if (!all) return SSM_OK;
     int rc = SSM_OK;
-    for (unsigned k = 0; k < 2; ++k) {           // oldest first
-        IngestSet& w = all->set[(all->calls + k) & 1u];
+    for (unsigned k = 0; k < kIngestSets; ++k) {           // oldest first
+        IngestSet& w = all->set[(all->calls + k) % kIngestSets];
         if (!w.done) continue;
         SSM_CUDA(cudaEventSynchronize(w.done));
         const int r = ingest_check_status(w);
@@ -857,7 +889,7 @@ int ssm_zlib_inflate_batch(ssm_ctx* c, int n, const uint8_t* const* streams, con
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, in_host.data(), in_total, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(InflateJob) * n, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) {
-        k_inflate<<<(n + 7) / 8, 256, 0, c->stream>>>(d_in, d_jobs, n, d_o, d_status);
+        k_inflate<<<(n + kInflateWarps - 1) / kInflateWarps, 32 * kInflateWarps, 0, c->stream>>>(d_in, d_jobs, n, d_o, d_status);
         c->launches++;
         e = cudaGetLastError();
     }
