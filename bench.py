@@ -559,7 +559,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int, pool, cores: int
     ab = algorithmic_bytes(cfg, pts)
     kernels = {"cost": "k_prefilter8 + k_cost_fused", "vertical": "k_vertical3 (cluster kernel)", "horizontal": "k_hfwd + k_hrev",
                "select": "k_select_fused (records -> L-R check -> median -> band-local speckle components)", "post": "k_cc_merge_bands + k_cc_count_roots + k_cc_apply_bands", "points": "k_depth + k_labels + k_moving_mask",
-               "fuse": "k_points_fuse" if world == 1 else "k_points_p2p + barrier + k_fuse_list"}
+               "fuse": "k_points_fuse" if world == 1 else "k_points_p2p + k_flag_barrier + k_fuse_list"}
     dom = max(stage, key=stage.get)
     achieved = ab[dom] * B / (stage[dom] * 1e-3) / 1e9
     stage_roof = {k: {"ms_per_step": round(v, 4), "alg_GBps": round(ab[k] * B / (v * 1e-3) / 1e9, 1) if v > 0 else None,
@@ -593,7 +593,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int, pool, cores: int
                    "map_rank0": {"slots": stats["slots"], "load_factor": round(stats["load_factor"], 4), "mean_probe": round(stats["mean_probe"], 3),
                                  "max_probe": stats["max_probe"], "grow_steps": stats["grow_steps"], "table_GB": round(stats["table_bytes"] / 1e9, 2)},
                    "parallelism": (f"frames sharded over {world} GPU(s); voxel hash spatially owned; points routed to the owner by "
-                                   + ("NCCL send/recv all-to-all" if args.no_p2p else "peer-memory stores over NVLink fused into the point kernel + NCCL barrier"))
+                                   + ("NCCL send/recv all-to-all" if args.no_p2p else "peer-memory stores over NVLink fused into the point kernel + arrival flags in the peers' inbox headers (no collective)"))
                    if world > 1 else "1 GPU"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(round(frames_per_rank_step * (2 * W * H + 6 * W * H + 128))), "d2h_bytes_per_step": 4,
                 "api": "ssm_pipeline_batch_host_async (pinned host buffers, double-buffered staging) + ssm_synchronize"},

@@ -422,6 +422,7 @@ static int check_overflow(ssm_ctx* c, cudaStream_t s, uint64_t* n_voxels)
         return fail(SSM_ERR_CAPACITY, c->auto_grow ? "voxel hash table and its spill list are full (raise ssm_params.map_capacity)"
                                                    : "voxel hash table is full and cannot grow (device memory, or SSM_NO_GROW)");
     if (h[2] & 2u) return fail(SSM_ERR_CAPACITY, "point outside the 21-bit voxel coordinate range");
+    if (h[2] & 4u) return fail(SSM_ERR_COMM, "a peer rank did not reach the exchange step within the time-out (its points are missing from the map)");
     if (n_voxels) *n_voxels = h[1];
     return SSM_OK;
 }

@@ -256,7 +256,10 @@ int points_route_p2p(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t* 
     c->p2p_step++;
     int rc = launch_points_p2p(c, B, d_depth, d_sem, d_rgb, d_pose, c->d_peer_base, parity, s);
     if (rc) return rc;
-    if ((rc = comm_barrier(c, s))) return rc;   // every peer's stores for this step have landed
+    // every peer's stores for this step have landed: arrival flags in the peers' inbox headers (SSM_NCCL_BARRIER=1: the
+    // one-word ncclAllReduce of round 1)
+    static const bool nccl_barrier = [] { const char* e = getenv("SSM_NCCL_BARRIER"); return e && e[0] == '1'; }();
+    if ((rc = nccl_barrier ? comm_barrier(c, s) : launch_flag_barrier(c, (uint32_t)c->p2p_step, s))) return rc;
     return launch_fuse_inbox(c, parity, s);
 }
 
@@ -312,10 +315,10 @@ int ssm_comm_ipc_export(ssm_ctx* c, uint8_t handle[SSM_IPC_HANDLE_BYTES])
         // worst case every peer's whole batch is owned by this rank; sized for twice a local batch per parity,
         // overflow is reported (SSM_ERR_CAPACITY) rather than silently dropped
         c->inbox_cap = 2 * (size_t)c->cap_w * c->cap_h * c->cap_b;
-        const size_t bytes = kInboxHeader + 2 * c->inbox_cap * sizeof(Point);
+        const size_t bytes = kInboxHeader + 2 * c->inbox_cap * 16;   // 16-byte records (mapper.cu: k_points_p2p)
         SSM_CUDA(cudaMalloc(&c->ipc_base, bytes));
-        SSM_CUDA(cudaMemset(c->ipc_base, 0, kInboxHeader));
     }
+    SSM_CUDA(cudaMemset(c->ipc_base, 0, kInboxHeader));   // counts, overflow flag and the arrival flags (the step counter restarts at connect)
     cudaIpcMemHandle_t h;
     SSM_CUDA(cudaIpcGetMemHandle(&h, c->ipc_base));
     memset(handle, 0, SSM_IPC_HANDLE_BYTES);

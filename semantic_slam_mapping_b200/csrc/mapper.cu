@@ -473,8 +473,9 @@ __global__ void __launch_bounds__(256) k_points_p2p(const uint16_t* __restrict__
             char* base = static_cast<char*>(peer_base[owner[k]]);
             const uint32_t slot = s_base[owner[k]] + pos[k];
             if (slot < inbox_cap) {
-                Point* dst = reinterpret_cast<Point*>(base + kInboxHeader) + (size_t)parity * inbox_cap + slot;
-                *dst = pt[k];
+                // 16-byte inbox records (the label rides in the free top byte of 0x00RRGGBB): one aligned 128-bit store over NVLink per point
+                uint4* dst = reinterpret_cast<uint4*>(base + kInboxHeader) + (size_t)parity * inbox_cap + slot;
+                *dst = make_uint4(__float_as_uint(pt[k].x), __float_as_uint(pt[k].y), __float_as_uint(pt[k].z), pt[k].rgba | (pt[k].label << 24));
             } else {
                 atomicOr_system(reinterpret_cast<uint32_t*>(base) + 2, 1u);
             }
@@ -484,6 +485,30 @@ __global__ void __launch_bounds__(256) k_points_p2p(const uint16_t* __restrict__
     for (int k = 0; k < kPixPerThread; ++k) fuse_point_warp(p, tr, pt[k], owner[k] == rank);
     made = __reduce_add_sync(0xffffffffu, made);
     if (lane == 0 && made) atomicAdd(&tr.counters[0], made);
+}
+
+// Step barrier of the peer-memory exchange without a collective: thread t tells rank t "my points of step `step` are in your
+// inbox" (a store into t's header over NVLink, behind a system-scope fence; the point stores themselves were issued by the
+// previous kernel on this stream) and then waits until rank t has said the same here.  One small CTA, no NCCL launch; a peer
+// that never arrives (a rank that died or lost step) trips the time-out and raises a sticky flag instead of hanging the GPU.
+__global__ void __launch_bounds__(64) k_flag_barrier(void* const* __restrict__ peer_base, int rank, int nranks, uint32_t step,
+                                                     uint32_t* __restrict__ counters, long long timeout_cycles)
+{
+    const int t = threadIdx.x;
+    if (t >= nranks) return;
+    __threadfence_system();
+    volatile uint32_t* theirs = reinterpret_cast<volatile uint32_t*>(static_cast<char*>(peer_base[t]) + kInboxFlags) + rank;
+    *theirs = step;
+    volatile uint32_t* mine = reinterpret_cast<volatile uint32_t*>(static_cast<char*>(peer_base[rank]) + kInboxFlags) + t;
+    const long long t0 = clock64();
+    while ((int32_t)(*mine - step) < 0) {
+        if (clock64() - t0 > timeout_cycles) {
+            atomicOr(&counters[2], 4u);
+            break;
+        }
+        __nanosleep(100);
+    }
+    __threadfence_system();
 }
 
 // COMPACT mode (ordered, row-major like the reference's push_back loop): count per block, scan, scatter
@@ -567,7 +592,8 @@ __global__ void __launch_bounds__(kCompactBlock) k_points_scatter(const uint16_t
 }
 
 // fuse an explicit list of points (host-provided clouds, or points received from other ranks)
-__global__ void __launch_bounds__(256) k_fuse_list(const Point* __restrict__ pts, const uint32_t* __restrict__ count,
+template <bool PACKED /* 16-byte inbox records instead of 20-byte points */>
+__global__ void __launch_bounds__(256) k_fuse_list(const void* __restrict__ pts_, const uint32_t* __restrict__ count,
                                                    uint32_t max_count, TableRef tr, SSM_DP)
 {
     const uint32_t n = count ? min(*count, max_count) : max_count;
@@ -582,7 +608,15 @@ __global__ void __launch_bounds__(256) k_fuse_list(const Point* __restrict__ pts
             const uint64_t i = base + k * 32 + lane;
             ok[k] = i < n;
             pt[k] = Point{};
-            if (ok[k]) pt[k] = pts[i];
+            if (ok[k]) {
+                if constexpr (PACKED) {
+                    const uint4 q = static_cast<const uint4*>(pts_)[i];
+                    pt[k].x = __uint_as_float(q.x); pt[k].y = __uint_as_float(q.y); pt[k].z = __uint_as_float(q.z);
+                    pt[k].rgba = q.w & 0x00ffffffu; pt[k].label = q.w >> 24;
+                } else {
+                    pt[k] = static_cast<const Point*>(pts_)[i];
+                }
+            }
         }
 #pragma unroll
         for (int k = 0; k < kPixPerThread; ++k)
@@ -709,12 +743,19 @@ int launch_points_p2p(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t*
     return SSM_OK;
 }
 
+int launch_flag_barrier(ssm_ctx* c, uint32_t step, cudaStream_t s)
+{
+    k_flag_barrier<<<1, 64, 0, s>>>(c->d_peer_base, c->rank, c->nranks, step, c->d_counters, 20000000000ll /* ~10 s */);
+    SSM_LAUNCH_CHECK(c);
+    return SSM_OK;
+}
+
 int launch_fuse_inbox(ssm_ctx* c, int parity, cudaStream_t s)
 {
     char* base = static_cast<char*>(c->ipc_base);
-    const Point* pts = reinterpret_cast<const Point*>(base + kInboxHeader) + (size_t)parity * c->inbox_cap;
+    const uint4* pts = reinterpret_cast<const uint4*>(base + kInboxHeader) + (size_t)parity * c->inbox_cap;
     uint32_t* count = reinterpret_cast<uint32_t*>(base) + parity;
-    k_fuse_list<<<c->sm_count * 16, 256, 0, s>>>(pts, count, (uint32_t)c->inbox_cap, table_ref(c), c->dp);
+    k_fuse_list<true><<<c->sm_count * 16, 256, 0, s>>>(pts, count, (uint32_t)c->inbox_cap, table_ref(c), c->dp);
     SSM_LAUNCH_CHECK(c);
     SSM_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), s));   // ready for the step after next
     return SSM_OK;
@@ -724,7 +765,7 @@ int launch_fuse_points(ssm_ctx* c, const Point* d_pts, const uint32_t* d_count, 
 {
     if (max_count == 0) return SSM_OK;
     const unsigned grid = (unsigned)std::min<size_t>(((size_t)max_count + 255) / 256, (size_t)c->sm_count * 16);
-    k_fuse_list<<<grid, 256, 0, s>>>(d_pts, d_count, max_count, table_ref(c), c->dp);
+    k_fuse_list<false><<<grid, 256, 0, s>>>(d_pts, d_count, max_count, table_ref(c), c->dp);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }

@@ -78,8 +78,10 @@ struct DevParams {
     int dilate_radius, colour_source;
 };
 
-// inbox layout: [256-byte header: u32 count[2] (per parity), u32 overflow][parity 0 points][parity 1 points]
-constexpr size_t kInboxHeader = 256;
+// inbox layout: [512-byte header: u32 count[2] (per parity), u32 overflow; at byte 256: u32 arrived[64], one word per source rank
+// = the last step whose points that rank has stored here][parity 0 points][parity 1 points]
+constexpr size_t kInboxHeader = 512;
+constexpr size_t kInboxFlags = 256;
 
 struct Point {                              // routed between ranks, 20 bytes
     float x, y, z;
@@ -281,6 +283,7 @@ int launch_points_p2p(ssm_ctx* c, int B, const uint16_t* d_depth, const uint8_t*
                       void* const* d_peer_base, int parity, cudaStream_t s);
 int launch_fuse_inbox(ssm_ctx* c, int parity, cudaStream_t s);
 int comm_barrier(ssm_ctx* c, cudaStream_t s);
+int launch_flag_barrier(ssm_ctx* c, uint32_t step, cudaStream_t s);   // mapper.cu: peer-memory arrival flags instead of a collective
 int comm_allreduce_max(ssm_ctx* c, uint32_t* value, cudaStream_t s);   // blocking: *value = max over the ranks
 
 // packed 16x2 helpers --------------------------------------------------------------------------
