@@ -7,7 +7,7 @@ import json
 import subprocess
 import sys
 
-STAGE_OF = {"k_prefilter8": "cost", "k_cost_fused": "cost", "k_vertical3": "vertical", "k_hfwd": "horizontal", "k_hrev": "horizontal",
+STAGE_OF = {"k_prefilter8": "cost", "k_cost_fused": "cost", "k_prefilter_tab": "cost", "k_cost_tma": "cost", "k_vertical3": "vertical", "k_hfwd": "horizontal", "k_hrev": "horizontal",
             "k_points_fuse": "fuse", "k_select_fused": "select", "k_cc_apply_bands": "post"}
 SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 

@@ -962,6 +962,8 @@ static int launch_cost_tma_t(ssm_ctx* c, int B, cudaStream_t s)
     SSM_CUDA(cudaFuncSetAttribute(k_cost_tma<TX, RAD, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (p.W1 + TX - 1) / TX;
     int bands = std::max(1, std::min(p.H / 32, (c->sm_count * 8 + tiles * B - 1) / (tiles * B)));
+    static const int force_bands = [] { const char* e = getenv("SSM_COST_BANDS"); return e ? atoi(e) : 0; }();
+    if (force_bands > 0) bands = std::min(force_bands, std::max(1, p.H / 16));
     const int band_rows = (p.H + bands - 1) / bands;
     bands = (p.H + band_rows - 1) / band_rows;
     dim3 grid(tiles, bands, B);
