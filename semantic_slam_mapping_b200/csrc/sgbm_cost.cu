@@ -686,7 +686,8 @@ struct CostGeom2 : CostGeom<TX> {
     }
 };
 
-template <int TX, int RAD, bool PAD>
+template <int TX, int RAD, bool PAD, int NKK = CostGeom<TX>::WPL /* 16-word groups of a pixel that phase 1 computes: the groups above hold
+          only cells at d >= Dv of a padded layout (written as `padw`, never read from the tile) */>
 __global__ void __launch_bounds__(256, 2) k_cost_tma(const uint2* __restrict__ recL, const uint32_t* __restrict__ ptab,
                                                      int16_t* __restrict__ C, int W, int H, int Dv, int band_rows, int pitch, int margin,
                                                      uint32_t mone, uint32_t padw)
@@ -828,31 +829,32 @@ __global__ void __launch_bounds__(256, 2) k_cost_tma(const uint2* __restrict__ r
                 const int sg = threadIdx.x >> 4, jl = threadIdx.x & 15;
                 const int el0 = (sg >> 1) * 2 * SL + (sg & 1);
                 const bool work = el0 < n_e;
-                uint32_t loG[WPL], hiG[WPL], vG[WPL], loR[WPL], hiR[WPL], vR[WPL];
+                uint32_t loG[NKK], hiG[NKK], vG[NKK], loR[NKK], hiR[NKK], vR[NKK];
                 if (work) {
                     const uint32_t* q = P + el0 - 2 * jl;
 #pragma unroll
-                    for (int kk = 0; kk < WPL; ++kk) {
+                    for (int kk = 0; kk < NKK; ++kk) {
                         loG[kk] = q[0 * PTW - 2 * kk * LPP]; hiG[kk] = q[1 * PTW - 2 * kk * LPP]; vG[kk] = q[2 * PTW - 2 * kk * LPP];
                         loR[kk] = q[3 * PTW - 2 * kk * LPP]; hiR[kk] = q[4 * PTW - 2 * kk * LPP]; vR[kk] = q[5 * PTW - 2 * kk * LPP];
                     }
-                }
-                if (work) {
 #pragma unroll
                     for (int t = 0; t < SL; ++t) {
                         const int el = el0 + 2 * t;
                         if (el < n_e) {
                             if (t > 0 && jl + t == LPP) {
                                 const uint32_t* q2 = P + el;         // word 0 of pixel el
-                                loG[WPL - 1] = q2[0]; hiG[WPL - 1] = q2[PTW]; vG[WPL - 1] = q2[2 * PTW];
-                                loR[WPL - 1] = q2[3 * PTW]; hiR[WPL - 1] = q2[4 * PTW]; vR[WPL - 1] = q2[5 * PTW];
+                                loG[NKK - 1] = q2[0]; hiG[NKK - 1] = q2[PTW]; vG[NKK - 1] = q2[2 * PTW];
+                                loR[NKK - 1] = q2[3 * PTW]; hiR[NKK - 1] = q2[4 * PTW]; vR[NKK - 1] = q2[5 * PTW];
                             }
                             const uint4 la = reinterpret_cast<const uint4*>(L + el * 8)[0];
                             const uint4 lb = reinterpret_cast<const uint4*>(L + el * 8)[1];
                             uint32_t* out = pix + el * PS;
 #pragma unroll
-                            for (int kk = 0; kk < WPL; ++kk)
-                                out[(kk * LPP + jl + t) & (WPP - 1)] = bt_word(la, lb, loG[kk], hiG[kk], vG[kk], loR[kk], hiR[kk], vR[kk]);
+                            for (int kk = 0; kk < NKK; ++kk) {
+                                // the ring of NKK * LPP words: the top group's lanes that run off it re-enter at the bottom
+                                const int wi = (kk == NKK - 1 && jl + t >= LPP) ? jl + t - LPP : kk * LPP + jl + t;
+                                out[wi] = bt_word(la, lb, loG[kk], hiG[kk], vG[kk], loR[kk], hiR[kk], vR[kk]);
+                            }
                         }
                     }
                 }
@@ -954,12 +956,12 @@ static int launch_cost_fused_t(ssm_ctx* c, int B, cudaStream_t s)
     return SSM_OK;
 }
 
-template <int TX, int RAD, bool PAD>
+template <int TX, int RAD, bool PAD, int NKK = CostGeom<TX>::WPL>
 static int launch_cost_tma_t(ssm_ctx* c, int B, cudaStream_t s)
 {
     const DevParams& p = c->dp;
     const size_t smem = CostGeom2<TX>::smem_bytes(p.bs);
-    SSM_CUDA(cudaFuncSetAttribute(k_cost_tma<TX, RAD, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSM_CUDA(cudaFuncSetAttribute(k_cost_tma<TX, RAD, PAD, NKK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (p.W1 + TX - 1) / TX;
     int bands = std::max(1, std::min(p.H / 32, (c->sm_count * 8 + tiles * B - 1) / (tiles * B)));
     static const int force_bands = [] { const char* e = getenv("SSM_COST_BANDS"); return e ? atoi(e) : 0; }();
@@ -967,7 +969,7 @@ static int launch_cost_tma_t(ssm_ctx* c, int B, cudaStream_t s)
     const int band_rows = (p.H + bands - 1) / bands;
     bands = (p.H + band_rows - 1) / band_rows;
     dim3 grid(tiles, bands, B);
-    k_cost_tma<TX, RAD, PAD><<<grid, 256, smem, s>>>(reinterpret_cast<const uint2*>(c->d_recL), c->d_ptab, c->d_C, p.W, p.H, p.D, band_rows,
+    k_cost_tma<TX, RAD, PAD, NKK><<<grid, 256, smem, s>>>(reinterpret_cast<const uint2*>(c->d_recL), c->d_ptab, c->d_C, p.W, p.H, p.D, band_rows,
                                                      c->ptab_pitch, c->ptab_margin, 0xffffffffu, (kBig - (uint32_t)p.P2) * 0x10001u);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
@@ -976,7 +978,11 @@ static int launch_cost_tma_t(ssm_ctx* c, int B, cudaStream_t s)
 int launch_cost_volume(ssm_ctx* c, int B, cudaStream_t s)
 {
     const DevParams& p = c->dp;
-    if (use_cost_tma(c)) return p.Dl != p.D ? launch_cost_tma_t<32, 5, true>(c, B, s) : launch_cost_tma_t<32, 5, false>(c, B, s);
+    if (use_cost_tma(c)) {
+        if (p.Dl == p.D) return launch_cost_tma_t<32, 5, false>(c, B, s);
+        // padded layouts: 80 and 96 disparities (the reference's default is 80) fill three of the four 16-word groups of a pixel
+        return p.D <= 96 ? launch_cost_tma_t<32, 5, true, 3>(c, B, s) : launch_cost_tma_t<32, 5, true>(c, B, s);
+    }
     if (use_fused_cost(c)) {
         // TX * D/2 = 2048 words per CTA row
         const bool r5 = p.bs == 11;   // the reference's block size gets the compile-time window; others the generic one

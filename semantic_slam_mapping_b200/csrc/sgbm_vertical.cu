@@ -75,7 +75,7 @@ __device__ __forceinline__ void st_async_word(uint32_t remote_addr, uint32_t v, 
 }
 
 template <int NR, int NWARPS, bool FULL /* D == 2 * NR * LANES: every lane owns disparities */, int LANES = 32 /* lanes per column */>
-__global__ void __launch_bounds__(NWARPS * 32, 1) k_vertical3(const int16_t* __restrict__ C, uint16_t* __restrict__ S, int W1, int H,
+__global__ void __launch_bounds__(NWARPS * 32, NWARPS <= 8 ? 2 : 1) k_vertical3(const int16_t* __restrict__ C, uint16_t* __restrict__ S, int W1, int H,
                                                              int D /* disparities per column in the layout */, int P1, int P2, int T,
                                                              uint32_t one, int pf_rows, int Dv /* valid disparities <= D */)
 {
@@ -299,7 +299,10 @@ static int launch_vertical_t(ssm_ctx* c, int B, const VerticalPlan& plan, cudaSt
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
+    const cudaError_t occ = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+    static const bool dbg = getenv("SSM_DEBUG_CLUSTERS") != nullptr;
+    if (dbg) fprintf(stderr, "k_vertical3<%d,%d>: cluster %d, T %d, smem %zu, max active clusters %d (%s)\n", NR, NWARPS, plan.cluster, plan.T, plan.smem, nclusters, cudaGetErrorString(occ));
+    if (occ != cudaSuccess || nclusters < 1) {
         cudaGetLastError();      // this cluster shape cannot be co-scheduled on this device: fall back
         return SSM_OK;
     }
@@ -362,6 +365,7 @@ static int launch_vertical_plan(ssm_ctx* c, int B, const VerticalPlan& plan, cud
         }
         if (D == 128 && full && c->tune[2] == 2) return launch_vertical_t<4, 24, true, 16>(c, B, plan, s, done);
         if (D == 128 && full && c->tune[2] == 4) return launch_vertical_t<4, 18, true, 16>(c, B, plan, s, done);
+        if (D == 128 && full && c->tune[2] == 6) return launch_vertical_t<4, 8, true, 16>(c, B, plan, s, done);   // two CTAs per SM (8-CTA clusters)
         if (D == 128 && full && c->tune[2] == 5) return launch_vertical_t<4, 20, true, 16>(c, B, plan, s, done);
         if (full && c->tune[2] == 1) return launch_vertical_t<2, 24, true>(c, B, plan, s, done);
         return full ? launch_vertical_t<2, 32, true>(c, B, plan, s, done) : launch_vertical_t<2, 32, false>(c, B, plan, s, done);
