@@ -527,7 +527,7 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
         for (auto& ev : set) A(cudaEventCreate(&ev));
     A(dalloc(&c->d_left, npix)); A(dalloc(&c->d_right, npix));
     A(dalloc(&c->d_recL, npix)); A(dalloc(&c->d_recR, npix));
-    if (layout_disparities(c, p->num_disparities) == 128) {   // right image in table format for k_cost_tma (sgbm_cost.cu)
+    if (layout_disparities(c, p->num_disparities) == 128 || layout_disparities(c, p->num_disparities) == 256) {   // right image in table format for k_cost_tma (sgbm_cost.cu)
         const int ld = layout_disparities(c, p->num_disparities);
         const size_t margin = ld != p->num_disparities ? (size_t)(ld - p->num_disparities + 4 + 3) / 4 * 4 : 0;
         A(dalloc(&c->d_ptab, (margin + (size_t)(c->cap_w + 3) / 4 * 4 + 4) * 6 * c->cap_h * c->cap_b));

@@ -690,7 +690,8 @@ template <int TX, int RAD, bool PAD, int NKK = CostGeom<TX>::WPL /* 16-word grou
           only cells at d >= Dv of a padded layout (written as `padw`, never read from the tile) */>
 __global__ void __launch_bounds__(256, 2) k_cost_tma(const uint2* __restrict__ recL, const uint32_t* __restrict__ ptab,
                                                      int16_t* __restrict__ C, int W, int H, int Dv, int band_rows, int pitch, int margin,
-                                                     uint32_t mone, uint32_t padw)
+                                                     uint32_t mone, uint32_t padw, int nsplit /* the layout has nsplit * D disparities per column:
+                                                     blockIdx.x = tile * nsplit + part, part = which D of them this CTA computes */)
 {
     using G = CostGeom2<TX>;
     constexpr int D = G::D, WPP = G::WPP, PS = G::PS, LPP = G::LPP, WPL = G::WPL, PTW = G::PTW, NG = G::NG, SL = G::SL;
@@ -698,12 +699,13 @@ __global__ void __launch_bounds__(256, 2) k_cost_tma(const uint2* __restrict__ r
     static_assert(G::DIAG && RAD >= 0, "diagonal-sweep shapes with a compile-time window only");
     extern __shared__ __align__(16) uint32_t smem[];
     const int W1 = W - Dv;
-    const int t0 = blockIdx.x * TX, b = blockIdx.z;
+    const int part = (int)(blockIdx.x % (unsigned)nsplit), dbase = part * D;   // this CTA's disparities: dbase .. dbase + D - 1
+    const int t0 = (int)(blockIdx.x / (unsigned)nsplit) * TX, b = blockIdx.z;
     const int y0 = blockIdx.y * band_rows, y1 = min(H, y0 + band_rows);
     const int e_lo = max(t0 - radius, 0), e_hi = min(t0 + TX - 1 + radius, W1 - 1);
     const int n_e = e_hi - e_lo + 1;
-    const int xs = (e_lo + Dv - (D - 2)) & ~3;       // image pixel of table word 0 (may be negative: the zero margin)
-    const int xoff = e_lo + Dv - xs;                 // table index of (pixel e_lo, word 0); index(el, w) = xoff + el - 2w
+    const int xs = (e_lo + Dv - dbase - (D - 2)) & ~3;   // image pixel of table word 0 (may be negative: the zero margin)
+    const int xoff = e_lo + Dv - dbase - xs;         // table index of (pixel e_lo, word 0); index(el, w) = xoff + el - 2w
     const uint32_t copy_bytes = (uint32_t)((xoff + n_e + 3) & ~3) * 4u;
     uint32_t one = 0u - mone;
     asm volatile("" : "+r"(one));
@@ -770,12 +772,13 @@ __global__ void __launch_bounds__(256, 2) k_cost_tma(const uint2* __restrict__ r
     const int c0 = t0 + cgp * 8;
     const bool interior = c0 - RAD >= 0 && c0 + 7 + RAD <= W1 - 1;
     const int nvalid = min(8, W1 - c0);              // <= 0: this thread has no columns
-    const bool padded_word = PAD && 2 * w2 >= Dv;
+    const bool padded_word = PAD && dbase + 2 * w2 >= Dv;
     uint32_t crun[8], hs[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { crun[i] = 0u; hs[i] = 0u; }
-    uint32_t* dst = reinterpret_cast<uint32_t*>(C) + (((size_t)b * H + y0) * W1 + c0) * WPP + w2;
-    const size_t rowstep = (size_t)W1 * WPP;
+    const int colw = WPP * nsplit;                   // words per column of the layout
+    uint32_t* dst = reinterpret_cast<uint32_t*>(C) + (((size_t)b * H + y0) * W1 + c0) * colw + part * WPP + w2;
+    const size_t rowstep = (size_t)W1 * colw;
     uint4* const ring_t = reinterpret_cast<uint4*>(ring) + (size_t)cgp * 2 * WPP + w2;   // this thread's cell of slot 0
     __syncthreads();                                 // ring zeroed, Lt[0] built, mbarriers initialised
 
@@ -800,11 +803,11 @@ __global__ void __launch_bounds__(256, 2) k_cost_tma(const uint2* __restrict__ r
             if (jj - radius >= y0) {
                 if (nvalid == 8) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) dst[c * WPP] = padded_word ? padw : crun[c];
+                    for (int c = 0; c < 8; ++c) dst[c * colw] = padded_word ? padw : crun[c];
                 } else {
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
-                        if (c < nvalid) dst[c * WPP] = padded_word ? padw : crun[c];
+                        if (c < nvalid) dst[c * colw] = padded_word ? padw : crun[c];
                 }
                 dst += rowstep;
             }
@@ -901,10 +904,10 @@ static bool use_fused_cost(const ssm_ctx* c)
     return !c->force_legacy_cost && (D == 16 || D == 32 || D == 64 || D == 128 || D == 256 || D == 512);
 }
 
-// k_cost_tma: 128-disparity layouts (D = 128, or 80 / 96 / 112 padded), the reference's block size
+// k_cost_tma: 128- and 256-disparity layouts (D = 128 / 256, or 80 ... 112 / 144 ... 240 padded), the reference's block size
 static bool use_cost_tma(const ssm_ctx* c)
 {
-    return use_fused_cost(c) && !c->no_cost_tma && c->d_ptab && c->dp.Dl == 128 && c->dp.bs == 11;
+    return use_fused_cost(c) && !c->no_cost_tma && c->d_ptab && (c->dp.Dl == 128 || c->dp.Dl == 256) && c->dp.bs == 11;
 }
 
 int launch_prefilter(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, cudaStream_t s)
@@ -962,7 +965,8 @@ static int launch_cost_tma_t(ssm_ctx* c, int B, cudaStream_t s)
     const DevParams& p = c->dp;
     const size_t smem = CostGeom2<TX>::smem_bytes(p.bs);
     SSM_CUDA(cudaFuncSetAttribute(k_cost_tma<TX, RAD, PAD, NKK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tiles = (p.W1 + TX - 1) / TX;
+    const int nsplit = p.Dl / CostGeom<TX>::D;     // 256-disparity layouts: two CTAs per tile, 128 disparities each (halo 1.31 x instead of the 1.62 x of a 16-column tile)
+    const int tiles = (p.W1 + TX - 1) / TX * nsplit;
     int bands = std::max(1, std::min(p.H / 32, (c->sm_count * 8 + tiles * B - 1) / (tiles * B)));
     static const int force_bands = [] { const char* e = getenv("SSM_COST_BANDS"); return e ? atoi(e) : 0; }();
     if (force_bands > 0) bands = std::min(force_bands, std::max(1, p.H / 16));
@@ -970,7 +974,7 @@ static int launch_cost_tma_t(ssm_ctx* c, int B, cudaStream_t s)
     bands = (p.H + band_rows - 1) / band_rows;
     dim3 grid(tiles, bands, B);
     k_cost_tma<TX, RAD, PAD, NKK><<<grid, 256, smem, s>>>(reinterpret_cast<const uint2*>(c->d_recL), c->d_ptab, c->d_C, p.W, p.H, p.D, band_rows,
-                                                     c->ptab_pitch, c->ptab_margin, 0xffffffffu, (kBig - (uint32_t)p.P2) * 0x10001u);
+                                                     c->ptab_pitch, c->ptab_margin, 0xffffffffu, (kBig - (uint32_t)p.P2) * 0x10001u, nsplit);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }
@@ -981,7 +985,7 @@ int launch_cost_volume(ssm_ctx* c, int B, cudaStream_t s)
     if (use_cost_tma(c)) {
         if (p.Dl == p.D) return launch_cost_tma_t<32, 5, false>(c, B, s);
         // padded layouts: 80 and 96 disparities (the reference's default is 80) fill three of the four 16-word groups of a pixel
-        return p.D <= 96 ? launch_cost_tma_t<32, 5, true, 3>(c, B, s) : launch_cost_tma_t<32, 5, true>(c, B, s);
+        return (p.Dl == 128 && p.D <= 96) ? launch_cost_tma_t<32, 5, true, 3>(c, B, s) : launch_cost_tma_t<32, 5, true>(c, B, s);
     }
     if (use_fused_cost(c)) {
         // TX * D/2 = 2048 words per CTA row
