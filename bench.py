@@ -51,7 +51,7 @@ CONFIGS = {
     2: dict(W=1241, H=376, D=128, labels=12, leaf=0.05, batch=66, seq_frames=4541, scaling="strong", capacity=1 << 29, steps=None,
             workload="configs[2]: 4541-frame KITTI-00-length synthetic sequence, batched frames sharded across the GPUs, spatially owned voxel "
                      "hash, 1241x376, 128 disparities, 12 classes, 0.05 m voxels (100 distinct stereo pairs, 4541 distinct poses, map never cleared)"),
-    3: dict(W=2048, H=1024, D=256, labels=19, leaf=0.05, batch=8, seq_frames=100, scaling="weak", capacity=1 << 26, steps=20, distinct=24,
+    3: dict(W=2048, H=1024, D=256, labels=19, leaf=0.05, batch=14, seq_frames=100, scaling="weak", capacity=1 << 26, steps=20, distinct=24,
             workload="configs[3]: Cityscapes-shaped 2048x1024 stereo, 256 disparities, 19-class labels, 0.05 m voxels"),
     4: dict(W=1241, H=376, D=128, labels=12, leaf=0.02, batch=66, seq_frames=2500, scaling="weak", capacity=1 << 29, steps=None,
             workload="configs[4]: large-map stress, 0.02 m voxels, 2500 frames per GPU (20 000 over 8 GPUs), label-histogram fusion with all "
@@ -625,7 +625,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4], help="BASELINE.json configs[k]")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="frames per step per GPU (default 66 = two sub-batches of 33, each one full wave of 4-CTA clusters on 132 SMs; 8 for config 3)")
+    ap.add_argument("--batch", type=int, default=0, help="frames per step per GPU (default 66 = two sub-batches of 33, each one full wave of 4-CTA clusters on 132 SMs; 14 = two waves of seven 16-CTA clusters for config 3)")
     ap.add_argument("--no-route-overlap", action="store_true", help="N > 1: keep the point exchange on the pipeline stream")
     ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic frames generated on the host per GPU (default 100; 24 for config 3)")
     ap.add_argument("--map-capacity", type=int, default=0, help="initial voxel hash slots (the table doubles when half full)")

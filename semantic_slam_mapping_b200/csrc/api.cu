@@ -286,7 +286,9 @@ static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR,
     if ((rc = maybe_grow(c, s))) return rc;
     // sub-batches of at least ~one full wave of the vertical cluster kernel each (33 KITTI frames on a B200): kernels of
     // different sub-batches are bound by different units (shared memory, issue slots, HBM) and fill each other's tails
-    const int want = c->tune[3] >= 0 ? c->tune[3] : (B >= 96 ? 3 : (B >= 64 ? 2 : 1));
+    // (the wave of the vertical cluster kernel sets the sub-batch size: 33 KITTI frames at 128 disparities, 7 Cityscapes-sized ones at 256)
+    const int wave = vertical_wave_frames(c);
+    const int want = c->tune[3] >= 0 ? c->tune[3] : (wave > 0 && B >= 2 * wave - wave / 8 ? std::min((B + wave - 1) / wave, (int)ssm_ctx::kMaxSplit) : 1);
     const int nsplit = std::min({want, (int)ssm_ctx::kMaxSplit, B});
     if (nsplit <= 1 || c->timing) {
         if (c->route_pending) {   // an overlapped exchange is still in flight: order this call after it

@@ -302,6 +302,12 @@ static int launch_vertical_t(ssm_ctx* c, int B, const VerticalPlan& plan, cudaSt
     const cudaError_t occ = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
     static const bool dbg = getenv("SSM_DEBUG_CLUSTERS") != nullptr;
     if (dbg) fprintf(stderr, "k_vertical3<%d,%d>: cluster %d, T %d, smem %zu, max active clusters %d (%s)\n", NR, NWARPS, plan.cluster, plan.T, plan.smem, nclusters, cudaGetErrorString(occ));
+    if (c->vert_query) {             // vertical_wave_frames(): the answer is the occupancy, nothing is launched
+        c->vert_wave = occ == cudaSuccess ? nclusters : 0;
+        if (occ != cudaSuccess) cudaGetLastError();
+        *done = true;
+        return SSM_OK;
+    }
     if (occ != cudaSuccess || nclusters < 1) {
         cudaGetLastError();      // this cluster shape cannot be co-scheduled on this device: fall back
         return SSM_OK;
@@ -385,6 +391,24 @@ int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done)
     // the latency-oriented cluster shape cannot be co-scheduled here: the smallest shape that fits shared memory
     if (plan_vertical(c, 1 << 20, smallest) && smallest.cluster != plan.cluster) return launch_vertical_plan(c, B, smallest, s, done);
     return SSM_OK;
+}
+
+// One wave of the cluster kernel = as many frames as clusters are co-resident (33 four-CTA clusters at KITTI size with 128
+// disparities, 7 sixteen-CTA clusters at 2048 x 1024 with 256): the kernel's duration is rows x trips per row whatever the number of
+// clusters in flight, so a batch is best cut into sub-batches of whole waves (api.cu: run_pipeline).
+int vertical_wave_frames(ssm_ctx* c)
+{
+    if (c->vert_wave_w == c->dp.W && c->vert_wave_h == c->dp.H) return c->vert_wave;
+    c->vert_wave_w = c->dp.W; c->vert_wave_h = c->dp.H; c->vert_wave = 0;
+    VerticalPlan plan;
+    if (c->force_legacy_vertical || !plan_vertical(c, 1 << 20, plan)) return 0;
+    bool done = false;
+    c->vert_query = true;
+    const uint64_t launches = c->launches;
+    launch_vertical_plan(c, 1 << 20, plan, nullptr, &done);
+    c->vert_query = false;
+    c->launches = launches;
+    return c->vert_wave;
 }
 
 }  // namespace ssm

@@ -142,6 +142,8 @@ struct ssm_ctx {
     double* stage_pose[2] = {};
     uint64_t async_calls = 0;
 
+    int vert_wave = 0, vert_wave_w = 0, vert_wave_h = 0;   // vertical_wave_frames() cache (per frame shape)
+    bool vert_query = false;                              // launch_vertical_t: report the occupancy, do not launch
     int cap_w = 0, cap_h = 0, cap_b = 0;
     // stereo
     uint8_t *d_left = nullptr, *d_right = nullptr;   // [B][H][W] staging for host calls
@@ -243,6 +245,7 @@ int launch_cost_volume(ssm_ctx* c, int B, cudaStream_t s);
 int launch_aggregate_vertical(ssm_ctx* c, int B, cudaStream_t s);     // down, down-right, down-left -> S_v
 int launch_aggregate_horizontal(ssm_ctx* c, int B, cudaStream_t s);   // right, left, winner-take-all records
 int launch_vertical(ssm_ctx* c, int B, cudaStream_t s, bool* done);   // cluster kernel; *done = false -> caller falls back
+int vertical_wave_frames(ssm_ctx* c);   // frames whose vertical clusters are co-resident (one full wave of the cluster kernel); 0 = unknown
 int launch_select(ssm_ctx* c, int B, cudaStream_t s);
 int launch_hsweep(ssm_ctx* c, int B, cudaStream_t s);
 int launch_hsweep2(ssm_ctx* c, int B, cudaStream_t s);       // checkpointed recomputation (D <= 128)
