@@ -687,11 +687,11 @@ struct CostGeom2 : CostGeom<TX> {
 };
 
 template <int TX, int RAD, bool PAD, int NKK = CostGeom<TX>::WPL /* 16-word groups of a pixel that phase 1 computes: the groups above hold
-          only cells at d >= Dv of a padded layout (written as `padw`, never read from the tile) */>
+          only cells at d >= Dv of a padded layout (written as `padw`, never read from the tile) */,
+          int NSPLIT = 1 /* the layout has NSPLIT * D disparities per column: blockIdx.x = tile * NSPLIT + part, part = which D of them this CTA computes */>
 __global__ void __launch_bounds__(256, 2) k_cost_tma(const uint2* __restrict__ recL, const uint32_t* __restrict__ ptab,
                                                      int16_t* __restrict__ C, int W, int H, int Dv, int band_rows, int pitch, int margin,
-                                                     uint32_t mone, uint32_t padw, int nsplit /* the layout has nsplit * D disparities per column:
-                                                     blockIdx.x = tile * nsplit + part, part = which D of them this CTA computes */)
+                                                     uint32_t mone, uint32_t padw)
 {
     using G = CostGeom2<TX>;
     constexpr int D = G::D, WPP = G::WPP, PS = G::PS, LPP = G::LPP, WPL = G::WPL, PTW = G::PTW, NG = G::NG, SL = G::SL;
@@ -699,8 +699,8 @@ __global__ void __launch_bounds__(256, 2) k_cost_tma(const uint2* __restrict__ r
     static_assert(G::DIAG && RAD >= 0, "diagonal-sweep shapes with a compile-time window only");
     extern __shared__ __align__(16) uint32_t smem[];
     const int W1 = W - Dv;
-    const int part = (int)(blockIdx.x % (unsigned)nsplit), dbase = part * D;   // this CTA's disparities: dbase .. dbase + D - 1
-    const int t0 = (int)(blockIdx.x / (unsigned)nsplit) * TX, b = blockIdx.z;
+    const int part = (int)(blockIdx.x % (unsigned)NSPLIT), dbase = part * D;   // this CTA's disparities: dbase .. dbase + D - 1
+    const int t0 = (int)(blockIdx.x / (unsigned)NSPLIT) * TX, b = blockIdx.z;
     const int y0 = blockIdx.y * band_rows, y1 = min(H, y0 + band_rows);
     const int e_lo = max(t0 - radius, 0), e_hi = min(t0 + TX - 1 + radius, W1 - 1);
     const int n_e = e_hi - e_lo + 1;
@@ -776,7 +776,7 @@ __global__ void __launch_bounds__(256, 2) k_cost_tma(const uint2* __restrict__ r
     uint32_t crun[8], hs[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { crun[i] = 0u; hs[i] = 0u; }
-    const int colw = WPP * nsplit;                   // words per column of the layout
+    constexpr int colw = WPP * NSPLIT;               // words per column of the layout
     uint32_t* dst = reinterpret_cast<uint32_t*>(C) + (((size_t)b * H + y0) * W1 + c0) * colw + part * WPP + w2;
     const size_t rowstep = (size_t)W1 * colw;
     uint4* const ring_t = reinterpret_cast<uint4*>(ring) + (size_t)cgp * 2 * WPP + w2;   // this thread's cell of slot 0
@@ -959,22 +959,22 @@ static int launch_cost_fused_t(ssm_ctx* c, int B, cudaStream_t s)
     return SSM_OK;
 }
 
-template <int TX, int RAD, bool PAD, int NKK = CostGeom<TX>::WPL>
+template <int TX, int RAD, bool PAD, int NKK = CostGeom<TX>::WPL, int NSPLIT = 1>
 static int launch_cost_tma_t(ssm_ctx* c, int B, cudaStream_t s)
 {
     const DevParams& p = c->dp;
     const size_t smem = CostGeom2<TX>::smem_bytes(p.bs);
-    SSM_CUDA(cudaFuncSetAttribute(k_cost_tma<TX, RAD, PAD, NKK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int nsplit = p.Dl / CostGeom<TX>::D;     // 256-disparity layouts: two CTAs per tile, 128 disparities each (halo 1.31 x instead of the 1.62 x of a 16-column tile)
-    const int tiles = (p.W1 + TX - 1) / TX * nsplit;
+    SSM_CUDA(cudaFuncSetAttribute(k_cost_tma<TX, RAD, PAD, NKK, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (NSPLIT = 2: 256-disparity layouts, two CTAs per tile with 128 disparities each -- halo 1.31 x instead of the 1.62 x of a 16-column tile)
+    const int tiles = (p.W1 + TX - 1) / TX * NSPLIT;
     int bands = std::max(1, std::min(p.H / 32, (c->sm_count * 8 + tiles * B - 1) / (tiles * B)));
     static const int force_bands = [] { const char* e = getenv("SSM_COST_BANDS"); return e ? atoi(e) : 0; }();
     if (force_bands > 0) bands = std::min(force_bands, std::max(1, p.H / 16));
     const int band_rows = (p.H + bands - 1) / bands;
     bands = (p.H + band_rows - 1) / band_rows;
     dim3 grid(tiles, bands, B);
-    k_cost_tma<TX, RAD, PAD, NKK><<<grid, 256, smem, s>>>(reinterpret_cast<const uint2*>(c->d_recL), c->d_ptab, c->d_C, p.W, p.H, p.D, band_rows,
-                                                     c->ptab_pitch, c->ptab_margin, 0xffffffffu, (kBig - (uint32_t)p.P2) * 0x10001u, nsplit);
+    k_cost_tma<TX, RAD, PAD, NKK, NSPLIT><<<grid, 256, smem, s>>>(reinterpret_cast<const uint2*>(c->d_recL), c->d_ptab, c->d_C, p.W, p.H, p.D, band_rows,
+                                                     c->ptab_pitch, c->ptab_margin, 0xffffffffu, (kBig - (uint32_t)p.P2) * 0x10001u);
     SSM_LAUNCH_CHECK(c);
     return SSM_OK;
 }
@@ -983,9 +983,10 @@ int launch_cost_volume(ssm_ctx* c, int B, cudaStream_t s)
 {
     const DevParams& p = c->dp;
     if (use_cost_tma(c)) {
+        if (p.Dl == 256) return p.Dl == p.D ? launch_cost_tma_t<32, 5, false, 4, 2>(c, B, s) : launch_cost_tma_t<32, 5, true, 4, 2>(c, B, s);
         if (p.Dl == p.D) return launch_cost_tma_t<32, 5, false>(c, B, s);
         // padded layouts: 80 and 96 disparities (the reference's default is 80) fill three of the four 16-word groups of a pixel
-        return (p.Dl == 128 && p.D <= 96) ? launch_cost_tma_t<32, 5, true, 3>(c, B, s) : launch_cost_tma_t<32, 5, true>(c, B, s);
+        return p.D <= 96 ? launch_cost_tma_t<32, 5, true, 3>(c, B, s) : launch_cost_tma_t<32, 5, true>(c, B, s);
     }
     if (use_fused_cost(c)) {
         // TX * D/2 = 2048 words per CTA row
