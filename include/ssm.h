@@ -282,9 +282,11 @@ int ssm_comm_get_unique_id(uint8_t id[SSM_UNIQUE_ID_BYTES]);               /* ra
 int ssm_comm_init(ssm_ctx* ctx, const uint8_t id[SSM_UNIQUE_ID_BYTES], int rank, int nranks);
 /* Peer-memory routing (preferred on one NVLink/NVSwitch box): after ssm_comm_init every rank exports its inbox as a
  * CUDA IPC handle, the host all-gathers the handles ([nranks][SSM_IPC_HANDLE_BYTES]) and every rank connects.  From
- * then on point generation and the dispatch all-to-all are ONE kernel (peer stores over NVLink), followed by a
- * stream-ordered NCCL barrier and the fusion of the rank's inbox; no host synchronisation per batch.  Without this
- * call the NCCL send/recv all-to-all is used. */
+ * then on point generation and the dispatch all-to-all are ONE kernel (one 16-byte peer store over NVLink per routed point),
+ * followed by a stream-ordered step barrier over arrival flags in the peers' inbox headers (no collective, no host
+ * synchronisation per batch) and the fusion of the rank's inbox.  Every rank must make the same sequence of pipeline /
+ * integrate calls; a rank that waits more than ~10 s for a peer's flag gives up and the next blocking map call returns
+ * SSM_ERR_COMM (its map then lacks that step's remote points).  Without this call the NCCL send/recv all-to-all is used. */
 #define SSM_IPC_HANDLE_BYTES 64
 int ssm_comm_ipc_export(ssm_ctx* ctx, uint8_t handle[SSM_IPC_HANDLE_BYTES]);
 int ssm_comm_ipc_connect(ssm_ctx* ctx, const uint8_t* handles, int nranks);

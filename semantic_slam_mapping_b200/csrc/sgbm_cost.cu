@@ -1,12 +1,15 @@
 // sgbm_cost.cu -- matching-cost stage of the SGBM chain, sm_100a.
 //
 // Replaces the calcPixelCostBT + block-sum part of cv::StereoSGBM that /root/reference
-// src/stereo.cpp:13-30 calls.  Three kernels:
+// src/stereo.cpp:13-30 calls.  Three generations, all bit-exact with the oracle and all still covered by parity tests:
+//   r2  k_prefilter_tab + k_cost_tma     128- / 256-disparity layouts at the reference's block size: the right image is written in
+//                                        table format and pulled into shared memory by TMA bulk copies (mbarrier, two rows ahead)
+//   r1  k_prefilter8 + k_cost_fused      every power-of-two layout: one launch, tables built per row inside the kernel
+//   r0  k_prefilter + k_pix_hsum + k_vsum  any multiple of 16 disparities (SSM_LEGACY_COST=1): horizontal sums through HBM
 //   k_prefilter   image -> per-pixel record {v,-v,lo,-hi} for the Sobel-x and the raw channel (A-1, A-2 intervals)
 //   k_pix_hsum    records -> Birchfield-Tomasi pixel cost in packed s16x2 lanes (VIADDMNMX/VIMNMX), staged as a
 //                 shared-memory tile, then the bs-wide horizontal window sum hs[y][x'][d] (A-2, A-3 first half)
 //   k_vsum        bs-tall running window sum down the rows -> C[y][x'][d] int16 (A-3 second half)
-// All arithmetic is integer and bit-exact with the oracle.
 #include <algorithm>
 
 #include "ssm_internal.cuh"
