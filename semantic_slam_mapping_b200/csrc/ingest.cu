@@ -168,7 +168,9 @@ struct InflateJob {
 enum { INF_OK = 0, INF_BAD_HEADER = 1, INF_BAD_BLOCK = 2, INF_BAD_CODES = 3, INF_BAD_SYMBOL = 4, INF_BAD_DISTANCE = 5, INF_TRUNCATED = 6,
        INF_BAD_CHECK = 7, INF_SHORT = 8, INF_BAD_FILTER = 9 };
 
+constexpr int kPB = 12;                          // index bits of the literal-pair table
 struct InflateTabs {
+    uint32_t pair[1 << kPB];                     // bits 0-3 bits consumed, 4-5 literals (0: no literal in front), 8-15 / 16-23 the literals
     uint16_t llut[1 << kLB];                     // (symbol << 4) | length, 0 = not a first-level code
     uint16_t dlut[1 << kDB];
     uint16_t lsym[288], dsym[32];                // symbols in canonical order
@@ -251,6 +253,26 @@ __device__ __noinline__ int build_table(const uint8_t* lens, int n, uint16_t* lu
     return 0;
 }
 
+// The literal-pair table: index = the next kPB bits; an entry resolves one first-level literal, or two when the second literal's code
+// ends inside the kPB bits as well.  Photo-like PNG data is mostly literals with 5 ... 9-bit codes, and every symbol is a chain of
+// dependent steps, so two literals per look-up shorten the chain per byte.  Warp-collective; needs llut.
+__device__ void build_pair_table(InflateTabs& T, int lane)
+{
+    for (int idx = lane; idx < (1 << kPB); idx += 32) {
+        uint32_t e = 0u;
+        const uint32_t e1 = T.llut[idx & ((1 << kLB) - 1)];
+        if (e1 - 1u < 0x0fffu) {
+            const uint32_t l1 = e1 & 15u;
+            e = l1 | (1u << 4) | ((e1 >> 4) << 8);
+            const uint32_t e2 = T.llut[(idx >> l1) & ((1 << kLB) - 1)];
+            // (the bits above kPB - l1 of the second index are zeros, not stream bits: only a code that ends inside the kPB bits counts)
+            if (e2 - 1u < 0x0fffu && l1 + (e2 & 15u) <= (uint32_t)kPB) e = (l1 + (e2 & 15u)) | (2u << 4) | ((e1 >> 4) << 8) | ((e2 >> 4) << 16);
+        }
+        T.pair[idx] = e;
+    }
+    __syncwarp();
+}
+
 // a code longer than the first-level table (or an unused pattern): canonical bit-by-bit decode; -1 = invalid
 __device__ __forceinline__ int decode_slow(BitReader& br, const uint16_t* cnt, const uint16_t* sym)
 {
@@ -329,6 +351,7 @@ __global__ void __launch_bounds__(32 * kInflateWarps) k_inflate(const uint8_t* _
                 for (int s = lane; s < 32; s += 32) T.lens[s] = 5;
                 __syncwarp();
                 build_table(T.lens, 30, T.dlut, kDB, T.dsym, T.dcnt, T.code, lane);
+                build_pair_table(T, lane);
                 tables = 1;
             }
         } else {
@@ -387,38 +410,40 @@ __global__ void __launch_bounds__(32 * kInflateWarps) k_inflate(const uint8_t* _
             __syncwarp();
             if ((err = build_table(T.lens + 288, ndist, T.dlut, kDB, T.dsym, T.dcnt, T.code, lane))) break;
             if ((err = build_table(T.lens, nlen, T.llut, kLB, T.lsym, T.lcnt, T.code, lane))) break;
+            build_pair_table(T, lane);
             tables = 2;
         }
         // ---- symbols of the block.  Literals dominate photo-like PNG data, and every symbol is a chain of dependent steps (table
-        // look-up -> code length -> shift -> next look-up), so the literal path is kept to that chain: up to three first-level
-        // literals (3 x 10 bits) per refill, each one = store, shift, next look-up; everything else takes the general path.
+        // look-up -> code length -> shift -> next look-up), so the literal path is kept to that chain and resolves up to two
+        // literals per link (pair table); everything else takes the general path.
         for (;;) {
             br.refill();
-            uint32_t e = T.llut[(uint32_t)br.buf & ((1u << kLB) - 1u)];
-            // entry = (symbol << 4) | length: a first-level literal is 0 < e < 0x1000.  The look-up behind the current code is
-            // issued before the literal test (it only assumes a first-level code; a wrong guess is simply not used), so the
-            // branch resolves under the shared-memory latency instead of in front of it.
-#define SSM_INFLATE_LITERAL()                                                      \
-            {                                                                              \
-                const unsigned long long nbuf = br.buf >> (e & 15u);                       \
-                const uint32_t e2 = T.llut[(uint32_t)nbuf & ((1u << kLB) - 1u)];           \
-                if (e - 1u < 0x0fffu && pos < cap) {                                       \
-                    if (lane == 0) out[pos] = (uint8_t)(e >> 4);                           \
-                    ++pos;                                                                 \
-                    br.buf = nbuf; br.cnt -= (int)(e & 15u);                               \
-                    e = e2;
-            SSM_INFLATE_LITERAL()
-                    SSM_INFLATE_LITERAL()
-                            SSM_INFLATE_LITERAL()
-                                    continue;        // three literals: refill
-                                }
-                            }
-                        }
-                    }
-                    br.refill();                     // (the low bits, hence e, stay as they are)
+            // literal fast path: two pair-table look-ups (2 x 12 bits) per refill, one or two literals each.  The look-up behind
+            // the current entry is issued before the entry is tested, so the branch resolves under the shared-memory latency.
+            {
+                uint32_t pe = T.pair[(uint32_t)br.buf & ((1u << kPB) - 1u)];
+#define SSM_INFLATE_PAIR(LAST)                                                             \
+                {                                                                                  \
+                    const uint32_t n = (pe >> 4) & 3u;                                              \
+                    const unsigned long long nbuf = br.buf >> (pe & 15u);                          \
+                    const uint32_t pe2 = LAST ? 0u : T.pair[(uint32_t)nbuf & ((1u << kPB) - 1u)];  \
+                    if (n == 0u || pos + n > cap) goto general;                                    \
+                    if (lane == 0) {                                                               \
+                        out[pos] = (uint8_t)(pe >> 8);                                             \
+                        if (n == 2u) out[pos + 1] = (uint8_t)(pe >> 16);                           \
+                    }                                                                              \
+                    pos += n;                                                                      \
+                    br.buf = nbuf; br.cnt -= (int)(pe & 15u);                                      \
+                    pe = pe2;                                                                      \
                 }
+                SSM_INFLATE_PAIR(false)
+                SSM_INFLATE_PAIR(true)
+#undef SSM_INFLATE_PAIR
+                continue;                            // up to four literals: refill
             }
-#undef SSM_INFLATE_LITERAL
+        general:
+            br.refill();                             // (at least 33 bits again; the low bits stay as they are)
+            const uint32_t e = T.llut[(uint32_t)br.buf & ((1u << kLB) - 1u)];
             int s;
             if (e) { br.drop((int)(e & 15u)); s = (int)(e >> 4); }
             else if ((s = decode_slow(br, T.lcnt, T.lsym)) < 0) { err = INF_BAD_SYMBOL; break; }
