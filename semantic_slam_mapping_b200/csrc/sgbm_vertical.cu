@@ -367,6 +367,9 @@ static int launch_vertical_plan(ssm_ctx* c, int B, const VerticalPlan& plan, cud
             // 291 of a 1241-pixel frame at the reference's 80 disparities: nine trips instead of ten)
             if ((plan.T + 33) / 34 < (plan.T + 31) / 32)
                 return full ? launch_vertical_t<4, 17, true, 16>(c, B, plan, s, done) : launch_vertical_t<4, 17, false, 16>(c, B, plan, s, done);
+            // ... and 18 warps (36 columns per trip) when only they do: the 279-column strips of a 1241-pixel frame at 128
+            // disparities take eight trips instead of nine (2.175 -> 2.152 ms per 33 frames; 20 and 24 warps measure slower)
+            if (full && (plan.T + 35) / 36 < (plan.T + 31) / 32) return launch_vertical_t<4, 18, true, 16>(c, B, plan, s, done);
             return full ? launch_vertical_t<4, 16, true, 16>(c, B, plan, s, done) : launch_vertical_t<4, 16, false, 16>(c, B, plan, s, done);
         }
         if (D == 128 && full && c->tune[2] == 2) return launch_vertical_t<4, 24, true, 16>(c, B, plan, s, done);
