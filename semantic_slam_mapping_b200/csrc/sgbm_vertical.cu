@@ -335,9 +335,11 @@ static bool plan_vertical(const ssm_ctx* c, int B, VerticalPlan& plan)
     const int NR = p.Dl <= 64 ? 1 : (p.Dl <= 128 ? 2 : (p.Dl <= 256 ? 4 : 8));
     const size_t limit = 225 * 1024;
     bool found = false;
-    for (int cs : {1, 2, 4, 8, 16}) {
+    // powers of two, plus an explicitly requested size (SSM_MIN_CLUSTER = 3, 5, 6, 7 ...: any strip count works)
+    for (int cs : {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16}) {
         if (cs > c->max_cluster) break;
         if (cs < c->min_cluster) continue;
+        if ((cs & (cs - 1)) != 0 && cs != c->min_cluster) continue;
         const int T = (p.W1 + cs - 1) / cs;
         const size_t need = vertical_smem(NR, T);
         if (need > limit) continue;

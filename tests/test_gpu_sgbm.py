@@ -135,7 +135,7 @@ def test_error_behaviour():
             ctx.sgbm(np.zeros((10, 30), np.uint8), np.zeros((10, 30), np.uint8))    # W <= D
 
 
-@pytest.mark.parametrize("min_cluster", [1, 2, 4, 8])
+@pytest.mark.parametrize("min_cluster", [1, 2, 3, 4, 5, 6, 8])
 @pytest.mark.parametrize("H,W,D,seed", [(40, 101, 32, 31), (33, 21, 16, 32), (50, 333, 128, 33), (24, 270, 256, 34), (30, 200, 80, 35)])
 def test_vertical_cluster_kernel_all_cluster_sizes(monkeypatch, min_cluster, H, W, D, seed):
     """The three top-down paths in one cluster launch: strips of unequal / zero width, 1..8 CTAs per frame."""
