@@ -126,6 +126,8 @@ static void free_all(ssm_ctx* c)
         if (st) cudaStreamDestroy(st);
     for (auto& e : c->sub_join)
         if (e) cudaEventDestroy(e);
+    for (auto& e : c->sub_cost)
+        if (e) cudaEventDestroy(e);
     if (c->sub_fork) cudaEventDestroy(c->sub_fork);
     for (int k = 0; k < 2; ++k) {
         void* st[] = {c->stage_left[k], c->stage_right[k], c->stage_sem[k], c->stage_rgb[k], c->stage_pose[k]};
@@ -153,6 +155,7 @@ static int run_sgbm(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR, int
     mark(c, 0, s);
     if ((rc = launch_prefilter(c, B, dL, dR, s))) return rc;
     if ((rc = launch_cost_volume(c, B, s))) return rc;
+    if (c->ev_after_cost) SSM_CUDA(cudaEventRecord(c->ev_after_cost, s));
     mark(c, 1, s);
     if ((rc = launch_aggregate_vertical(c, B, s))) return rc;
     mark(c, 2, s);
@@ -305,6 +308,7 @@ static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR,
         for (int i = 0; i < ssm_ctx::kMaxSplit; ++i) {
             SSM_CUDA(cudaStreamCreateWithFlags(&c->sub_stream[i], cudaStreamNonBlocking));
             SSM_CUDA(cudaEventCreateWithFlags(&c->sub_join[i], cudaEventDisableTiming));
+            SSM_CUDA(cudaEventCreateWithFlags(&c->sub_cost[i], cudaEventDisableTiming));
         }
     }
     const bool overlap = c->route_overlap && c->nranks > 1;
@@ -329,8 +333,11 @@ static int run_pipeline(ssm_ctx* c, int B, const uint8_t* dL, const uint8_t* dR,
         cudaStream_t ss = c->sub_stream[i];
         SSM_CUDA(cudaStreamWaitEvent(ss, c->sub_fork, 0));
         // no early return between the two offset_buffers calls: the work pointers must always be shifted back
+        if (c->stagger && i > 0) SSM_CUDA(cudaStreamWaitEvent(ss, c->sub_cost[i - 1], 0));
         offset_buffers(c, first);
+        c->ev_after_cost = c->stagger ? c->sub_cost[i] : nullptr;
         rc = run_sgbm(c, n, dL + first * npix, dR + first * npix, d_disp + first * npix, ss);
+        c->ev_after_cost = nullptr;
         if (rc == SSM_OK) {
             // one GPU: the sub-batch fuses its own points; several ranks: routing is one exchange per batch (below)
             if (c->nranks > 1) {
@@ -511,6 +518,8 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
         c->no_cost_tma = nt && nt[0] == '1';
         const char* ng = getenv("SSM_NO_GROW");
         c->auto_grow = !(ng && ng[0] == '1');
+        const char* sg = getenv("SSM_STAGGER");
+        if (sg) c->stagger = atoi(sg);
         const char* m = getenv("SSM_MAX_CLUSTER");
         if (m && atoi(m) > 0) c->max_cluster = atoi(m);
         const char* n = getenv("SSM_MIN_CLUSTER");
