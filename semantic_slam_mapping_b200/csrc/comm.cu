@@ -287,6 +287,10 @@ int ssm_comm_init(ssm_ctx* c, const uint8_t id[SSM_UNIQUE_ID_BYTES], int rank, i
         set_error("bad rank / nranks");
         return SSM_ERR_INVALID_ARGUMENT;
     }
+    if (c->comm) {
+        set_error("this context already has a communicator: call ssm_comm_destroy first");
+        return SSM_ERR_COMM;
+    }
     int rc = load_nccl();
     if (rc) return rc;
     SSM_CUDA(cudaSetDevice(c->device));
@@ -358,6 +362,11 @@ int ssm_comm_destroy(ssm_ctx* c)
     if (c && c->ipc_base) { cudaFree(c->ipc_base); c->ipc_base = nullptr; }
     if (!c || !c->comm) return SSM_OK;
     g_nccl.CommDestroy((ncclComm_t)c->comm);
+    // the routing buffers belong to the communicator (a later ssm_comm_init allocates them for its own rank count)
+    if (c->d_send) { cudaFree(c->d_send); c->d_send = nullptr; }
+    if (c->d_recv) { cudaFree(c->d_recv); c->d_recv = nullptr; }
+    if (c->d_send_counts) { cudaFree(c->d_send_counts); c->d_send_counts = nullptr; }
+    c->route_cap = 0;
     c->comm = nullptr;
     c->rank = 0;
     c->nranks = 1;
