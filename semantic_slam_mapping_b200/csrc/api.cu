@@ -500,7 +500,7 @@ int ssm_create(const ssm_params* p, int device, ssm_ctx** out)
         for (int t = 0; t < 4; ++t) {
             const std::string name = "SSM_TUNE" + std::to_string(t);
             const char* v = getenv(name.c_str());
-            static const int defaults[4] = {2 /* vertical: L2 prefetch distance in rows */, 0 /* hsweep: L2 prefetch off */, 0 /* vertical kernel variant */,
+            static const int defaults[4] = {-1 /* vertical: L2 prefetch distance in rows (automatic: sgbm_vertical.cu) */, 0 /* hsweep: L2 prefetch off */, 0 /* vertical kernel variant */,
                                              -1 /* sub-batch streams: automatic */};
             c->tune[t] = v ? atoi(v) : defaults[t];
         }

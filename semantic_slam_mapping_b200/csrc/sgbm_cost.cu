@@ -970,7 +970,9 @@ static int launch_cost_tma_t(ssm_ctx* c, int B, cudaStream_t s)
     SSM_CUDA(cudaFuncSetAttribute(k_cost_tma<TX, RAD, PAD, NKK, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // (NSPLIT = 2: 256-disparity layouts, two CTAs per tile with 128 disparities each -- halo 1.31 x instead of the 1.62 x of a 16-column tile)
     const int tiles = (p.W1 + TX - 1) / TX * NSPLIT;
-    int bands = std::max(1, std::min(p.H / 32, (c->sm_count * 8 + tiles * B - 1) / (tiles * B)));
+    // bands of rows per tile: every band re-computes 2 * radius rows of pixel costs, so as few as still give every SM four CTAs
+    // (33 KITTI frames: one band, 1155 CTAs, 2.037 ms -- two bands 2.072 ms, three 2.110 ms)
+    int bands = std::max(1, std::min(p.H / 32, (c->sm_count * 4 + tiles * B - 1) / (tiles * B)));
     static const int force_bands = [] { const char* e = getenv("SSM_COST_BANDS"); return e ? atoi(e) : 0; }();
     if (force_bands > 0) bands = std::min(force_bands, std::max(1, p.H / 16));
     const int band_rows = (p.H + bands - 1) / bands;

@@ -312,7 +312,10 @@ static int launch_vertical_t(ssm_ctx* c, int B, const VerticalPlan& plan, cudaSt
         cudaGetLastError();      // this cluster shape cannot be co-scheduled on this device: fall back
         return SSM_OK;
     }
-    SSM_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int16_t*)c->d_C, c->d_S, p.W1, p.H, p.Dl, p.P1, p.P2, plan.T, 1u, c->tune[0], p.D));
+    // L2 prefetch distance of the cost rows (SSM_TUNE0): two rows ahead, one for the two-columns-per-warp kernels of 128-disparity
+    // layouts (measured at KITTI size, 18 warps: 0 / 1 / 2 / 3 / 4 / 6 rows -> 2.39 / 2.12 / 2.15 / 2.28 / 2.41 / 2.47 ms per 33 frames)
+    const int pf_rows = c->tune[0] >= 0 ? c->tune[0] : (NR == 4 && LANES == 16 ? 1 : 2);
+    SSM_CUDA(cudaLaunchKernelEx(&cfg, kern, (const int16_t*)c->d_C, c->d_S, p.W1, p.H, p.Dl, p.P1, p.P2, plan.T, 1u, pf_rows, p.D));
     SSM_LAUNCH_CHECK(c);
     *done = true;
     return SSM_OK;
