@@ -4,7 +4,16 @@
  * Plain-C restatement of the reference hot path.  Each function cites the reference
  * file:line it follows; the SGBM chain follows SURVEY.md Appendix A (the semantics of
  * the un-vendored cv::StereoSGBM that src/stereo.cpp:13-30 calls), and is pinned
- * bit-exactly against cv2 4.13 by tests/test_oracle_vs_cv2.py + tests/golden/.
+ * bit-exactly against cv2 4.13 (tests/test_oracle_golden.py: committed vectors from
+ * tests/golden/make_golden.py, plus live comparisons where cv2 is importable).
+ * The glue (rgbdframe.cpp:85-116, rgbdframe.h:63-75, mapper.cpp:12-94,189-216) and the
+ * motion cues (stereo.cpp:41-192, uvdisparity.cpp:195-366) are pinned to the reference's
+ * own source files compiled untouched into oracle/_ref (tests/test_oracle_mapper_ref.py,
+ * tests/test_oracle_cues.py; vectors in tests/golden/mapper_ref.npz, cues_ref.npz).
+ * PARITY UNPINNED for the PCL 1.7 part only (pcl::VoxelGrid / pcl::transformPointCloud,
+ * SURVEY.md Appendix B): PCL cannot be built or run here, the voxel fusion below restates
+ * its published algorithm; this affects centroid rounding (tolerance 1e-5) and the output
+ * order, not voxel membership, counts or votes.
  *
  * Build: see oracle/Makefile  (-O2 -ffp-contract=off: the fp64 glue must not be fused).
  */
