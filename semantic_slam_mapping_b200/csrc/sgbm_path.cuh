@@ -45,6 +45,33 @@ __device__ __forceinline__ void store_words(void* p, const uint32_t (&w)[NR])
     }
 }
 
+// the same with the evict-first ("streaming") cache hint: data that is read or written exactly once by the kernel and is far too
+// large to be found in L2 by the next kernel either
+template <int NR>
+__device__ __forceinline__ void load_words_cs(const void* p, uint32_t (&w)[NR])
+{
+    if constexpr (NR == 1) asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(w[0]) : "l"(p));
+    else if constexpr (NR == 2) asm volatile("ld.global.cs.v2.u32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p));
+    else {
+#pragma unroll
+        for (int q = 0; q < NR / 4; ++q)
+            asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * q]), "=r"(w[4 * q + 1]), "=r"(w[4 * q + 2]), "=r"(w[4 * q + 3])
+                         : "l"(static_cast<const char*>(p) + 16 * q));
+    }
+}
+template <int NR>
+__device__ __forceinline__ void store_words_cs(void* p, const uint32_t (&w)[NR])
+{
+    if constexpr (NR == 1) asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(w[0]) : "memory");
+    else if constexpr (NR == 2) asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(w[0]), "r"(w[1]) : "memory");
+    else {
+#pragma unroll
+        for (int q = 0; q < NR / 4; ++q)
+            asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(static_cast<char*>(p) + 16 * q), "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]),
+                         "r"(w[4 * q + 3]) : "memory");
+    }
+}
+
 // shared-memory accesses through 32-bit shared-window addresses (no generic-to-shared conversion per access)
 template <int NR>
 __device__ __forceinline__ void lds_words(uint32_t addr, uint32_t (&w)[NR])

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(NWARPS * 32, NWARPS <= 8 ? 2 : 1) k_vertical3(
     uint32_t Cw[NR], Cn[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) { Cw[r] = padC; Cn[r] = padC; }
-    if (active && nk > 0) load_words<NR>(Crow + (size_t)warp * D * 2, Cw);
+    if (active && nk > 0) load_words_cs<NR>(Crow + (size_t)warp * D * 2, Cw);
 
     // ring phases: my column c lives in slot (c + o1) mod R of ring 1 and (c + o2) mod R of ring 2
     int o1 = 0, o2 = 0;
@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(NWARPS * 32, NWARPS <= 8 ? 2 : 1) k_vertical3(
             const bool mine = VPW == 1 || k < nk;    // the last trip of a warp may cover only its first column(s)
             // prefetch the cost of my next column (next row's first one at the end of the row)
             if (active) {
-                if (k + 1 < nk) load_words<NR>(Crow + off + cstep, Cn);
-                else if (k + 1 == nk && y + 1 < H) load_words<NR>(Crow + rowbytes + (size_t)warp * D * 2, Cn);
+                if (k + 1 < nk) load_words_cs<NR>(Crow + off + cstep, Cn);
+                else if (k + 1 == nk && y + 1 < H) load_words_cs<NR>(Crow + rowbytes + (size_t)warp * D * 2, Cn);
             }
             const uint32_t p0 = a0 + c * LWB, p1 = a1 + s1 * LWB, p2 = a2 + s2 * LWB;
             const uint32_t q0 = am0 + c * 4, q1 = am1 + s1 * 4, q2 = am2 + s2 * 4;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(NWARPS * 32, NWARPS <= 8 ? 2 : 1) k_vertical3(
                 uint32_t o[NR];
 #pragma unroll
                 for (int r = 0; r < NR; ++r) o[r] = __viaddmin_u16x2(__viaddmin_u16x2(L0[r], L1[r], kSatW), L2[r], kSatW);
-                store_words<NR>(Srow + off, o);
+                store_words_cs<NR>(Srow + off, o);
             }
 #pragma unroll
             for (int r = 0; r < NR; ++r) Cw[r] = Cn[r];
